@@ -1,0 +1,143 @@
+/* physicsml_b200 — C ABI of the B200-native MACE / NequIP message-passing hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + the caller's CUDA stream, enqueues its
+ * work on that stream without synchronising or allocating, returns 0 on success and a negative code otherwise and
+ * never throws.  The CALLER owns every buffer (the PyTorch host side allocates through torch's caching allocator so
+ * CUDA-graph capture works); the library owns nothing but its code.  All floating-point data is fp32, row-major.
+ *
+ * Each function names the reference (Exscientia/physicsml, paths relative to src/physicsml/) operation it replaces;
+ * INTEGRATION.md shows the ctypes / torch.library binding a maintainer adds on the reference side.
+ *
+ * "spec id" arguments select a build-time generated specialisation (physicsml_b200/csrc/gen/registry.json maps an
+ * irreps signature to its id; physicsml_b200/codegen.py documents the signature strings).
+ */
+#ifndef PHYSICSML_B200_H
+#define PHYSICSML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pml_stream_t; /* == cudaStream_t */
+
+#define PML_OK 0
+#define PML_ERR_BAD_ARG (-1)
+#define PML_ERR_UNSUPPORTED (-2)
+#define PML_ERR_LAUNCH (-3)
+
+int pml_abi_version(void);
+int pml_num_tp_specs(void);
+int pml_num_sym_specs(void);
+
+/* ---- K2: edge featurisation ------------------------------------------------------------------------------------
+ * Replaces compute_lengths_and_vectors (models/utils.py:71-95) + o3.SphericalHarmonics (models/mace/modules/mace.py:50-54,149;
+ * models/nequip/modules/nequip.py:41-45,122) + RadialEmbeddingBlock (models/mace/modules/blocks.py:31-51, radial.py:6-49;
+ * models/nequip/modules/radial.py:4-76).
+ * pos [N,3]; snd/rcv [E] int32 (edge_index[0] / edge_index[1]); shift [E,3] or NULL; cell [3,3] or NULL;
+ * bessel_w [nb].  B_n = prefactor * sin(bessel_w[n]*w_scale*d)/d * f_cut(d).  Y [E,(lmax+1)^2], B [E,nb], len [E] or NULL. */
+int pml_edge_featurise_fwd(const float* pos, const int* snd, const int* rcv, const float* shift, const float* cell,
+                           const float* bessel_w, float r_max, float prefactor, float w_scale, int p, int nb, int lmax,
+                           float* Y, float* B, float* len, int E, pml_stream_t stream);
+/* gpos [N,3] += J^T (gY, gB)  (caller zero-initialises gpos; gY / gB may be NULL) */
+int pml_edge_featurise_bwd(const float* pos, const int* snd, const int* rcv, const float* shift, const float* cell,
+                           const float* bessel_w, float r_max, float prefactor, float w_scale, int p, int nb, int lmax,
+                           const float* gY, const float* gB, float* gpos, int E, pml_stream_t stream);
+/* (tY, tB) = J t for a displacement field t [N,3]  (double backward of the force loss; lightning/module.py:28-48) */
+int pml_edge_featurise_jvp(const float* pos, const int* snd, const int* rcv, const float* shift, const float* cell,
+                           const float* bessel_w, float r_max, float prefactor, float w_scale, int p, int nb, int lmax,
+                           const float* t, float* tY, float* tB, int E, pml_stream_t stream);
+
+/* ---- K4: fused channelwise tensor product + gather + segmented scatter-sum ----------------------------------------
+ * Replaces w_h[sender] -> conv_tp -> scatter (models/mace/modules/blocks.py:214-226; models/nequip/modules/interaction_block.py:95-96).
+ * h [N_src, C*DIN] (irreps layout), Y [E,NSH], R [E,NP*C], gather [E] int32, rowptr [N+1] int32 (CSR over the scatter
+ * index), perm [E] int32 edge ids grouped by scatter index or NULL when edges are already grouped. out [N, C*DOUT]. */
+int pml_tp_fwd(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
+               const int* perm, float* out, int N, int C, pml_stream_t stream);
+/* Cotangents; any of dh [N_src,C*DIN] (zero-initialised by the caller, accumulated with fp32 atomics), dY [E,NSH]
+ * (zero-initialised when C > 32), dR [E,NP*C] may be NULL to skip it. g [N, C*DOUT]. */
+int pml_tp_bwd(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
+               const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, pml_stream_t stream);
+
+/* ---- K6: symmetric contraction ------------------------------------------------------------------------------------
+ * Replaces SymmetricContraction.forward (models/mace/modules/symmetric_contraction.py:75-77,218-239).
+ * x [N,C,S]; attrs [N,Z] (one-hot rows take the fast path); out [N, C*DOUT] (hidden irreps layout). */
+#define PML_SYM_MAX_OUT 3
+#define PML_SYM_MAX_NU 3
+typedef struct {
+  const float* w[PML_SYM_MAX_OUT][PML_SYM_MAX_NU]; /* w[a][nu-1]: [Z, K[a][nu-1], C] */
+  float* gw[PML_SYM_MAX_OUT][PML_SYM_MAX_NU];      /* gradient accumulators (zero-initialised) or NULL */
+  int K[PML_SYM_MAX_OUT][PML_SYM_MAX_NU];
+} pml_sym_weights;
+int pml_sym_fwd(int spec, const float* x, const float* attrs, const pml_sym_weights* W, float* out, int N, int C, int Z,
+                pml_stream_t stream);
+int pml_sym_bwd(int spec, const float* x, const float* attrs, const pml_sym_weights* W, const float* g, float* dx, int N,
+                int C, int Z, pml_stream_t stream);
+/* directional second order: dg = J v, ddx = (g . H) v, W->gw += d/dW <g, J v> */
+int pml_sym_dbl(int spec, const float* x, const float* v, const float* attrs, const pml_sym_weights* W, const float* g,
+                float* dg, float* ddx, int N, int C, int Z, pml_stream_t stream);
+
+/* ---- K5a / K3: grouped strided fp32 GEMM (o3.Linear, nn.FullyConnectedNet layers, weight gradients) ----------------
+ * Replaces o3.Linear (models/mace/modules/blocks.py:139-144,176-181,65-70; mace.py:57-60; nequip interaction_block.py:22-27,66-71)
+ * and the FullyConnectedNet matmuls (blocks.py:157-160; interaction_block.py:61-64). */
+#define PML_GEMM_MAX_CHUNKS 8
+typedef struct {
+  long long a_off[PML_GEMM_MAX_CHUNKS];
+  long long b_off[PML_GEMM_MAX_CHUNKS];
+  int kc[PML_GEMM_MAX_CHUNKS];       /* < 0: runtime extent */
+  float cscale[PML_GEMM_MAX_CHUNKS]; /* per-chunk scale */
+  int nchunks;
+  long long c_off;
+  long long a_rs, a_cs, a_bs;
+  long long b_rs, b_cs, b_bs;
+  long long c_rs, c_cs, c_bs;
+  int M, N; /* M < 0: runtime extent */
+  int nbatch;
+  float alpha;
+  int accumulate;
+} pml_gemm_problem;
+/* probs: DEVICE pointer to nprobs problems. */
+int pml_gemm_grouped(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
+                     int max_M, int max_N, int max_batch, int splitk, pml_stream_t stream);
+
+/* ---- K5b: element-indexed linear (FullyConnectedTensorProduct with one-hot node attributes) ------------------------
+ * Replaces mix_layer / residual_connection_layer (models/mace/modules/blocks.py:183-188,72-78) and NequIP's
+ * self_connection_layer (models/nequip/modules/interaction_block.py:73-82). */
+#define PML_EL_MAX_PATHS 8
+typedef struct {
+  int npaths;
+  int d[PML_EL_MAX_PATHS];
+  int mul_in[PML_EL_MAX_PATHS];
+  int mul_out[PML_EL_MAX_PATHS];
+  long long w_off[PML_EL_MAX_PATHS];
+  long long x_off[PML_EL_MAX_PATHS];
+  long long o_off[PML_EL_MAX_PATHS];
+  long long o_ws[PML_EL_MAX_PATHS];
+  float alpha[PML_EL_MAX_PATHS];
+  long long x_rs, o_rs;
+} pml_el_plan;
+int pml_element_linear_fwd(const float* x, const float* attrs, const float* W, const pml_el_plan* plan, float* out, int N,
+                           int Z, int accumulate, pml_stream_t stream);
+int pml_element_linear_bwd_x(const float* g, const float* attrs, const float* W, const pml_el_plan* plan, float* dx, int N,
+                             int Z, int accumulate, pml_stream_t stream);
+int pml_element_linear_bwd_w(const float* x, const float* g, const float* attrs, const pml_el_plan* plan, float* dW, int N,
+                             int Z, int accumulate, pml_stream_t stream);
+
+/* ---- small kernels ------------------------------------------------------------------------------------------------ */
+/* kind 0 SiLU / 1 tanh; order 0: y=c f(x); 1: y=g c f'(x); 2: y=g v c f''(x)   (normalize2mom activations) */
+int pml_act(const float* x, const float* g, const float* v, float c, int kind, int order, float* y, long long n,
+            pml_stream_t stream);
+/* per-graph pooled readout (models/mace/modules/mace.py:252-258): out[batch[n],f] += x[n,f]; out zero-initialised */
+int pml_pool_sum(const float* x, const long long* batch, float* out, int N, int F, pml_stream_t stream);
+int pml_pool_gather(const float* g, const long long* batch, float* out, int N, int F, pml_stream_t stream);
+/* CSR row pointer over an int64 index vector (counts: zeroed scratch [N]) */
+int pml_csr_rowptr(const long long* idx, int* counts, int* rowptr, int E, int N, pml_stream_t stream);
+int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int E, pml_stream_t stream);
+/* [N, C*S] irreps layout <-> [N, C, S] (models/mace/modules/irreps_tools.py:47-67) */
+int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse, pml_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYSICSML_B200_H */

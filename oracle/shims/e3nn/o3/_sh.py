@@ -35,7 +35,7 @@ def _raw_sh(lmax: int, x: torch.Tensor, y: torch.Tensor, z: torch.Tensor) -> lis
         return out
     c30 = math.sqrt(30.0) / 6.0
     s5 = math.sqrt(5.0)
-    c6 = math.sqrt(6.0) / 8.0
+    c6 = math.sqrt(6.0) / 4.0
     sh30 = c30 * (sh20 * z + sh24 * x)
     sh31 = s5 * sh20 * y
     sh32 = c6 * (4.0 * y2 - x2z2) * x

@@ -1,0 +1,134 @@
+"""ctypes binding of ``csrc/libphysicsml_b200.so`` (C ABI declared in ``include/physicsml_b200.h``).
+
+There is NO fallback: if the CUDA library has not been built (``python -m physicsml_b200.build`` or
+``__graft_entry__.build()``) any attempt to run an op raises :class:`MissingExtensionError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libphysicsml_b200.so")
+REGISTRY_PATH = os.path.join(HERE, "csrc", "gen", "registry.json")
+
+GEMM_MAX_CHUNKS = 8
+EL_MAX_PATHS = 8
+SYM_MAX_OUT = 3
+SYM_MAX_NU = 3
+
+
+class MissingExtensionError(RuntimeError):
+    pass
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [
+        ("a_off", C.c_longlong * GEMM_MAX_CHUNKS),
+        ("b_off", C.c_longlong * GEMM_MAX_CHUNKS),
+        ("kc", C.c_int * GEMM_MAX_CHUNKS),
+        ("cscale", C.c_float * GEMM_MAX_CHUNKS),
+        ("nchunks", C.c_int),
+        ("c_off", C.c_longlong),
+        ("a_rs", C.c_longlong), ("a_cs", C.c_longlong), ("a_bs", C.c_longlong),
+        ("b_rs", C.c_longlong), ("b_cs", C.c_longlong), ("b_bs", C.c_longlong),
+        ("c_rs", C.c_longlong), ("c_cs", C.c_longlong), ("c_bs", C.c_longlong),
+        ("M", C.c_int), ("N", C.c_int),
+        ("nbatch", C.c_int),
+        ("alpha", C.c_float),
+        ("accumulate", C.c_int),
+    ]
+
+
+class ElPlan(C.Structure):
+    _fields_ = [
+        ("npaths", C.c_int),
+        ("d", C.c_int * EL_MAX_PATHS),
+        ("mul_in", C.c_int * EL_MAX_PATHS),
+        ("mul_out", C.c_int * EL_MAX_PATHS),
+        ("w_off", C.c_longlong * EL_MAX_PATHS),
+        ("x_off", C.c_longlong * EL_MAX_PATHS),
+        ("o_off", C.c_longlong * EL_MAX_PATHS),
+        ("o_ws", C.c_longlong * EL_MAX_PATHS),
+        ("alpha", C.c_float * EL_MAX_PATHS),
+        ("x_rs", C.c_longlong),
+        ("o_rs", C.c_longlong),
+    ]
+
+
+class SymWeights(C.Structure):
+    _fields_ = [
+        ("w", (C.c_void_p * SYM_MAX_NU) * SYM_MAX_OUT),
+        ("gw", (C.c_void_p * SYM_MAX_NU) * SYM_MAX_OUT),
+        ("K", (C.c_int * SYM_MAX_NU) * SYM_MAX_OUT),
+    ]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_LL = C.c_longlong
+
+# name -> argtypes (every function returns int); must list every symbol include/physicsml_b200.h declares
+SIGNATURES = {
+    "pml_abi_version": [],
+    "pml_num_tp_specs": [],
+    "pml_num_sym_specs": [],
+    "pml_edge_featurise_fwd": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P],
+    "pml_edge_featurise_bwd": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P],
+    "pml_edge_featurise_jvp": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P],
+    "pml_tp_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "pml_tp_bwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "pml_sym_fwd": [_I, _P, _P, C.POINTER(SymWeights), _P, _I, _I, _I, _P],
+    "pml_sym_bwd": [_I, _P, _P, C.POINTER(SymWeights), _P, _P, _I, _I, _I, _P],
+    "pml_sym_dbl": [_I, _P, _P, _P, C.POINTER(SymWeights), _P, _P, _P, _I, _I, _I, _P],
+    "pml_gemm_grouped": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pml_element_linear_fwd": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
+    "pml_element_linear_bwd_x": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
+    "pml_element_linear_bwd_w": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
+    "pml_act": [_P, _P, _P, _F, _I, _I, _P, _LL, _P],
+    "pml_pool_sum": [_P, _P, _P, _I, _I, _P],
+    "pml_pool_gather": [_P, _P, _P, _I, _I, _P],
+    "pml_csr_rowptr": [_P, _P, _P, _I, _I, _P],
+    "pml_split_edge_index": [_P, _P, _P, _I, _P],
+    "pml_irreps_to_channel": [_P, _P, _LL, _I, _I, _I, _P],
+}
+
+_lib = None
+_registry = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MissingExtensionError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (python -m physicsml_b200.build). "
+                "physicsml_b200 has no CPU or PyTorch fallback."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = handle
+    return _lib
+
+
+def registry() -> dict:
+    global _registry
+    if _registry is None:
+        if not os.path.exists(REGISTRY_PATH):
+            raise MissingExtensionError(f"{REGISTRY_PATH} is missing: run python -m physicsml_b200.build")
+        with open(REGISTRY_PATH) as f:
+            _registry = json.load(f)
+    return _registry
+
+
+_ERRORS = {-1: "bad argument", -2: "unsupported configuration (no compiled specialisation)", -3: "CUDA launch failed"}
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError(f"physicsml_b200: {what} failed: {_ERRORS.get(code, code)}")

@@ -1,0 +1,384 @@
+"""Generates the straight-line CUDA device code for the two kernels whose arithmetic is a sparse, statically known
+multilinear form:
+
+  * the channelwise edge tensor product (reference ``models/mace/modules/blocks.py:164-171,214-218``,
+    ``models/nequip/modules/interaction_block.py:51-58,95``): per (edge, channel)
+        out[o] += R[p] * c * h[i] * Y[j]                                     (sparse Wigner-3j, c includes sqrt(2 l3+1))
+  * the symmetric contraction (row a12; reference ``models/mace/modules/symmetric_contraction.py:218-239``): per (node, channel)
+        out[M] = sum_nu sum_k W_nu[z,k,c] * sum_mono c * x_i1 .. x_inu        (symmetrised generalised CG)
+
+Register indices must be compile-time constants, so the path / monomial tables are unrolled into source here rather
+than walked at run time.  Output: one header per kernel family under ``physicsml_b200/csrc/gen`` containing
+explicit template specialisations ``TPCode<ID>`` / ``SymCode<ID>``, plus ``registry.json`` mapping signature -> ID.
+"""
+from __future__ import annotations
+
+import json
+import os
+from collections import defaultdict
+
+from . import so3
+
+GEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "gen")
+
+
+def _f(x: float) -> str:
+    s = repr(float(x))
+    if "e" in s or "." in s or "inf" in s or "nan" in s:
+        return s + "f"
+    return s + ".0f"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tensor product
+# ----------------------------------------------------------------------------------------------------------------------
+def default_tp_specs() -> list[so3.TPSpec]:
+    """Signatures compiled by default: every BASELINE config + the reference's fixture models (+ small test shapes)."""
+    specs = {}
+
+    def add(node, lmax, target, parity=-1):
+        s = so3.build_tp_spec(node, lmax, target, parity)
+        specs[s.key] = s
+
+    for lmax in (1, 2, 3):
+        tgt = so3.irreps_str([(1, l, (-1) ** l) for l in range(lmax + 1)])
+        add("1x0e", lmax, tgt)
+        add("1x0e+1x1o", lmax, tgt)
+        if lmax >= 2:
+            add("1x0e+1x1o+1x2e", lmax, tgt)
+    # NequIP (parity=True): hidden = F x {0e,0o,1e,1o,2e,2o} restricted to what is reachable layer by layer
+    for lmax in (1, 2):
+        hidden = [(1, l, p) for l in range(lmax + 1) for p in (1, -1)]
+        hidden, _ = so3.sort_irreps(hidden)
+        node = [(1, 0, 1)]
+        for _layer in range(4):
+            # conv_irreps_out = scalars + gates + gated that are reachable (convnet_layer.py:45-81)
+            reach = set()
+            for _, l1, p1 in node:
+                for l2 in range(lmax + 1):
+                    for l3 in range(abs(l1 - l2), l1 + l2 + 1):
+                        reach.add((l3, p1 * (-1) ** l2))
+            out = [(1, l, p) for _, l, p in hidden if (l, p) in reach]
+            gate_ir = (0, 1) if (0, 1) in reach else (0, -1)
+            tgt = sorted(set([(l, p) for _, l, p in out] + [gate_ir]))
+            add(so3.irreps_str(node), lmax, so3.irreps_str([(1, l, p) for l, p in tgt]))
+            node = out
+    return list(specs.values())
+
+
+def _emit_tp(spec: so3.TPSpec, ident: int) -> str:
+    terms = so3.tp_terms(spec)
+    NP, DIN, DOUT, NSH = spec.n_paths, spec.d_in, spec.d_out, spec.n_sh
+    by_path = defaultdict(list)
+    for p, o, i, j, c in terms:
+        by_path[p].append((o, i, j, c))
+    L = []
+    L.append(f"// {spec.key}")
+    L.append(f"template <> struct TPCode<{ident}> {{")
+    L.append(f"  static constexpr int NP = {NP}, DIN = {DIN}, DOUT = {DOUT}, NSH = {NSH};")
+    # ---- per-channel gather / scatter of the irreps layout (blocks [C, 2l+1], mul-major)
+    L.append("  // h_row points at node_feats[s, 0]; block b of irrep l sits at C*in_off_b + u*(2l+1) + i")
+    L.append("  __device__ __forceinline__ static void load_h(const float* __restrict__ hrow, int C, int u, float (&h)[DIN]) {")
+    off = 0
+    for l, _ in spec.node_ls:
+        d = 2 * l + 1
+        for i in range(d):
+            L.append(f"    h[{off + i}] = __ldg(hrow + (size_t)C * {off} + (size_t)u * {d} + {i});")
+        off += d
+    L.append("  }")
+    L.append("  __device__ __forceinline__ static void atomic_add_h(float* __restrict__ hrow, int C, int u, const float (&h)[DIN]) {")
+    off = 0
+    for l, _ in spec.node_ls:
+        d = 2 * l + 1
+        for i in range(d):
+            L.append(f"    atomicAdd(hrow + (size_t)C * {off} + (size_t)u * {d} + {i}, h[{off + i}]);")
+        off += d
+    L.append("  }")
+    for name, op in (("load_out", "a[{k}] = __ldg(row + (size_t)C * {off} + (size_t)u * {d} + {m});"),
+                     ("store_out", "row[(size_t)C * {off} + (size_t)u * {d} + {m}] = a[{k}];")):
+        const = "const " if name == "load_out" else ""
+        aconst = "" if name == "load_out" else "const "
+        L.append(f"  __device__ __forceinline__ static void {name}({const}float* __restrict__ row, int C, int u, {aconst}float (&a)[DOUT]) {{")
+        off = 0
+        for l, _ in spec.out_ls:
+            d = 2 * l + 1
+            for m in range(d):
+                L.append("    " + op.format(k=off + m, off=off, d=d, m=m))
+            off += d
+        L.append("  }")
+    # ---- forward: acc[o] += R[p] * sum c h[i] Y[j]
+    L.append("  __device__ __forceinline__ static void fwd(const float (&h)[DIN], const float (&Y)[NSH], const float (&R)[NP], float (&acc)[DOUT]) {")
+    for p in range(NP):
+        grp = defaultdict(list)
+        for o, i, j, c in by_path[p]:
+            grp[o].append((i, j, c))
+        L.append("    {")
+        for o in sorted(grp):
+            expr = " + ".join(f"{_f(c)} * (h[{i}] * Y[{j}])" for i, j, c in grp[o])
+            L.append(f"      acc[{o}] = fmaf(R[{p}], {expr}, acc[{o}]);")
+        L.append("    }")
+    L.append("  }")
+    # ---- backward: given g = dL/d out (receiver row), accumulate dh, dY; write dR
+    L.append("  template <bool WANT_H, bool WANT_Y, bool WANT_R, int NY>")
+    L.append("  __device__ __forceinline__ static void bwd(const float (&h)[DIN], const float (&Y)[NSH], const float (&R)[NP], const float (&g)[DOUT],")
+    L.append("                                             float (&dh)[DIN], float (&dY)[NY], float (&dR)[NP]) {")
+    for p in range(NP):
+        outs = sorted({o for o, _, _, _ in by_path[p]})
+        L.append("    {")
+        L.append("      if (WANT_R) {")
+        expr = " + ".join(f"{_f(c)} * (h[{i}] * Y[{j}]) * g[{o}]" for o, i, j, c in by_path[p])
+        L.append(f"        dR[{p}] = {expr};")
+        L.append("      }")
+        L.append("      if (WANT_H || WANT_Y) {")
+        for o in outs:
+            L.append(f"        const float rg{o} = R[{p}] * g[{o}];")
+        L.append("        if (WANT_H) {")
+        gi = defaultdict(list)
+        for o, i, j, c in by_path[p]:
+            gi[i].append((o, j, c))
+        for i in sorted(gi):
+            expr = " + ".join(f"{_f(c)} * (Y[{j}] * rg{o})" for o, j, c in gi[i])
+            L.append(f"          dh[{i}] += {expr};")
+        L.append("        }")
+        L.append("        if (WANT_Y) {")
+        gj = defaultdict(list)
+        for o, i, j, c in by_path[p]:
+            gj[j].append((o, i, c))
+        for j in sorted(gj):
+            expr = " + ".join(f"{_f(c)} * (h[{i}] * rg{o})" for o, i, c in gj[j])
+            L.append(f"          dY[{j}] += {expr};")
+        L.append("        }")
+        L.append("      }")
+        L.append("    }")
+    L.append("  }")
+    L.append("};")
+    return "\n".join(L)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# symmetric contraction
+# ----------------------------------------------------------------------------------------------------------------------
+class SymSpec:
+    """One ``SymmetricContraction``: coupling irreps 0..lmax (parity (-1)^l), output irreps, correlation order."""
+
+    def __init__(self, lmax: int, outs, corr: int) -> None:
+        self.lmax = lmax
+        self.coupling = tuple((l, (-1) ** l) for l in range(lmax + 1))
+        self.outs = tuple((int(l), int(p)) for l, p in outs)
+        self.corr = int(corr)
+        self.S = (lmax + 1) ** 2
+        # number of weight rows k per (out, nu)
+        self.K = [[so3.u_matrix(self.coupling, o, nu).shape[-1] for nu in range(1, corr + 1)] for o in self.outs]
+        self.d_out = sum(2 * l + 1 for l, _ in self.outs)
+
+    @property
+    def key(self) -> str:
+        o = "_".join(f"{l}{'e' if p == 1 else 'o'}" for l, p in self.outs)
+        return f"l{self.lmax}__o{o}__c{self.corr}"
+
+
+def default_sym_specs() -> list[SymSpec]:
+    specs = {}
+    for lmax in (2, 3):
+        for corr in (2, 3):
+            for outs in ([(0, 1)], [(0, 1), (1, -1)], [(0, 1), (1, -1), (2, 1)]):
+                if max(l for l, _ in outs) > lmax:
+                    continue
+                s = SymSpec(lmax, outs, corr)
+                specs[s.key] = s
+    return list(specs.values())
+
+
+def _mono_expr(idx, xs="x") -> str:
+    return " * ".join(f"{xs}[{a}]" for a in idx)
+
+
+def _dmono(idx, j):
+    """d/dx_j of prod x_idx -> (multiplicity, remaining index tuple) or None."""
+    cnt = idx.count(j)
+    if cnt == 0:
+        return None
+    rest = list(idx)
+    rest.remove(j)
+    return cnt, tuple(rest)
+
+
+def _emit_sym(spec: SymSpec, ident: int) -> str:
+    S, corr = spec.S, spec.corr
+    NO = len(spec.outs)
+    L = []
+    L.append(f"// {spec.key}")
+    L.append(f"template <> struct SymCode<{ident}> {{")
+    L.append(f"  static constexpr int S = {S}, DOUT = {spec.d_out}, NOUT = {NO}, CORR = {corr};")
+    ks = ", ".join("{" + ", ".join(str(k) for k in row) + "}" for row in spec.K)
+    L.append(f"  // K[out][nu-1]: {ks}")
+    dims = ", ".join(str(2 * l + 1) for l, _ in spec.outs)
+    L.append(f"  // out dims: {dims}")
+
+    # per-channel access to the [N, sum_a C*(2L_a+1)] hidden-irreps layout (block a at C*off_a + c*(2L_a+1) + M)
+    for name, op in (("load_out", "o[{k}] = __ldg(row + (size_t)C * {off} + (size_t)c * {d} + {m});"),
+                     ("store_out", "row[(size_t)C * {off} + (size_t)c * {d} + {m}] = o[{k}];")):
+        const = "const " if name == "load_out" else ""
+        oconst = "" if name == "load_out" else "const "
+        L.append(f"  __device__ __forceinline__ static void {name}({const}float* __restrict__ row, int C, int c, {oconst}float (&o)[DOUT]) {{")
+        off = 0
+        for lo, _ in spec.outs:
+            d = 2 * lo + 1
+            for m in range(d):
+                L.append("    " + op.format(k=off + m, off=off, d=d, m=m))
+            off += d
+        L.append("  }")
+
+    # gather all monomials: per out index a, per nu: dict (k, M, idx) -> coef
+    monos = [[so3.contraction_monomials(spec.coupling, o, nu) for nu in range(1, corr + 1)] for o in spec.outs]
+
+    # ---------------- forward
+    L.append("  // out[M] per output irrep, concatenated: out[off_a + M]")
+    L.append("  template <class WT> __device__ __forceinline__ static void fwd(const float (&x)[S], const WT& W, float (&out)[DOUT]) {")
+    off = 0
+    for a, (lo, _) in enumerate(spec.outs):
+        for nu in range(1, corr + 1):
+            byk = defaultdict(lambda: defaultdict(list))
+            for (k, M, idx), c in monos[a][nu - 1].items():
+                byk[k][M].append((idx, c))
+            for k in sorted(byk):
+                L.append("    {")
+                L.append(f"      const float w = W.load({a}, {nu - 1}, {k});")
+                for M in sorted(byk[k]):
+                    expr = " + ".join(f"{_f(c)} * ({_mono_expr(idx)})" for idx, c in byk[k][M])
+                    L.append(f"      out[{off + M}] = fmaf(w, {expr}, out[{off + M}]);")
+                L.append("    }")
+        off += 2 * lo + 1
+    L.append("  }")
+
+    # ---------------- backward: dx += sum_M g_M d out_M / dx ; dW_k = sum_M g_M T_kM(x)
+    L.append("  template <bool WANT_W, class WT, class GW> __device__ __forceinline__ static void bwd(const float (&x)[S], const WT& W, const float (&g)[DOUT], float (&dx)[S], GW& gw) {")
+    off = 0
+    for a, (lo, _) in enumerate(spec.outs):
+        for nu in range(1, corr + 1):
+            byk = defaultdict(lambda: defaultdict(list))
+            for (k, M, idx), c in monos[a][nu - 1].items():
+                byk[k][M].append((idx, c))
+            for k in sorted(byk):
+                L.append("    {")
+                L.append(f"      const float w = W.load({a}, {nu - 1}, {k});")
+                L.append("      if (WANT_W) {")
+                parts = []
+                for M in sorted(byk[k]):
+                    expr = " + ".join(f"{_f(c)} * ({_mono_expr(idx)})" for idx, c in byk[k][M])
+                    parts.append(f"g[{off + M}] * ({expr})")
+                L.append(f"        gw.add({a}, {nu - 1}, {k}, {' + '.join(parts)});")
+                L.append("      }")
+                for M in sorted(byk[k]):
+                    L.append(f"      const float s{M} = w * g[{off + M}];")
+                # group derivative terms by j
+                dj = defaultdict(list)
+                for M in sorted(byk[k]):
+                    for idx, c in byk[k][M]:
+                        for j in sorted(set(idx)):
+                            mult, rest = _dmono(idx, j)
+                            dj[j].append((M, c * mult, rest))
+                for j in sorted(dj):
+                    expr = " + ".join(
+                        f"{_f(c)} * (s{M}" + (f" * {_mono_expr(rest)}" if rest else "") + ")" for M, c, rest in dj[j]
+                    )
+                    L.append(f"      dx[{j}] += {expr};")
+                L.append("    }")
+        off += 2 * lo + 1
+    L.append("  }")
+
+    # ---------------- directional second order: phi'(x; v) = d/de phi(x + e v)
+    # dg_M  = sum_j v_j d out_M/dx_j                       (JVP)
+    # ddx_j = sum_M g_M sum_i v_i d2 out_M / dx_i dx_j     (HVP)
+    # ddW_k = sum_M g_M sum_i v_i d T_kM / dx_i
+    L.append("  template <bool WANT_W, class WT, class GW> __device__ __forceinline__ static void dbl(const float (&x)[S], const float (&v)[S], const WT& W, const float (&g)[DOUT],")
+    L.append("                                            float (&dg)[DOUT], float (&ddx)[S], GW& gw) {")
+    off = 0
+    for a, (lo, _) in enumerate(spec.outs):
+        for nu in range(1, corr + 1):
+            byk = defaultdict(lambda: defaultdict(list))
+            for (k, M, idx), c in monos[a][nu - 1].items():
+                byk[k][M].append((idx, c))
+            for k in sorted(byk):
+                L.append("    {")
+                L.append(f"      const float w = W.load({a}, {nu - 1}, {k});")
+                # JVP of basis: jv_M = sum_mono c * sum_i v_i d mono/dx_i
+                for M in sorted(byk[k]):
+                    parts = []
+                    for idx, c in byk[k][M]:
+                        for i in sorted(set(idx)):
+                            mult, rest = _dmono(idx, i)
+                            parts.append(f"{_f(c * mult)} * (v[{i}]" + (f" * {_mono_expr(rest)}" if rest else "") + ")")
+                    L.append(f"      const float jv{M} = {' + '.join(parts)};")
+                    L.append(f"      dg[{off + M}] = fmaf(w, jv{M}, dg[{off + M}]);")
+                L.append("      if (WANT_W) {")
+                L.append(f"        gw.add({a}, {nu - 1}, {k}, " + " + ".join(f"g[{off + M}] * jv{M}" for M in sorted(byk[k])) + ");")
+                L.append("      }")
+                if nu >= 2:
+                    for M in sorted(byk[k]):
+                        L.append(f"      const float s{M} = w * g[{off + M}];")
+                    hj = defaultdict(list)
+                    for M in sorted(byk[k]):
+                        for idx, c in byk[k][M]:
+                            for i in sorted(set(idx)):
+                                m1, rest1 = _dmono(idx, i)
+                                for j in sorted(set(rest1)):
+                                    m2, rest2 = _dmono(rest1, j)
+                                    hj[j].append((M, c * m1 * m2, i, rest2))
+                    for j in sorted(hj):
+                        expr = " + ".join(
+                            f"{_f(c)} * (s{M} * v[{i}]" + (f" * {_mono_expr(rest)}" if rest else "") + ")"
+                            for M, c, i, rest in hj[j]
+                        )
+                        L.append(f"      ddx[{j}] += {expr};")
+                L.append("    }")
+        off += 2 * lo + 1
+    L.append("  }")
+    L.append("};")
+    return "\n".join(L)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def generate(out_dir: str = GEN_DIR) -> dict:
+    os.makedirs(out_dir, exist_ok=True)
+    tp_specs = default_tp_specs()
+    sym_specs = default_sym_specs()
+    registry = {"tp": {}, "sym": {}}
+
+    parts = ["// GENERATED by physicsml_b200/codegen.py — do not edit.", "#pragma once", "template <int ID> struct TPCode;"]
+    for ident, spec in enumerate(tp_specs):
+        parts.append(_emit_tp(spec, ident))
+        registry["tp"][spec.key] = {"id": ident, "np": spec.n_paths, "din": spec.d_in, "dout": spec.d_out, "nsh": spec.n_sh}
+    _write_if_changed(os.path.join(out_dir, "tp_gen.cuh"), "\n".join(parts) + "\n")
+
+    parts = ["// GENERATED by physicsml_b200/codegen.py — do not edit.", "#pragma once", "template <int ID> struct SymCode;"]
+    for ident, spec in enumerate(sym_specs):
+        parts.append(_emit_sym(spec, ident))
+        registry["sym"][spec.key] = {"id": ident, "S": spec.S, "dout": spec.d_out, "K": spec.K, "outs": list(spec.outs)}
+    _write_if_changed(os.path.join(out_dir, "sym_gen.cuh"), "\n".join(parts) + "\n")
+
+    ids = [
+        "// GENERATED by physicsml_b200/codegen.py — do not edit.",
+        "#pragma once",
+        f"#define PML_TP_NUM_SPECS {len(tp_specs)}",
+        "#define PML_TP_FOREACH(X) " + " ".join(f"X({i})" for i in range(len(tp_specs))),
+        f"#define PML_SYM_NUM_SPECS {len(sym_specs)}",
+        "#define PML_SYM_FOREACH(X) " + " ".join(f"X({i})" for i in range(len(sym_specs))),
+    ]
+    _write_if_changed(os.path.join(out_dir, "pml_ids.h"), "\n".join(ids) + "\n")
+    _write_if_changed(os.path.join(out_dir, "registry.json"), json.dumps(registry, indent=1, sort_keys=True) + "\n")
+    return registry
+
+
+def _write_if_changed(path: str, text: str) -> None:
+    if os.path.exists(path):
+        with open(path) as f:
+            if f.read() == text:
+                return
+    with open(path, "w") as f:
+        f.write(text)
+
+
+if __name__ == "__main__":
+    reg = generate()
+    print(f"generated {len(reg['tp'])} tensor-product and {len(reg['sym'])} symmetric-contraction specialisations in {GEN_DIR}")

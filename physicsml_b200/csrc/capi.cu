@@ -1,0 +1,95 @@
+// C-ABI dispatch layer (include/physicsml_b200.h): routes spec ids to the per-signature translation units.
+#include <cuda_runtime.h>
+
+#include "gen/pml_ids.h"
+#include "pml_common.cuh"
+
+struct pml_sym_weights;
+
+#define DECL_TP(ID)                                                                                                      \
+  extern "C" int pml_tp_fwd_launch_##ID(const float*, const float*, const float*, const int*, const int*, const int*,    \
+                                        float*, int, int, cudaStream_t);                                                 \
+  extern "C" int pml_tp_bwd_launch_##ID(const float*, const float*, const float*, const float*, const int*, const int*,  \
+                                        const int*, float*, float*, float*, int, int, cudaStream_t);
+PML_TP_FOREACH(DECL_TP)
+#undef DECL_TP
+
+#define DECL_SYM(ID)                                                                                                     \
+  extern "C" int pml_sym_fwd_launch_##ID(const float*, const float*, const pml_sym_weights*, float*, int, int, int,     \
+                                         cudaStream_t);                                                                  \
+  extern "C" int pml_sym_bwd_launch_##ID(const float*, const float*, const pml_sym_weights*, const float*, float*, int, \
+                                         int, int, cudaStream_t);                                                        \
+  extern "C" int pml_sym_dbl_launch_##ID(const float*, const float*, const float*, const pml_sym_weights*, const float*, \
+                                         float*, float*, int, int, int, cudaStream_t);
+PML_SYM_FOREACH(DECL_SYM)
+#undef DECL_SYM
+
+extern "C" int pml_abi_version(void) { return 1; }
+extern "C" int pml_num_tp_specs(void) { return PML_TP_NUM_SPECS; }
+extern "C" int pml_num_sym_specs(void) { return PML_SYM_NUM_SPECS; }
+
+extern "C" int pml_tp_fwd(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
+                          const int* perm, float* out, int N, int C, cudaStream_t stream) {
+  switch (spec) {
+#define CASE(ID) \
+  case ID:       \
+    return pml_tp_fwd_launch_##ID(h, Y, R, gather, rowptr, perm, out, N, C, stream);
+    PML_TP_FOREACH(CASE)
+#undef CASE
+    default:
+      return PML_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int pml_tp_bwd(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                          const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C,
+                          cudaStream_t stream) {
+  switch (spec) {
+#define CASE(ID) \
+  case ID:       \
+    return pml_tp_bwd_launch_##ID(h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, stream);
+    PML_TP_FOREACH(CASE)
+#undef CASE
+    default:
+      return PML_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int pml_sym_fwd(int spec, const float* x, const float* attrs, const pml_sym_weights* W, float* out, int N,
+                           int C, int Z, cudaStream_t stream) {
+  switch (spec) {
+#define CASE(ID) \
+  case ID:       \
+    return pml_sym_fwd_launch_##ID(x, attrs, W, out, N, C, Z, stream);
+    PML_SYM_FOREACH(CASE)
+#undef CASE
+    default:
+      return PML_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int pml_sym_bwd(int spec, const float* x, const float* attrs, const pml_sym_weights* W, const float* g,
+                           float* dx, int N, int C, int Z, cudaStream_t stream) {
+  switch (spec) {
+#define CASE(ID) \
+  case ID:       \
+    return pml_sym_bwd_launch_##ID(x, attrs, W, g, dx, N, C, Z, stream);
+    PML_SYM_FOREACH(CASE)
+#undef CASE
+    default:
+      return PML_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int pml_sym_dbl(int spec, const float* x, const float* v, const float* attrs, const pml_sym_weights* W,
+                           const float* g, float* dg, float* ddx, int N, int C, int Z, cudaStream_t stream) {
+  switch (spec) {
+#define CASE(ID) \
+  case ID:       \
+    return pml_sym_dbl_launch_##ID(x, v, attrs, W, g, dg, ddx, N, C, Z, stream);
+    PML_SYM_FOREACH(CASE)
+#undef CASE
+    default:
+      return PML_ERR_UNSUPPORTED;
+  }
+}

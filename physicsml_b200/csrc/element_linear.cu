@@ -1,0 +1,208 @@
+// Element-indexed per-irrep linear maps: o3.FullyConnectedTensorProduct(x, node_attrs) with scalar (one-hot) attrs.
+//
+// Replaces  mix_layer (reference mace/modules/blocks.py:183-188,231-232), residual_connection_layer (blocks.py:72-78,88-92)
+// and NequIP's self_connection_layer (nequip/modules/interaction_block.py:73-82,91-92).  The reference contracts a dense
+// [mul_in, Z, mul_out] weight with the one-hot row, wasting a factor Z of work; here the element row selects the
+// [mul_in, mul_out] slab directly (dense attrs rows are still handled, term by term, for generality):
+//     out[n, w, m] = alpha * sum_v attrs[n, v] * sum_u W[u, v, w] * x[n, u, m]
+#include "pml_common.cuh"
+
+#define PML_EL_MAX_PATHS 8
+
+extern "C" {
+typedef struct {
+  int npaths;
+  int d[PML_EL_MAX_PATHS];            // 2l+1
+  int mul_in[PML_EL_MAX_PATHS];
+  int mul_out[PML_EL_MAX_PATHS];
+  long long w_off[PML_EL_MAX_PATHS];  // offset of this path's [mul_in, Z, mul_out] slab in the flat weight
+  long long x_off[PML_EL_MAX_PATHS];  // x[n, x_off + u*d + m]
+  long long o_off[PML_EL_MAX_PATHS];  // out[n, o_off + w*o_ws + m]
+  long long o_ws[PML_EL_MAX_PATHS];
+  float alpha[PML_EL_MAX_PATHS];
+  long long x_rs, o_rs;               // row strides
+} pml_el_plan;
+}
+
+namespace pml {
+
+__device__ __forceinline__ int one_hot_index(const float* __restrict__ row, int Z) {
+  int nz = 0, last = -1;
+  bool unit = true;
+  for (int e = 0; e < Z; ++e) {
+    const float y = __ldg(row + e);
+    if (y != 0.f) {
+      ++nz;
+      last = e;
+      unit = unit && (y == 1.f);
+    }
+  }
+  return (nz == 1 && unit) ? last : -1;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) el_fwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
+                                                     const float* __restrict__ W, pml_el_plan P, float* __restrict__ out,
+                                                     int N, int Z, int accumulate) {
+  const int n = blockIdx.x, p = blockIdx.y;
+  if (P.d[p] != D) return;
+  extern __shared__ float xs[];  // [mul_in * D]
+  const int MI = P.mul_in[p], MO = P.mul_out[p];
+  const float* xr = x + (size_t)n * P.x_rs + P.x_off[p];
+  for (int i = threadIdx.x; i < MI * D; i += blockDim.x) xs[i] = __ldg(xr + i);
+  __syncthreads();
+  const float* arow = attrs + (size_t)n * Z;
+  const int z = one_hot_index(arow, Z);
+  const float* Wp = W + P.w_off[p];
+  for (int w = threadIdx.x; w < MO; w += blockDim.x) {
+    float acc[D];
+#pragma unroll
+    for (int m = 0; m < D; ++m) acc[m] = 0.f;
+    for (int v = (z >= 0 ? z : 0); v < (z >= 0 ? z + 1 : Z); ++v) {
+      const float a = z >= 0 ? 1.f : __ldg(arow + v);
+      if (a == 0.f) continue;
+      for (int u = 0; u < MI; ++u) {
+        const float wv = a * __ldg(Wp + ((size_t)u * Z + v) * MO + w);
+#pragma unroll
+        for (int m = 0; m < D; ++m) acc[m] = fmaf(wv, xs[u * D + m], acc[m]);
+      }
+    }
+    float* o = out + (size_t)n * P.o_rs + P.o_off[p] + (size_t)w * P.o_ws[p];
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+      const float r = P.alpha[p] * acc[m];
+      o[m] = accumulate ? o[m] + r : r;
+    }
+  }
+}
+
+// dx[n, u, m] = alpha * sum_v a_v sum_w W[u, v, w] g[n, w, m]
+template <int D>
+__global__ void __launch_bounds__(128) el_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ attrs,
+                                                       const float* __restrict__ W, pml_el_plan P, float* __restrict__ dx,
+                                                       int N, int Z, int accumulate) {
+  const int n = blockIdx.x, p = blockIdx.y;
+  if (P.d[p] != D) return;
+  extern __shared__ float gs[];  // [mul_out * D]
+  const int MI = P.mul_in[p], MO = P.mul_out[p];
+  const float* gr = g + (size_t)n * P.o_rs + P.o_off[p];
+  for (int i = threadIdx.x; i < MO * D; i += blockDim.x) {
+    const int w = i / D, m = i - w * D;
+    gs[i] = __ldg(gr + (size_t)w * P.o_ws[p] + m);
+  }
+  __syncthreads();
+  const float* arow = attrs + (size_t)n * Z;
+  const int z = one_hot_index(arow, Z);
+  const float* Wp = W + P.w_off[p];
+  for (int u = threadIdx.x; u < MI; u += blockDim.x) {
+    float acc[D];
+#pragma unroll
+    for (int m = 0; m < D; ++m) acc[m] = 0.f;
+    for (int v = (z >= 0 ? z : 0); v < (z >= 0 ? z + 1 : Z); ++v) {
+      const float a = z >= 0 ? 1.f : __ldg(arow + v);
+      if (a == 0.f) continue;
+      const float* wr = Wp + ((size_t)u * Z + v) * MO;
+      for (int w = 0; w < MO; ++w) {
+        const float wv = a * __ldg(wr + w);
+#pragma unroll
+        for (int m = 0; m < D; ++m) acc[m] = fmaf(wv, gs[w * D + m], acc[m]);
+      }
+    }
+    float* o = dx + (size_t)n * P.x_rs + P.x_off[p] + (size_t)u * D;
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+      const float r = P.alpha[p] * acc[m];
+      o[m] = accumulate ? o[m] + r : r;
+    }
+  }
+}
+
+// dW[u, v, w] = alpha * sum_n a[n, v] sum_m x[n, u, m] g[n, w, m]   — one CTA per (path, v, 16x16 tile of (u, w)),
+// looping over the nodes: deterministic, no atomics.
+template <int D>
+__global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                       const float* __restrict__ attrs, pml_el_plan P,
+                                                       float* __restrict__ dW, int N, int Z, int accumulate) {
+  const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
+  if (P.d[p] != D) return;
+  const int MI = P.mul_in[p], MO = P.mul_out[p];
+  const int tiles_w = (MO + 15) / 16;
+  const int tu = blockIdx.x / tiles_w, tw = blockIdx.x - tu * tiles_w;
+  if (tu * 16 >= MI) return;
+  const int w = tw * 16 + (threadIdx.x & 15), u = tu * 16 + (threadIdx.x >> 4);
+  const bool ok = (u < MI) && (w < MO);
+  __shared__ float xs[16 * 7], gs[16 * 7];
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float a = __ldg(attrs + (size_t)n * Z + v);
+    if (a == 0.f) continue;  // uniform across the CTA
+    __syncthreads();
+    if (threadIdx.x < 16 * D) {
+      const int uu = threadIdx.x / D, m = threadIdx.x - uu * D;
+      const int gu = tu * 16 + uu;
+      xs[threadIdx.x] = gu < MI ? __ldg(x + (size_t)n * P.x_rs + P.x_off[p] + (size_t)gu * D + m) : 0.f;
+    } else if (threadIdx.x >= 128 && threadIdx.x < 128 + 16 * D) {
+      const int t = threadIdx.x - 128;
+      const int ww = t / D, m = t - ww * D;
+      const int gw = tw * 16 + ww;
+      gs[t] = gw < MO ? __ldg(g + (size_t)n * P.o_rs + P.o_off[p] + (size_t)gw * P.o_ws[p] + m) : 0.f;
+    }
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int m = 0; m < D; ++m) s = fmaf(xs[(threadIdx.x >> 4) * D + m], gs[(threadIdx.x & 15) * D + m], s);
+    acc = fmaf(a, s, acc);
+  }
+  if (ok) {
+    float* o = dW + P.w_off[p] + ((size_t)u * Z + v) * MO + w;
+    const float r = P.alpha[p] * acc;
+    *o = accumulate ? *o + r : r;
+  }
+}
+
+}  // namespace pml
+
+#define PML_EL_FOR_D(CALL) \
+  CALL(1) CALL(3) CALL(5) CALL(7)
+
+extern "C" int pml_element_linear_fwd(const float* x, const float* attrs, const float* W, const pml_el_plan* plan,
+                                      float* out, int N, int Z, int accumulate, cudaStream_t stream) {
+  if (N <= 0 || plan->npaths <= 0) return PML_OK;
+  dim3 grid(N, plan->npaths);
+  int max_mi = 0;
+  for (int p = 0; p < plan->npaths; ++p) max_mi = plan->mul_in[p] > max_mi ? plan->mul_in[p] : max_mi;
+#define CALL(D) pml::el_fwd_kernel<D><<<grid, 128, (size_t)max_mi * D * sizeof(float), stream>>>(x, attrs, W, *plan, out, N, Z, accumulate);
+  PML_EL_FOR_D(CALL)
+#undef CALL
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, const float* W, const pml_el_plan* plan,
+                                        float* dx, int N, int Z, int accumulate, cudaStream_t stream) {
+  if (N <= 0 || plan->npaths <= 0) return PML_OK;
+  dim3 grid(N, plan->npaths);
+  int max_mo = 0;
+  for (int p = 0; p < plan->npaths; ++p) max_mo = plan->mul_out[p] > max_mo ? plan->mul_out[p] : max_mo;
+#define CALL(D) pml::el_bwd_x_kernel<D><<<grid, 128, (size_t)max_mo * D * sizeof(float), stream>>>(g, attrs, W, *plan, dx, N, Z, accumulate);
+  PML_EL_FOR_D(CALL)
+#undef CALL
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_element_linear_bwd_w(const float* x, const float* g, const float* attrs, const pml_el_plan* plan,
+                                        float* dW, int N, int Z, int accumulate, cudaStream_t stream) {
+  if (plan->npaths <= 0) return PML_OK;
+  int max_t = 0;
+  for (int p = 0; p < plan->npaths; ++p) {
+    const int t = ((plan->mul_in[p] + 15) / 16) * ((plan->mul_out[p] + 15) / 16);
+    max_t = t > max_t ? t : max_t;
+  }
+  dim3 grid(max_t, 1, plan->npaths * Z);
+#define CALL(D) pml::el_bwd_w_kernel<D><<<grid, 256, 0, stream>>>(x, g, attrs, *plan, dW, N, Z, accumulate);
+  PML_EL_FOR_D(CALL)
+#undef CALL
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}

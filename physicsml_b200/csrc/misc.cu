@@ -1,0 +1,176 @@
+// Small elementwise / segmented kernels on the path: normalised SiLU (and tanh) with first and second derivative
+// forms for the radial MLP and readout (e3nn nn.FullyConnectedNet / normalize2mom; reference blocks.py:157-160,11-28),
+// the per-graph pooled readout (mace.py:252-258) and the receiver-CSR build used by the fused edge kernels.
+#include "pml_common.cuh"
+
+namespace pml {
+
+// kind 0: SiLU, 1: tanh.   order 0: c*f(x) ; 1: g*c*f'(x) ; 2: g*v*c*f''(x)
+template <int KIND, int ORDER>
+__global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                  const float* __restrict__ v, float c, float* __restrict__ y,
+                                                  long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = x[i];
+  float r;
+  if (KIND == 0) {
+    const float s = 1.f / (1.f + expf(-t));
+    if (ORDER == 0) r = t * s;
+    else if (ORDER == 1) r = s * (1.f + t * (1.f - s));
+    else r = s * (1.f - s) * (2.f + t * (1.f - 2.f * s));
+  } else {
+    const float th = tanhf(t);
+    if (ORDER == 0) r = th;
+    else if (ORDER == 1) r = 1.f - th * th;
+    else r = -2.f * th * (1.f - th * th);
+  }
+  r *= c;
+  if (ORDER >= 1) r *= g[i];
+  if (ORDER >= 2) r *= v[i];
+  y[i] = r;
+}
+
+// out[batch[n], f] += x[n, f]   (batch sorted ascending; G tiny) — one thread per (n, f)
+__global__ void __launch_bounds__(256) pool_sum_kernel(const float* __restrict__ x, const long long* __restrict__ batch,
+                                                       float* __restrict__ out, int N, int F) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * F) return;
+  const int n = (int)(i / F), f = (int)(i - (long long)n * F);
+  atomicAdd(out + (size_t)batch[n] * F + f, x[i]);
+}
+
+__global__ void __launch_bounds__(256) pool_gather_kernel(const float* __restrict__ g, const long long* __restrict__ batch,
+                                                          float* __restrict__ out, int N, int F) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * F) return;
+  const int n = (int)(i / F), f = (int)(i - (long long)n * F);
+  out[i] = g[(size_t)batch[n] * F + f];
+}
+
+// ---- receiver-CSR build: histogram -> (scan on the caller's side or single-block scan) -> stable fill ----------------
+__global__ void __launch_bounds__(256) csr_count_kernel(const long long* __restrict__ idx, int* __restrict__ counts, int E) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) atomicAdd(counts + (int)idx[e], 1);
+}
+
+// single-CTA exclusive scan (N up to a few hundred thousand is fine: one pass of 1024-wide chunks)
+__global__ void __launch_bounds__(1024) csr_scan_kernel(const int* __restrict__ counts, int* __restrict__ rowptr, int N) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < N ? counts[i] : 0;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if ((threadIdx.x & 31) >= o) s += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_tot[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += t;
+      }
+      warp_tot[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int woff = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0;
+    const int incl = carry + woff + s;
+    if (i < N) rowptr[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowptr[N] = carry;
+}
+
+// int64 [2,E] edge_index -> int32 sender / receiver copies
+__global__ void __launch_bounds__(256) split_edge_index_kernel(const long long* __restrict__ ei, int* __restrict__ a,
+                                                               int* __restrict__ b, int E) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) {
+    a[e] = (int)ei[e];
+    b[e] = (int)ei[(size_t)E + e];
+  }
+}
+
+// [N, C*S] irreps layout (blocks [C, 2l+1]) <-> [N, C, S] channel-major layout (reference irreps_tools.py:47-67)
+__global__ void __launch_bounds__(256) irreps_to_channel_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                long long total, int C, int S, int lmax, int inverse) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // i indexes the channel-major tensor: (n, c, s)
+  const int s = (int)(i % S);
+  const long long nc = i / S;
+  const int c = (int)(nc % C);
+  const long long n = nc / C;
+  int l = 0;
+  while ((l + 1) * (l + 1) <= s) ++l;
+  (void)lmax;
+  const int m = s - l * l, d = 2 * l + 1;
+  const long long j = n * (long long)C * S + (long long)C * l * l + (long long)c * d + m;
+  if (inverse) y[j] = x[i];
+  else y[i] = x[j];
+}
+
+}  // namespace pml
+
+extern "C" int pml_act(const float* x, const float* g, const float* v, float c, int kind, int order, float* y,
+                       long long n, cudaStream_t stream) {
+  if (n <= 0) return PML_OK;
+  const int grid = pml::ceil_div(n, 256);
+#define PML_ACT_CASE(K, O) \
+  if (kind == K && order == O) pml::act_kernel<K, O><<<grid, 256, 0, stream>>>(x, g, v, c, y, n);
+  PML_ACT_CASE(0, 0) PML_ACT_CASE(0, 1) PML_ACT_CASE(0, 2) PML_ACT_CASE(1, 0) PML_ACT_CASE(1, 1) PML_ACT_CASE(1, 2)
+#undef PML_ACT_CASE
+  if (kind < 0 || kind > 1 || order < 0 || order > 2) return PML_ERR_BAD_ARG;
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+// out [G, F] must be zero-initialised
+extern "C" int pml_pool_sum(const float* x, const long long* batch, float* out, int N, int F, cudaStream_t stream) {
+  if (N <= 0 || F <= 0) return PML_OK;
+  pml::pool_sum_kernel<<<pml::ceil_div((long long)N * F, 256), 256, 0, stream>>>(x, batch, out, N, F);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_pool_gather(const float* g, const long long* batch, float* out, int N, int F, cudaStream_t stream) {
+  if (N <= 0 || F <= 0) return PML_OK;
+  pml::pool_gather_kernel<<<pml::ceil_div((long long)N * F, 256), 256, 0, stream>>>(g, batch, out, N, F);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+// rowptr [N+1]; counts is scratch [N], zero-initialised by the caller
+extern "C" int pml_csr_rowptr(const long long* idx, int* counts, int* rowptr, int E, int N, cudaStream_t stream) {
+  if (E > 0) pml::csr_count_kernel<<<pml::ceil_div(E, 256), 256, 0, stream>>>(idx, counts, E);
+  pml::csr_scan_kernel<<<1, 1024, 0, stream>>>(counts, rowptr, N);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int E, cudaStream_t stream) {
+  if (E <= 0) return PML_OK;
+  pml::split_edge_index_kernel<<<pml::ceil_div(E, 256), 256, 0, stream>>>(edge_index, row0, row1, E);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse,
+                                     cudaStream_t stream) {
+  const int S = (lmax + 1) * (lmax + 1);
+  const long long total = N * C * S;
+  if (total <= 0) return PML_OK;
+  pml::irreps_to_channel_kernel<<<pml::ceil_div(total, 256), 256, 0, stream>>>(x, y, total, C, S, lmax, inverse);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}

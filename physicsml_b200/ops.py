@@ -1,0 +1,778 @@
+"""``torch.library`` custom ops (namespace ``physicsml_b200``) over the C ABI, each with an autograd formula whose
+backward is again made of these ops, so that forces (first derivative, ``lightning/module.py:28-48`` of the reference)
+and force-matching training (second derivative, ``create_graph=True``) never fall back to generic autograd
+gather/scatter.
+
+CUDA only.  There is deliberately no CPU implementation and no PyTorch-eager fallback: calling an op with CPU
+tensors raises ``NotImplementedError`` from the dispatcher, and a missing shared library raises
+``MissingExtensionError`` at the first launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib, plans
+
+NS = "physicsml_b200"
+
+# count of kernel launches issued through the C ABI (bench.py reports it as `gpu_launches`)
+LAUNCHES = [0]
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"physicsml_b200 ops are fp32 only, got {t.dtype}")
+    return t.contiguous()
+
+
+def _call(name: str, *args, launches: int = 1) -> None:
+    LAUNCHES[0] += launches
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+# ======================================================================================================================
+# edge featurisation
+# ======================================================================================================================
+def _feat_args(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax):
+    return (_p(pos), _p(snd), _p(rcv), _p(shift), _p(cell), _p(bessel_w), float(r_max), float(prefactor),
+            float(w_scale), int(p), int(bessel_w.numel()), int(lmax))
+
+
+@torch.library.custom_op(f"{NS}::edge_featurise", mutates_args=(), device_types="cuda")
+def edge_featurise(pos: Tensor, snd: Tensor, rcv: Tensor, shift: Optional[Tensor], cell: Optional[Tensor],
+                   bessel_w: Tensor, r_max: float, prefactor: float, w_scale: float, p: int,
+                   lmax: int) -> Tuple[Tensor, Tensor]:
+    pos = _f32c(pos)
+    E = snd.numel()
+    Y = pos.new_empty(E, (lmax + 1) ** 2)
+    B = pos.new_empty(E, bessel_w.numel())
+    _call("pml_edge_featurise_fwd", *_feat_args(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax),
+          _p(Y), _p(B), None, E, _stream())
+    return Y, B
+
+
+@edge_featurise.register_fake
+def _(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax):
+    E = snd.numel()
+    return pos.new_empty(E, (lmax + 1) ** 2), pos.new_empty(E, bessel_w.numel())
+
+
+@torch.library.custom_op(f"{NS}::edge_featurise_bwd", mutates_args=(), device_types="cuda")
+def edge_featurise_bwd(pos: Tensor, snd: Tensor, rcv: Tensor, shift: Optional[Tensor], cell: Optional[Tensor],
+                       bessel_w: Tensor, r_max: float, prefactor: float, w_scale: float, p: int, lmax: int,
+                       gY: Optional[Tensor], gB: Optional[Tensor]) -> Tensor:
+    pos = _f32c(pos)
+    gpos = torch.zeros_like(pos)
+    gY = None if gY is None else _f32c(gY)
+    gB = None if gB is None else _f32c(gB)
+    _call("pml_edge_featurise_bwd", *_feat_args(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax),
+          _p(gY), _p(gB), _p(gpos), snd.numel(), _stream())
+    return gpos
+
+
+@edge_featurise_bwd.register_fake
+def _(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax, gY, gB):
+    return torch.empty_like(pos)
+
+
+@torch.library.custom_op(f"{NS}::edge_featurise_jvp", mutates_args=(), device_types="cuda")
+def edge_featurise_jvp(pos: Tensor, snd: Tensor, rcv: Tensor, shift: Optional[Tensor], cell: Optional[Tensor],
+                       bessel_w: Tensor, r_max: float, prefactor: float, w_scale: float, p: int, lmax: int,
+                       t: Tensor) -> Tuple[Tensor, Tensor]:
+    pos, t = _f32c(pos), _f32c(t)
+    E = snd.numel()
+    tY = pos.new_empty(E, (lmax + 1) ** 2)
+    tB = pos.new_empty(E, bessel_w.numel())
+    _call("pml_edge_featurise_jvp", *_feat_args(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax),
+          _p(t), _p(tY), _p(tB), E, _stream())
+    return tY, tB
+
+
+@edge_featurise_jvp.register_fake
+def _(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax, t):
+    E = snd.numel()
+    return pos.new_empty(E, (lmax + 1) ** 2), pos.new_empty(E, bessel_w.numel())
+
+
+def _feat_save(ctx, inputs):
+    ctx.save_for_backward(*inputs[:6])  # pos, snd, rcv, shift, cell, bessel_w (None allowed)
+    ctx.consts = tuple(inputs[6:11])
+
+
+def _feat_args_from(ctx):
+    return tuple(ctx.saved_tensors) + ctx.consts
+
+
+def _feat_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    _feat_save(ctx, inputs)
+
+
+def _feat_bwd(ctx, gY, gB):
+    g = None
+    if ctx.needs_input_grad[0] and (gY is not None or gB is not None):
+        g = edge_featurise_bwd(*_feat_args_from(ctx), gY, gB)
+    return (g,) + (None,) * 10
+
+
+edge_featurise.register_autograd(_feat_bwd, setup_context=_feat_setup)
+
+
+def _feat_bwd_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    _feat_save(ctx, inputs)
+    ctx.has = (inputs[11] is not None, inputs[12] is not None)
+
+
+def _feat_bwd_bwd(ctx, v):
+    # gpos is linear in (gY, gB): their cotangents are the tangent map applied to v.  The second derivative of the
+    # harmonics / radial basis w.r.t. the coordinates only feeds d(loss)/d(coordinates), which nothing consumes
+    # (SURVEY §7 "hard parts"); it is not propagated.
+    if v is None:
+        return (None,) * 13
+    tY, tB = edge_featurise_jvp(*_feat_args_from(ctx), v)
+    return (None,) * 11 + (tY if ctx.has[0] else None, tB if ctx.has[1] else None)
+
+
+edge_featurise_bwd.register_autograd(_feat_bwd_bwd, setup_context=_feat_bwd_setup)
+
+
+def _feat_jvp_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    _feat_save(ctx, inputs)
+
+
+def _feat_jvp_bwd(ctx, gtY, gtB):
+    g = None
+    if gtY is not None or gtB is not None:
+        g = edge_featurise_bwd(*_feat_args_from(ctx), gtY, gtB)
+    return (None,) * 11 + (g,)
+
+
+edge_featurise_jvp.register_autograd(_feat_jvp_bwd, setup_context=_feat_jvp_setup)
+
+
+# ======================================================================================================================
+# fused tensor product + scatter
+# ======================================================================================================================
+@torch.library.custom_op(f"{NS}::tp_scatter", mutates_args=(), device_types="cuda")
+def tp_scatter(h: Tensor, Y: Tensor, R: Tensor, gather: Tensor, rowptr: Tensor, perm: Optional[Tensor],
+               plan: int) -> Tensor:
+    pl = plans.get(plan)
+    h, Y, R = _f32c(h), _f32c(Y), _f32c(R)
+    N = rowptr.numel() - 1
+    out = h.new_empty(N, pl.C * pl.DOUT)
+    _call("pml_tp_fwd", pl.spec_id, _p(h), _p(Y), _p(R), _p(gather), _p(rowptr), _p(perm), _p(out), N, pl.C, _stream())
+    return out
+
+
+@tp_scatter.register_fake
+def _(h, Y, R, gather, rowptr, perm, plan):
+    pl = plans.get(plan)
+    return h.new_empty(rowptr.numel() - 1, pl.C * pl.DOUT)
+
+
+@torch.library.custom_op(f"{NS}::tp_scatter_bwd", mutates_args=(), device_types="cuda")
+def tp_scatter_bwd(h: Tensor, Y: Tensor, R: Tensor, g: Tensor, gather: Tensor, rowptr: Tensor, perm: Optional[Tensor],
+                   plan: int, need_h: bool, need_y: bool, need_r: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    pl = plans.get(plan)
+    h, Y, R, g = _f32c(h), _f32c(Y), _f32c(R), _f32c(g)
+    N = rowptr.numel() - 1
+    dh = torch.zeros_like(h) if need_h else h.new_empty(0)
+    dY = (torch.zeros_like(Y) if pl.C > 32 else torch.empty_like(Y)) if need_y else Y.new_empty(0)
+    dR = torch.empty_like(R) if need_r else R.new_empty(0)
+    if need_h or need_y or need_r:
+        _call("pml_tp_bwd", pl.spec_id, _p(h), _p(Y), _p(R), _p(g), _p(gather), _p(rowptr), _p(perm),
+              _p(dh) if need_h else None, _p(dY) if need_y else None, _p(dR) if need_r else None, N, pl.C, _stream())
+    return dh, dY, dR
+
+
+@tp_scatter_bwd.register_fake
+def _(h, Y, R, g, gather, rowptr, perm, plan, need_h, need_y, need_r):
+    return (torch.empty_like(h) if need_h else h.new_empty(0), torch.empty_like(Y) if need_y else Y.new_empty(0),
+            torch.empty_like(R) if need_r else R.new_empty(0))
+
+
+def _tp_setup(ctx, inputs, output):
+    h, Y, R, gather, rowptr, perm, plan = inputs
+    ctx.save_for_backward(h, Y, R, gather, rowptr, perm)
+    ctx.plan = plan
+
+
+def _tp_bwd(ctx, g):
+    h, Y, R, gather, rowptr, perm = ctx.saved_tensors
+    nh, ny, nr = ctx.needs_input_grad[:3]
+    dh, dY, dR = tp_scatter_bwd(h, Y, R, g, gather, rowptr, perm, ctx.plan, nh, ny, nr)
+    return (dh if nh else None, dY if ny else None, dR if nr else None, None, None, None, None)
+
+
+tp_scatter.register_autograd(_tp_bwd, setup_context=_tp_setup)
+
+
+def _tp_bwd_setup(ctx, inputs, output):
+    h, Y, R, g, gather, rowptr, perm, plan, need_h, need_y, need_r = inputs
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(h, Y, R, g, gather, rowptr, perm)
+    ctx.plan = plan
+    ctx.needs = (need_h, need_y, need_r)
+
+
+def _acc(a, b):
+    if a is None:
+        return b
+    if b is None:
+        return a
+    return a + b
+
+
+def _tp_bwd_bwd(ctx, vh, vY, vR):
+    """The op is the gradient of the 4-linear form Phi(h, Y, R, g); differentiating
+    <vh, dPhi/dh> + <vY, dPhi/dY> + <vR, dPhi/dR> needs only the same two kernels with permuted arguments."""
+    h, Y, R, g, gather, rowptr, perm = ctx.saved_tensors
+    plan = ctx.plan
+    nh, ny, nr, ng = ctx.needs_input_grad[:4]
+    if not ctx.needs[0]:
+        vh = None
+    if not ctx.needs[1]:
+        vY = None
+    if not ctx.needs[2]:
+        vR = None
+    gh = gY = gR = gg = None
+    if vh is not None:  # Phi(vh, Y, R, g)
+        if ng:
+            gg = _acc(gg, tp_scatter(vh, Y, R, gather, rowptr, perm, plan))
+        if ny or nr:
+            _, a, b = tp_scatter_bwd(vh, Y, R, g, gather, rowptr, perm, plan, False, ny, nr)
+            gY, gR = _acc(gY, a if ny else None), _acc(gR, b if nr else None)
+    if vY is not None:  # Phi(h, vY, R, g)
+        if ng:
+            gg = _acc(gg, tp_scatter(h, vY, R, gather, rowptr, perm, plan))
+        if nh or nr:
+            a, _, b = tp_scatter_bwd(h, vY, R, g, gather, rowptr, perm, plan, nh, False, nr)
+            gh, gR = _acc(gh, a if nh else None), _acc(gR, b if nr else None)
+    if vR is not None:  # Phi(h, Y, vR, g)
+        if ng:
+            gg = _acc(gg, tp_scatter(h, Y, vR, gather, rowptr, perm, plan))
+        if nh or ny:
+            a, b, _ = tp_scatter_bwd(h, Y, vR, g, gather, rowptr, perm, plan, nh, ny, False)
+            gh, gY = _acc(gh, a if nh else None), _acc(gY, b if ny else None)
+    return (gh, gY, gR, gg) + (None,) * 7
+
+
+tp_scatter_bwd.register_autograd(_tp_bwd_bwd, setup_context=_tp_bwd_setup)
+
+
+# ======================================================================================================================
+# per-irrep linear (grouped GEMM)
+# ======================================================================================================================
+def _splitk_for(n_rows: int) -> int:
+    return max(1, min(64, (n_rows + 2047) // 2048))
+
+
+@torch.library.custom_op(f"{NS}::irrep_linear", mutates_args=(), device_types="cuda")
+def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    x, w = _f32c(x), _f32c(w)
+    n = x.shape[0]
+    shape = (n, pl.channels, pl.S) if pl.out_layout == "channel" else (n, pl.d_out)
+    out = x.new_zeros(shape) if pl.has_unfed_output else x.new_empty(shape)
+    fwd, _, _ = pl.tables(x.device)
+    if fwd is not None and n > 0:
+        nprob = len(pl._fwd)
+        if pl.fwd_serial:
+            sz = C.sizeof(_lib.GemmProblem)
+            for k in range(nprob):
+                _call("pml_gemm_grouped", _p(x), _p(w), _p(out), fwd.data_ptr() + k * sz, 1, n, n, pl.max_mul_out,
+                      pl.max_d, 1, _stream())
+        else:
+            _call("pml_gemm_grouped", _p(x), _p(w), _p(out), _p(fwd), nprob, n, n, pl.max_mul_out, pl.max_d, 1, _stream())
+    return out
+
+
+@irrep_linear.register_fake
+def _(x, w, plan):
+    pl = plans.get(plan)
+    if pl.out_layout == "channel":
+        return x.new_empty(x.shape[0], pl.channels, pl.S)
+    return x.new_empty(x.shape[0], pl.d_out)
+
+
+@torch.library.custom_op(f"{NS}::irrep_linear_bwd_x", mutates_args=(), device_types="cuda")
+def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    g, w = _f32c(g), _f32c(w)
+    n = g.shape[0]
+    dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else g.new_empty(n, pl.d_in)
+    _, bx, _ = pl.tables(g.device)
+    if bx is not None and n > 0:
+        _call("pml_gemm_grouped", _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, _stream())
+    return dx
+
+
+@irrep_linear_bwd_x.register_fake
+def _(g, w, plan):
+    return g.new_empty(g.shape[0], plans.get(plan).d_in)
+
+
+@torch.library.custom_op(f"{NS}::irrep_linear_bwd_w", mutates_args=(), device_types="cuda")
+def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    x, g = _f32c(x), _f32c(g)
+    n = x.shape[0]
+    dw = x.new_zeros(pl.weight_numel)
+    _, _, bw = pl.tables(x.device)
+    if bw is not None and n > 0:
+        _call("pml_gemm_grouped", _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d,
+              _splitk_for(n), _stream())
+    return dw
+
+
+@irrep_linear_bwd_w.register_fake
+def _(x, g, plan):
+    return x.new_empty(plans.get(plan).weight_numel)
+
+
+def _lin_setup(ctx, inputs, output):
+    x, w, plan = inputs
+    ctx.save_for_backward(x, w)
+    ctx.plan = plan
+
+
+def _lin_bwd(ctx, g):
+    x, w = ctx.saved_tensors
+    nx, nw = ctx.needs_input_grad[:2]
+    return (irrep_linear_bwd_x(g, w, ctx.plan) if nx else None, irrep_linear_bwd_w(x, g, ctx.plan) if nw else None, None)
+
+
+irrep_linear.register_autograd(_lin_bwd, setup_context=_lin_setup)
+
+
+def _lin_bx_setup(ctx, inputs, output):
+    g, w, plan = inputs
+    ctx.save_for_backward(g, w)
+    ctx.plan = plan
+
+
+def _lin_bx_bwd(ctx, v):  # dx = L^T(g; w);  <v, dx> = <L(v; w), g>
+    g, w = ctx.saved_tensors
+    ng, nw = ctx.needs_input_grad[:2]
+    return (irrep_linear(v, w, ctx.plan).reshape(g.shape) if ng else None,
+            irrep_linear_bwd_w(v, g, ctx.plan) if nw else None, None)
+
+
+irrep_linear_bwd_x.register_autograd(_lin_bx_bwd, setup_context=_lin_bx_setup)
+
+
+def _lin_bw_setup(ctx, inputs, output):
+    x, g, plan = inputs
+    ctx.save_for_backward(x, g)
+    ctx.plan = plan
+
+
+def _lin_bw_bwd(ctx, V):  # <V, dw> = <L(x; V), g>
+    x, g = ctx.saved_tensors
+    nx, ng = ctx.needs_input_grad[:2]
+    return (irrep_linear_bwd_x(g, V, ctx.plan) if nx else None,
+            irrep_linear(x, V, ctx.plan).reshape(g.shape) if ng else None, None)
+
+
+irrep_linear_bwd_w.register_autograd(_lin_bw_bwd, setup_context=_lin_bw_setup)
+
+
+# ======================================================================================================================
+# element-indexed linear
+# ======================================================================================================================
+@torch.library.custom_op(f"{NS}::element_linear", mutates_args=(), device_types="cuda")
+def element_linear(x: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    x, attrs, w = _f32c(x), _f32c(attrs), _f32c(w)
+    n = x.shape[0]
+    shape = (n, pl.d_out)
+    if pl.out_layout == "channel":
+        S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
+        shape = (n, pl.d_out // S, S)
+    out = x.new_zeros(shape) if pl.has_unfed_output else x.new_empty(shape)
+    _call("pml_element_linear_fwd", _p(x), _p(attrs), _p(w), C.byref(pl.c_plan), _p(out), n, pl.Z, 0, _stream(), launches=4)
+    return out
+
+
+@element_linear.register_fake
+def _(x, attrs, w, plan):
+    pl = plans.get(plan)
+    if pl.out_layout == "channel":
+        S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
+        return x.new_empty(x.shape[0], pl.d_out // S, S)
+    return x.new_empty(x.shape[0], pl.d_out)
+
+
+@torch.library.custom_op(f"{NS}::element_linear_bwd_x", mutates_args=(), device_types="cuda")
+def element_linear_bwd_x(g: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    g, attrs, w = _f32c(g), _f32c(attrs), _f32c(w)
+    n = g.shape[0]
+    dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else g.new_empty(n, pl.d_in)
+    _call("pml_element_linear_bwd_x", _p(g), _p(attrs), _p(w), C.byref(pl.c_plan), _p(dx), n, pl.Z, 0, _stream(), launches=4)
+    return dx
+
+
+@element_linear_bwd_x.register_fake
+def _(g, attrs, w, plan):
+    return g.new_empty(g.shape[0], plans.get(plan).d_in)
+
+
+@torch.library.custom_op(f"{NS}::element_linear_bwd_w", mutates_args=(), device_types="cuda")
+def element_linear_bwd_w(x: Tensor, g: Tensor, attrs: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    x, g, attrs = _f32c(x), _f32c(g), _f32c(attrs)
+    dw = x.new_empty(pl.weight_numel)
+    _call("pml_element_linear_bwd_w", _p(x), _p(g), _p(attrs), C.byref(pl.c_plan), _p(dw), x.shape[0], pl.Z, 0, _stream(),
+          launches=4)
+    return dw
+
+
+@element_linear_bwd_w.register_fake
+def _(x, g, attrs, plan):
+    return x.new_empty(plans.get(plan).weight_numel)
+
+
+def _el_setup(ctx, inputs, output):
+    x, attrs, w, plan = inputs
+    ctx.save_for_backward(x, attrs, w)
+    ctx.plan = plan
+
+
+def _el_bwd(ctx, g):
+    x, attrs, w = ctx.saved_tensors
+    nx, _, nw = ctx.needs_input_grad[:3]
+    return (element_linear_bwd_x(g, attrs, w, ctx.plan) if nx else None, None,
+            element_linear_bwd_w(x, g, attrs, ctx.plan) if nw else None, None)
+
+
+element_linear.register_autograd(_el_bwd, setup_context=_el_setup)
+
+
+def _el_bx_setup(ctx, inputs, output):
+    g, attrs, w, plan = inputs
+    ctx.save_for_backward(g, attrs, w)
+    ctx.plan = plan
+
+
+def _el_bx_bwd(ctx, v):
+    g, attrs, w = ctx.saved_tensors
+    ng, _, nw = ctx.needs_input_grad[:3]
+    return (element_linear(v, attrs, w, ctx.plan).reshape(g.shape) if ng else None, None,
+            element_linear_bwd_w(v, g, attrs, ctx.plan) if nw else None, None)
+
+
+element_linear_bwd_x.register_autograd(_el_bx_bwd, setup_context=_el_bx_setup)
+
+
+def _el_bw_setup(ctx, inputs, output):
+    x, g, attrs, plan = inputs
+    ctx.save_for_backward(x, g, attrs)
+    ctx.plan = plan
+
+
+def _el_bw_bwd(ctx, V):
+    x, g, attrs = ctx.saved_tensors
+    nx, ng = ctx.needs_input_grad[:2]
+    return (element_linear_bwd_x(g, attrs, V, ctx.plan) if nx else None,
+            element_linear(x, attrs, V, ctx.plan).reshape(g.shape) if ng else None, None, None)
+
+
+element_linear_bwd_w.register_autograd(_el_bw_bwd, setup_context=_el_bw_setup)
+
+
+# ======================================================================================================================
+# symmetric contraction
+# ======================================================================================================================
+@torch.library.custom_op(f"{NS}::sym_contract", mutates_args=(), device_types="cuda")
+def sym_contract(x: Tensor, attrs: Tensor, weights: List[Tensor], plan: int) -> Tensor:
+    pl = plans.get(plan)
+    x, attrs = _f32c(x), _f32c(attrs)
+    ws = [_f32c(w) for w in weights]
+    n = x.shape[0]
+    out = x.new_empty(n, pl.C * pl.DOUT)
+    st = pl.weight_struct(ws)
+    _call("pml_sym_fwd", pl.spec_id, _p(x), _p(attrs), C.byref(st), _p(out), n, pl.C, pl.Z, _stream())
+    return out
+
+
+@sym_contract.register_fake
+def _(x, attrs, weights, plan):
+    pl = plans.get(plan)
+    return x.new_empty(x.shape[0], pl.C * pl.DOUT)
+
+
+@torch.library.custom_op(f"{NS}::sym_contract_bwd", mutates_args=(), device_types="cuda")
+def sym_contract_bwd(x: Tensor, attrs: Tensor, weights: List[Tensor], g: Tensor, plan: int, need_x: bool,
+                     need_w: bool) -> List[Tensor]:
+    """returns [dx, dW_0, dW_1, ...] (empty tensors for what was not requested)"""
+    pl = plans.get(plan)
+    x, attrs, g = _f32c(x), _f32c(attrs), _f32c(g)
+    ws = [_f32c(w) for w in weights]
+    n = x.shape[0]
+    dx = torch.empty_like(x) if need_x else x.new_empty(0)
+    gws = [torch.zeros_like(w) for w in ws] if need_w else None
+    st = pl.weight_struct(ws, gws)
+    if need_x or need_w:
+        _call("pml_sym_bwd", pl.spec_id, _p(x), _p(attrs), C.byref(st), _p(g), _p(dx) if need_x else None, n, pl.C, pl.Z,
+              _stream())
+    return [dx] + (gws if need_w else [x.new_empty(0) for _ in ws])
+
+
+@sym_contract_bwd.register_fake
+def _(x, attrs, weights, g, plan, need_x, need_w):
+    return [torch.empty_like(x) if need_x else x.new_empty(0)] + [
+        torch.empty_like(w) if need_w else x.new_empty(0) for w in weights
+    ]
+
+
+@torch.library.custom_op(f"{NS}::sym_contract_dbl", mutates_args=(), device_types="cuda")
+def sym_contract_dbl(x: Tensor, v: Tensor, attrs: Tensor, weights: List[Tensor], g: Tensor, plan: int, need_g: bool,
+                     need_x: bool, need_w: bool) -> List[Tensor]:
+    """gradient of d/de <g, out(x + e v, W)> w.r.t. (g, x, W): returns [dg, ddx, ddW_0, ...]"""
+    pl = plans.get(plan)
+    x, v, attrs, g = _f32c(x), _f32c(v), _f32c(attrs), _f32c(g)
+    ws = [_f32c(w) for w in weights]
+    n = x.shape[0]
+    dg = torch.empty_like(g) if need_g else x.new_empty(0)
+    ddx = torch.empty_like(x) if need_x else x.new_empty(0)
+    gws = [torch.zeros_like(w) for w in ws] if need_w else None
+    st = pl.weight_struct(ws, gws)
+    if need_g or need_x or need_w:
+        _call("pml_sym_dbl", pl.spec_id, _p(x), _p(v), _p(attrs), C.byref(st), _p(g), _p(dg) if need_g else None,
+              _p(ddx) if need_x else None, n, pl.C, pl.Z, _stream())
+    return [dg, ddx] + (gws if need_w else [x.new_empty(0) for _ in ws])
+
+
+@sym_contract_dbl.register_fake
+def _(x, v, attrs, weights, g, plan, need_g, need_x, need_w):
+    return [torch.empty_like(g) if need_g else x.new_empty(0), torch.empty_like(x) if need_x else x.new_empty(0)] + [
+        torch.empty_like(w) if need_w else x.new_empty(0) for w in weights
+    ]
+
+
+def _sym_setup(ctx, inputs, output):
+    x, attrs, weights, plan = inputs
+    ctx.save_for_backward(x, attrs, *weights)
+    ctx.plan = plan
+
+
+def _sym_bwd(ctx, g):
+    x, attrs, *ws = ctx.saved_tensors
+    nx = ctx.needs_input_grad[0]
+    nw = ctx.needs_input_grad[2]
+    nw_any = any(nw) if isinstance(nw, (list, tuple)) else bool(nw)
+    res = sym_contract_bwd(x, attrs, list(ws), g, ctx.plan, nx, nw_any)
+    return (res[0] if nx else None, None, list(res[1:]) if nw_any else None, None)
+
+
+sym_contract.register_autograd(_sym_bwd, setup_context=_sym_setup)
+
+
+def _sym_bwd_setup(ctx, inputs, output):
+    x, attrs, weights, g, plan, need_x, need_w = inputs
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(x, attrs, g, *weights)
+    ctx.plan = plan
+    ctx.needs = (need_x, need_w)
+
+
+def _sym_bwd_bwd(ctx, grads):
+    # grads: list aligned with the op's output list [dx, dW...]
+    x, attrs, g, *ws = ctx.saved_tensors
+    nx, _, nw, ng = ctx.needs_input_grad[:4]
+    nw_any = any(nw) if isinstance(nw, (list, tuple)) else bool(nw)
+    vx = grads[0] if ctx.needs[0] else None
+    vws = grads[1:] if ctx.needs[1] else [None] * len(ws)
+    gx = gg = None
+    gw = [None] * len(ws)
+    if vx is not None:
+        r = sym_contract_dbl(x, vx, attrs, list(ws), g, ctx.plan, ng, nx, nw_any)
+        gg = r[0] if ng else None
+        gx = r[1] if nx else None
+        if nw_any:
+            gw = list(r[2:])
+    if any(v is not None for v in vws):
+        # Phi is linear in W: <vW, dPhi/dW> = Phi(x, vW, g)
+        vw = [v if v is not None else torch.zeros_like(w) for v, w in zip(vws, ws)]
+        if ng:
+            gg = _acc(gg, sym_contract(x, attrs, vw, ctx.plan))
+        if nx:
+            gx = _acc(gx, sym_contract_bwd(x, attrs, vw, g, ctx.plan, True, False)[0])
+    return (gx, None, gw if nw_any else None, gg, None, None, None)
+
+
+sym_contract_bwd.register_autograd(_sym_bwd_bwd, setup_context=_sym_bwd_setup)
+
+
+# ======================================================================================================================
+# activations, pooling, layout
+# ======================================================================================================================
+@torch.library.custom_op(f"{NS}::act", mutates_args=(), device_types="cuda")
+def act(x: Tensor, kind: int, c: float) -> Tensor:
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    _call("pml_act", _p(x), None, None, float(c), kind, 0, _p(y), x.numel(), _stream())
+    return y
+
+
+@act.register_fake
+def _(x, kind, c):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op(f"{NS}::act_bwd", mutates_args=(), device_types="cuda")
+def act_bwd(g: Tensor, x: Tensor, kind: int, c: float) -> Tensor:
+    g, x = _f32c(g), _f32c(x)
+    y = torch.empty_like(x)
+    _call("pml_act", _p(x), _p(g), None, float(c), kind, 1, _p(y), x.numel(), _stream())
+    return y
+
+
+@act_bwd.register_fake
+def _(g, x, kind, c):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op(f"{NS}::act_bwd2", mutates_args=(), device_types="cuda")
+def act_bwd2(g: Tensor, v: Tensor, x: Tensor, kind: int, c: float) -> Tensor:
+    g, v, x = _f32c(g), _f32c(v), _f32c(x)
+    y = torch.empty_like(x)
+    _call("pml_act", _p(x), _p(g), _p(v), float(c), kind, 2, _p(y), x.numel(), _stream())
+    return y
+
+
+@act_bwd2.register_fake
+def _(g, v, x, kind, c):
+    return torch.empty_like(x)
+
+
+def _act_setup(ctx, inputs, output):
+    x, kind, c = inputs
+    ctx.save_for_backward(x)
+    ctx.kc = (kind, c)
+
+
+act.register_autograd(lambda ctx, g: (act_bwd(g, ctx.saved_tensors[0], *ctx.kc), None, None), setup_context=_act_setup)
+
+
+def _act_bwd_setup(ctx, inputs, output):
+    g, x, kind, c = inputs
+    ctx.save_for_backward(g, x)
+    ctx.kc = (kind, c)
+
+
+def _act_bwd_bwd(ctx, v):
+    g, x = ctx.saved_tensors
+    ng, nx = ctx.needs_input_grad[:2]
+    return (act_bwd(v, x, *ctx.kc) if ng else None, act_bwd2(g, v, x, *ctx.kc) if nx else None, None, None)
+
+
+act_bwd.register_autograd(_act_bwd_bwd, setup_context=_act_bwd_setup)
+
+
+@torch.library.custom_op(f"{NS}::pool_sum", mutates_args=(), device_types="cuda")
+def pool_sum(x: Tensor, batch: Tensor, num_graphs: int) -> Tensor:
+    x = _f32c(x)
+    out = x.new_zeros(num_graphs, x.shape[1])
+    _call("pml_pool_sum", _p(x), _p(batch), _p(out), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+@pool_sum.register_fake
+def _(x, batch, num_graphs):
+    return x.new_empty(num_graphs, x.shape[1])
+
+
+@torch.library.custom_op(f"{NS}::pool_gather", mutates_args=(), device_types="cuda")
+def pool_gather(g: Tensor, batch: Tensor) -> Tensor:
+    g = _f32c(g)
+    out = g.new_empty(batch.numel(), g.shape[1])
+    _call("pml_pool_gather", _p(g), _p(batch), _p(out), batch.numel(), g.shape[1], _stream())
+    return out
+
+
+@pool_gather.register_fake
+def _(g, batch):
+    return g.new_empty(batch.numel(), g.shape[1])
+
+
+def _pool_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[1])
+    ctx.G = inputs[2]
+
+
+pool_sum.register_autograd(lambda ctx, g: (pool_gather(g, ctx.saved_tensors[0]), None, None), setup_context=_pool_setup)
+
+
+def _poolg_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[1])
+    ctx.G = inputs[0].shape[0]
+
+
+pool_gather.register_autograd(lambda ctx, v: (pool_sum(v, ctx.saved_tensors[0], ctx.G), None), setup_context=_poolg_setup)
+
+
+@torch.library.custom_op(f"{NS}::irreps_to_channel", mutates_args=(), device_types="cuda")
+def irreps_to_channel(x: Tensor, channels: int, lmax: int, inverse: bool) -> Tensor:
+    """[N, C*S] irreps layout -> [N, C, S] (inverse=False) or back (inverse=True); irreps_tools.py:47-67."""
+    x = _f32c(x)
+    n, S = x.shape[0], (lmax + 1) ** 2
+    y = x.new_empty(n, channels * S) if inverse else x.new_empty(n, channels, S)
+    _call("pml_irreps_to_channel", _p(x), _p(y), n, channels, lmax, 1 if inverse else 0, _stream())
+    return y
+
+
+@irreps_to_channel.register_fake
+def _(x, channels, lmax, inverse):
+    S = (lmax + 1) ** 2
+    return x.new_empty(x.shape[0], channels * S) if inverse else x.new_empty(x.shape[0], channels, S)
+
+
+def _i2c_setup(ctx, inputs, output):
+    ctx.a = inputs[1:]
+
+
+irreps_to_channel.register_autograd(
+    lambda ctx, g: (irreps_to_channel(g, ctx.a[0], ctx.a[1], not ctx.a[2]), None, None, None), setup_context=_i2c_setup
+)
+
+
+# ======================================================================================================================
+# graph structure (index plumbing only — no floating-point work)
+# ======================================================================================================================
+class EdgePlan:
+    """int32 copies of the edge list and the CSR over the scatter index, built once per batch and shared by every
+    layer's forward and backward kernels."""
+
+    def __init__(self, edge_index: Tensor, num_nodes: int, scatter_row: int = 1, assume_grouped: bool = False) -> None:
+        E = edge_index.shape[1]
+        dev = edge_index.device
+        ei = edge_index.contiguous()
+        self.E, self.N = E, num_nodes
+        self.snd = torch.empty(E, dtype=torch.int32, device=dev)
+        self.rcv = torch.empty(E, dtype=torch.int32, device=dev)
+        _call("pml_split_edge_index", _p(ei), _p(self.snd), _p(self.rcv), E, _stream())
+        self.scatter = self.rcv if scatter_row == 1 else self.snd
+        self.gather = self.snd if scatter_row == 1 else self.rcv
+        counts = torch.zeros(num_nodes, dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+        _call("pml_csr_rowptr", _p(ei[scatter_row]), _p(counts), _p(self.rowptr), E, num_nodes, _stream(), launches=2)
+        if assume_grouped:
+            self.perm = None
+        else:
+            self.perm = torch.argsort(ei[scatter_row], stable=True).to(torch.int32)

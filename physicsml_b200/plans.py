@@ -1,0 +1,268 @@
+"""Host-side plan objects: everything a kernel launch needs that depends only on the irreps configuration.
+
+A plan is built once per module (fp64 on the host), owns the small device tables the C ABI wants and is referred to
+from the ``torch.library`` ops by an integer handle (custom ops cannot take Python objects).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib, so3
+
+_PLANS: list = []
+
+
+def register(plan) -> int:
+    _PLANS.append(plan)
+    return len(_PLANS) - 1
+
+
+def get(handle: int):
+    return _PLANS[handle]
+
+
+def _upload(structs, device) -> torch.Tensor:
+    """ctypes array -> uint8 device tensor (synchronous copy; done once per plan and device)."""
+    raw = bytes(structs)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    return t.to(device)
+
+
+class LinearPlan:
+    """o3.Linear semantics: y[n, o, w, m] = alpha_o * sum_{paths i->o} sum_u W[u, w] x[n, i, u, m],
+    alpha_o = scale / sqrt(sum_{paths into o} mul_in).  Also covers nn.FullyConnectedNet layers (scalar irreps).
+
+    out_layout "irreps": [N, sum mul*(2l+1)] ; "channel": [N, C, S] with S = sum (2l+1) over the output blocks
+    (the reference's ``reshape_irreps``, irreps_tools.py:47-67, fused into the GEMM's output strides).
+    """
+
+    def __init__(self, irreps_in, irreps_out, scale: float = 1.0, out_layout: str = "irreps") -> None:
+        self.irreps_in = so3.parse_irreps(irreps_in)
+        self.irreps_out = so3.parse_irreps(irreps_out)
+        self.scale = float(scale)
+        self.out_layout = out_layout
+        self.d_in = so3.irreps_dim(self.irreps_in)
+        self.d_out = so3.irreps_dim(self.irreps_out)
+        in_off = so3.irreps_offsets(self.irreps_in)
+        paths = []
+        w_off = 0
+        for i, (mi, li, pi) in enumerate(self.irreps_in):
+            for o, (mo, lo, po) in enumerate(self.irreps_out):
+                if (li, pi) == (lo, po):
+                    paths.append((i, o, w_off))
+                    w_off += mi * mo
+        self.paths = paths
+        self.weight_numel = w_off
+        fan_in = [0] * len(self.irreps_out)
+        for i, o, _ in paths:
+            fan_in[o] += self.irreps_in[i][0]
+        self.alpha = [self.scale / math.sqrt(f) if f > 0 else 0.0 for f in fan_in]
+        # output addressing
+        if out_layout == "irreps":
+            o_off = so3.irreps_offsets(self.irreps_out)
+            o_cs = [2 * l + 1 for _, l, _ in self.irreps_out]
+            self.out_row = self.d_out
+        elif out_layout == "channel":
+            muls = {m for m, _, _ in self.irreps_out}
+            if len(muls) != 1:
+                raise ValueError("channel layout needs equal multiplicities")
+            S = sum(2 * l + 1 for _, l, _ in self.irreps_out)
+            o_off, acc = [], 0
+            for _, l, _ in self.irreps_out:
+                o_off.append(acc)
+                acc += 2 * l + 1
+            o_cs = [S] * len(self.irreps_out)
+            self.out_row = self.d_out
+            self.channels, self.S = muls.pop(), S
+        else:
+            raise ValueError(out_layout)
+        self.has_unfed_output = any(f == 0 for f in fan_in)
+        self.max_mul_in = max(m for m, _, _ in self.irreps_in)
+        self.max_mul_out = max(m for m, _, _ in self.irreps_out)
+        self.max_d = max(2 * l + 1 for _, l, _ in self.irreps_out)
+
+        def prob():
+            p = _lib.GemmProblem()
+            for c in range(_lib.GEMM_MAX_CHUNKS):
+                p.cscale[c] = 1.0
+            return p
+
+        # ---- forward: one problem per fed output block; chunks = its input blocks
+        fwd = []
+        for o, (mo, lo, _) in enumerate(self.irreps_out):
+            ch = [(i, w) for i, oo, w in paths if oo == o]
+            if not ch:
+                continue
+            d = 2 * lo + 1
+            for c0 in range(0, len(ch), _lib.GEMM_MAX_CHUNKS):
+                sub = ch[c0 : c0 + _lib.GEMM_MAX_CHUNKS]
+                p = prob()
+                p.nchunks = len(sub)
+                for c, (i, w) in enumerate(sub):
+                    p.a_off[c], p.b_off[c], p.kc[c] = in_off[i], w, self.irreps_in[i][0]
+                p.c_off = o_off[o]
+                p.a_rs, p.a_cs, p.a_bs = self.d_in, d, 1
+                p.b_rs, p.b_cs, p.b_bs = mo, 1, 0
+                p.c_rs, p.c_cs, p.c_bs = self.out_row, o_cs[o], 1
+                p.M, p.N, p.nbatch, p.alpha = -1, mo, d, self.alpha[o]
+                p.accumulate = 1 if c0 > 0 else 0
+                fwd.append(p)
+        # problems that accumulate onto an earlier problem's C would race inside one launch
+        self.fwd_serial = any(p.accumulate for p in fwd)
+        self._fwd = fwd
+        # ---- dx: one problem per fed input block; chunks = the output blocks it feeds (per-chunk alpha)
+        bx = []
+        for i, (mi, li, _) in enumerate(self.irreps_in):
+            ch = [(o, w) for ii, o, w in paths if ii == i]
+            if not ch:
+                continue
+            if len(ch) > _lib.GEMM_MAX_CHUNKS:
+                raise NotImplementedError("an input block feeding more than 8 output blocks")
+            d = 2 * li + 1
+            p = prob()
+            p.nchunks = len(ch)
+            for c, (o, w) in enumerate(ch):
+                p.a_off[c], p.b_off[c], p.kc[c], p.cscale[c] = o_off[o], w, self.irreps_out[o][0], self.alpha[o]
+            p.c_off = in_off[i]
+            # A = g (same addressing as the forward's C); all chunks of one input block share the output irrep's strides
+            o0 = ch[0][0]
+            p.a_rs, p.a_cs, p.a_bs = self.out_row, o_cs[o0], 1
+            mo = self.irreps_out[o0][0]
+            if any(self.irreps_out[o][0] != mo for o, _ in ch):
+                raise NotImplementedError("output blocks of one irrep with different multiplicities")
+            p.b_rs, p.b_cs, p.b_bs = 1, mo, 0  # B[k = w, col = u] = W[u, w]
+            p.c_rs, p.c_cs, p.c_bs = self.d_in, d, 1
+            p.M, p.N, p.nbatch, p.alpha, p.accumulate = -1, mi, d, 1.0, 0
+            bx.append(p)
+        self.has_unfed_input = len(bx) < len(self.irreps_in)
+        self._bwd_x = bx
+        # ---- dW: one problem per path, K = nodes (runtime), the (2l+1) batches reduce into the same C (atomic epilogue)
+        bw = []
+        for i, o, w in paths:
+            mi, li, _ = self.irreps_in[i]
+            mo = self.irreps_out[o][0]
+            d = 2 * li + 1
+            p = prob()
+            p.nchunks = 1
+            p.a_off[0], p.b_off[0], p.kc[0] = in_off[i], o_off[o], -1
+            p.c_off = w
+            p.a_rs, p.a_cs, p.a_bs = d, self.d_in, 1  # A[u, k = n] = x[n, in_off + u d + m]
+            p.b_rs, p.b_cs, p.b_bs = self.out_row, o_cs[o], 1  # B[k = n, w] = g[n, o_off + w cs + m]
+            p.c_rs, p.c_cs, p.c_bs = mo, 1, 0
+            p.M, p.N, p.nbatch, p.alpha, p.accumulate = mi, mo, d, self.alpha[o], 0
+            bw.append(p)
+        self._bwd_w = bw
+        self._dev: dict = {}
+        self.handle = register(self)
+
+    def tables(self, device):
+        key = str(device)
+        if key not in self._dev:
+            def up(lst):
+                if not lst:
+                    return None
+                return _upload((_lib.GemmProblem * len(lst))(*lst), device)
+
+            self._dev[key] = (up(self._fwd), up(self._bwd_x), up(self._bwd_w))
+        return self._dev[key]
+
+
+class ElementLinearPlan:
+    """FullyConnectedTensorProduct(x, Zx0e attrs) semantics."""
+
+    def __init__(self, irreps_in, num_elements: int, irreps_out, out_layout: str = "irreps") -> None:
+        self.irreps_in = so3.parse_irreps(irreps_in)
+        self.irreps_out = so3.parse_irreps(irreps_out)
+        self.Z = int(num_elements)
+        self.d_in = so3.irreps_dim(self.irreps_in)
+        self.d_out = so3.irreps_dim(self.irreps_out)
+        self.out_layout = out_layout
+        in_off = so3.irreps_offsets(self.irreps_in)
+        if out_layout == "irreps":
+            o_off = so3.irreps_offsets(self.irreps_out)
+            o_ws = [2 * l + 1 for _, l, _ in self.irreps_out]
+        else:
+            S = sum(2 * l + 1 for _, l, _ in self.irreps_out)
+            o_off, acc = [], 0
+            for _, l, _ in self.irreps_out:
+                o_off.append(acc)
+                acc += 2 * l + 1
+            o_ws = [S] * len(self.irreps_out)
+        paths, w_off = [], 0
+        for i, (mi, li, pi) in enumerate(self.irreps_in):
+            for o, (mo, lo, po) in enumerate(self.irreps_out):
+                if (li, pi) == (lo, po):
+                    paths.append((i, o, w_off))
+                    w_off += mi * self.Z * mo
+        self.weight_numel = w_off
+        fan = [0] * len(self.irreps_out)
+        for i, o, _ in paths:
+            fan[o] += self.irreps_in[i][0] * self.Z
+        if len(paths) > _lib.EL_MAX_PATHS:
+            raise NotImplementedError("more than 8 element-linear paths")
+        outs = [o for _, o, _ in paths]
+        if len(set(outs)) != len(outs):
+            raise NotImplementedError("several input blocks feeding one output block")
+        self.has_unfed_output = len(set(outs)) < len(self.irreps_out)
+        self.has_unfed_input = len({i for i, _, _ in paths}) < len(self.irreps_in)
+        p = _lib.ElPlan()
+        p.npaths = len(paths)
+        for k, (i, o, w) in enumerate(paths):
+            mi, li, _ = self.irreps_in[i]
+            p.d[k], p.mul_in[k], p.mul_out[k] = 2 * li + 1, mi, self.irreps_out[o][0]
+            p.w_off[k], p.x_off[k], p.o_off[k], p.o_ws[k] = w, in_off[i], o_off[o], o_ws[o]
+            p.alpha[k] = 1.0 / math.sqrt(fan[o])
+        p.x_rs, p.o_rs = self.d_in, self.d_out
+        self.c_plan = p
+        self.handle = register(self)
+
+
+class TPPlan:
+    def __init__(self, node_irreps, sh_lmax: int, target_irreps, sh_parity: int = -1) -> None:
+        self.spec = so3.build_tp_spec(node_irreps, sh_lmax, target_irreps, sh_parity)
+        muls = {m for m, _, _ in so3.parse_irreps(node_irreps)}
+        self.C = muls.pop()
+        reg = _lib.registry()["tp"]
+        if self.spec.key not in reg:
+            raise NotImplementedError(
+                f"no compiled tensor-product specialisation for {self.spec.key}; add it to "
+                "physicsml_b200.codegen.default_tp_specs() and rebuild"
+            )
+        self.spec_id = reg[self.spec.key]["id"]
+        self.NP, self.DIN, self.DOUT, self.NSH = self.spec.n_paths, self.spec.d_in, self.spec.d_out, self.spec.n_sh
+        # irreps of the aggregated message, sorted, one block per path (mul C each)
+        self.out_irreps = [(self.C, l, p) for l, p in self.spec.out_ls]
+        self.handle = register(self)
+
+
+class SymPlan:
+    def __init__(self, lmax: int, outs, corr: int, channels: int, num_elements: int) -> None:
+        from .codegen import SymSpec
+
+        self.spec = SymSpec(lmax, outs, corr)
+        reg = _lib.registry()["sym"]
+        if self.spec.key not in reg:
+            raise NotImplementedError(
+                f"no compiled symmetric-contraction specialisation for {self.spec.key}; add it to "
+                "physicsml_b200.codegen.default_sym_specs() and rebuild"
+            )
+        self.spec_id = reg[self.spec.key]["id"]
+        self.K = self.spec.K  # [out][nu-1]
+        self.S, self.DOUT, self.C, self.Z, self.corr = self.spec.S, self.spec.d_out, channels, num_elements, corr
+        self.n_out = len(self.spec.outs)
+        self.handle = register(self)
+
+    def weight_struct(self, weights, grads=None):
+        """weights: flat list ordered (out a, nu = 1..corr)."""
+        st = _lib.SymWeights()
+        k = 0
+        for a in range(self.n_out):
+            for nu in range(self.corr):
+                st.w[a][nu] = weights[k].data_ptr()
+                st.gw[a][nu] = grads[k].data_ptr() if grads is not None else None
+                st.K[a][nu] = self.K[a][nu]
+                k += 1
+        return st

@@ -1,0 +1,299 @@
+"""GPU parity of every custom op (called through the C ABI) against the oracle's dense PyTorch restatement of the
+same op, evaluated on the same device in fp32 (and fp64 where cancellation matters).  Tolerances are stated inline."""
+import math
+
+import pytest
+import torch
+
+import helpers  # noqa: F401  (sets sys.path for the oracle shims)
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _edges(N, deg, gen, device):
+    snd = torch.randint(0, N, (N * deg,), generator=gen)
+    rcv = torch.randint(0, N, (N * deg,), generator=gen)
+    return torch.stack([snd, rcv]).to(device)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lmax", [1, 2, 3])
+@pytest.mark.parametrize("pbc", [False, True])
+def test_edge_featurise(cuda, lmax, pbc):
+    from e3nn import o3
+    from oracle.ref_model import _Radial, edge_vectors
+    from physicsml_b200 import ops
+
+    g = torch.Generator().manual_seed(lmax + 10 * pbc)
+    N, E = 50, 700
+    pos = (torch.rand(N, 3, generator=g) * 6).to(cuda)
+    ei = _edges(N, 14, g, cuda)
+    ei = ei[:, ei[0] != ei[1]]
+    cell = shift = None
+    if pbc:
+        cell = (torch.eye(3) * 6 + 0.3 * torch.rand(3, 3, generator=g)).to(cuda)
+        shift = torch.randint(-1, 2, (ei.shape[1], 3), generator=g).float().to(cuda)
+    rc, p, nb = 5.0, 5, 8
+    rad = _Radial(rc, nb, p).to(cuda)
+    sh = o3.SphericalHarmonics(o3.Irreps.spherical_harmonics(lmax), normalize=True, normalization="component")
+    plan = ops.EdgePlan(ei, N)
+
+    pos_r = pos.clone().requires_grad_(True)
+    d, r = edge_vectors(pos_r, ei, cell, shift)
+    Yr, Br = sh(r), rad(d)
+    pos_t = pos.clone().requires_grad_(True)
+    Y, B = ops.edge_featurise(pos_t, plan.snd, plan.rcv, shift, cell, rad.bessel_fn.bessel_weights, rc, rad.bessel_fn.pref, 1.0, p, lmax)
+    assert (Y - Yr).abs().max() < 2e-6  # fp32 polynomial evaluation, |Y| <= sqrt(7)
+    assert (B - Br).abs().max() < 2e-6 * max(1.0, Br.abs().max().item())
+    gY, gB = torch.randn(Y.shape, generator=g).to(cuda), torch.randn(B.shape, generator=g).to(cuda)
+    (gr,) = torch.autograd.grad([Yr, Br], [pos_r], [gY, gB])
+    gY_t, gB_t = gY.clone().requires_grad_(True), gB.clone().requires_grad_(True)
+    (gt,) = torch.autograd.grad([Y, B], [pos_t], [gY_t, gB_t], create_graph=True)
+    assert _rel(gt, gr) < 2e-5
+    # tangent map = transpose of the cotangent map: <v, J^T g> == <J v, g>
+    v = torch.randn(N, 3, generator=g).to(cuda)
+    tY, tB = torch.autograd.grad([gt], [gY_t, gB_t], [v])
+    lhs = (v * gt.detach()).sum().item()
+    rhs = ((tY * gY).sum() + (tB * gB).sum()).item()
+    assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+TP_CASES = [
+    ("4x0e", 2, 4), ("4x0e+4x1o", 2, 4), ("32x0e+32x1o", 2, 32), ("8x0e+8x1o", 3, 8),
+    ("128x0e+128x1o", 3, 128), ("40x0e", 3, 40), ("16x0e+16x1o+16x2e", 3, 16),
+]
+
+
+def _ref_tp(node_irreps, lmax, C):
+    from e3nn import o3
+    from oracle.ref_model import uvu_instructions
+
+    node = o3.Irreps(node_irreps)
+    sh = o3.Irreps.spherical_harmonics(lmax)
+    target = (sh * C).sort().irreps.simplify()
+    tp_irreps, ins = uvu_instructions(node, sh, target)
+    return o3.TensorProduct(node, sh, tp_irreps, instructions=ins, shared_weights=False, internal_weights=False), target
+
+
+@pytest.mark.parametrize("node_irreps,lmax,C", TP_CASES)
+def test_tp_scatter(cuda, node_irreps, lmax, C):
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import TPPlan
+
+    g = torch.Generator().manual_seed(7)
+    N, deg = 37, 9
+    ei = _edges(N, deg, g, cuda)
+    E = ei.shape[1]
+    tp_ref, target = _ref_tp(node_irreps, lmax, C)
+    tp_ref = tp_ref.to(cuda)
+    plan = TPPlan(node_irreps, lmax, str(target))
+    h = torch.randn(N, tp_ref.irreps_in1.dim, generator=g).to(cuda).requires_grad_(True)
+    Y = torch.randn(E, (lmax + 1) ** 2, generator=g).to(cuda).requires_grad_(True)
+    R = torch.randn(E, tp_ref.weight_numel, generator=g).to(cuda).requires_grad_(True)
+    assert tp_ref.weight_numel == plan.NP * C
+
+    def ref(h, Y, R):
+        m = tp_ref(h[ei[0]], Y, R)
+        return torch.zeros(N, m.shape[1], device=cuda, dtype=m.dtype).index_add_(0, ei[1], m)
+
+    ep = ops.EdgePlan(ei, N)
+    out = ops.tp_scatter(h, Y, R, ep.gather, ep.rowptr, ep.perm, plan.handle)
+    out_r = ref(h, Y, R)
+    assert _rel(out, out_r) < 1e-5
+    w = torch.randn(out.shape, generator=g).to(cuda).requires_grad_(True)
+    gs = torch.autograd.grad([out], [h, Y, R], [w], create_graph=True)
+    gr = torch.autograd.grad([out_r], [h, Y, R], [w], create_graph=True)
+    for a, b in zip(gs, gr):
+        assert _rel(a, b) < 1e-5
+    # second order: differentiate <v, grads> w.r.t. everything
+    vs = [torch.randn(a.shape, generator=g).to(cuda) for a in gs]
+    s = sum((a * v).sum() for a, v in zip(gs, vs))
+    sr = sum((a * v).sum() for a, v in zip(gr, vs))
+    g2 = torch.autograd.grad(s, [h, Y, R, w])
+    g2r = torch.autograd.grad(sr, [h, Y, R, w])
+    for a, b in zip(g2, g2r):
+        assert _rel(a, b) < 2e-5
+
+
+def test_tp_scatter_grouped_edges(cuda):
+    """perm=None fast path (edges already grouped by receiver)"""
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import TPPlan
+
+    g = torch.Generator().manual_seed(3)
+    N, C, lmax = 20, 8, 2
+    ei = _edges(N, 6, g, cuda)
+    ei = ei[:, torch.argsort(ei[1], stable=True)]
+    tp_ref, target = _ref_tp("8x0e+8x1o", lmax, C)
+    tp_ref = tp_ref.to(cuda)
+    plan = TPPlan("8x0e+8x1o", lmax, str(target))
+    E = ei.shape[1]
+    h = torch.randn(N, 32, generator=g).to(cuda)
+    Y = torch.randn(E, 9, generator=g).to(cuda)
+    R = torch.randn(E, plan.NP * C, generator=g).to(cuda)
+    ep = ops.EdgePlan(ei, N, assume_grouped=True)
+    out = ops.tp_scatter(h, Y, R, ep.gather, ep.rowptr, None, plan.handle)
+    m = tp_ref(h[ei[0]], Y, R)
+    ref = torch.zeros(N, m.shape[1], device=cuda).index_add_(0, ei[1], m)
+    assert _rel(out, ref) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------------------------
+LIN_CASES = [
+    ("4x0e", "4x0e", "irreps"), ("8x0e+8x1o", "8x0e+8x1o", "irreps"), ("64x0e+96x1o+64x2e", "32x0e+32x1o+32x2e", "irreps"),
+    ("64x0e+96x1o+64x2e", "32x0e+32x1o+32x2e", "channel"), ("32x0e+32x1o", "1x0e", "irreps"), ("8x0e", "70x0e", "irreps"),
+    ("256x0e+384x1o+384x2e+256x3o", "128x0e+128x1o+128x2e+128x3o", "channel"),
+]
+
+
+@pytest.mark.parametrize("irr_in,irr_out,layout", LIN_CASES)
+@pytest.mark.parametrize("N", [1, 77, 300])
+def test_irrep_linear(cuda, irr_in, irr_out, layout, N):
+    from e3nn import o3
+    from oracle.ref_model import to_channel_major
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import LinearPlan
+
+    g = torch.Generator().manual_seed(11)
+    ref = o3.Linear(o3.Irreps(irr_in), o3.Irreps(irr_out)).to(cuda)
+    plan = LinearPlan(irr_in, irr_out, scale=0.37, out_layout=layout)
+    assert plan.weight_numel == ref.weight_numel
+    x = torch.randn(N, ref.irreps_in.dim, generator=g).to(cuda).requires_grad_(True)
+    w = ref.weight.detach().clone().requires_grad_(True)
+    y = ops.irrep_linear(x, w, plan.handle)
+    ref.weight.data.copy_(w.data)
+    yr = ref(x) * 0.37
+    if layout == "channel":
+        yr = to_channel_major(yr, ref.irreps_out)
+    assert _rel(y, yr) < 1e-5
+    gy = torch.randn(y.shape, generator=g).to(cuda).requires_grad_(True)
+    gs = torch.autograd.grad([y], [x, w], [gy], create_graph=True)
+    gr = torch.autograd.grad([yr], [x, ref.weight], [gy], create_graph=True)
+    for a, b in zip(gs, gr):
+        assert _rel(a, b) < 2e-5
+    vs = [torch.randn(a.shape, generator=g).to(cuda) for a in gs]
+    g2 = torch.autograd.grad(sum((a * v).sum() for a, v in zip(gs, vs)), [x, w, gy])
+    g2r = torch.autograd.grad(sum((a * v).sum() for a, v in zip(gr, vs)), [x, ref.weight, gy])
+    for a, b in zip(g2, g2r):
+        assert _rel(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("irr_in,irr_out,layout", [
+    ("8x0e+8x1o+8x2e", "8x0e+8x1o+8x2e", "irreps"), ("8x0e+8x1o+8x2e", "8x0e+8x1o+8x2e", "channel"),
+    ("32x0e+32x1o", "32x0e", "irreps"), ("128x0e+128x1o+128x2e+128x3o", "128x0e+128x1o+128x2e+128x3o", "channel"),
+])
+@pytest.mark.parametrize("onehot", [True, False])
+def test_element_linear(cuda, irr_in, irr_out, layout, onehot):
+    from e3nn import o3
+    from oracle.ref_model import to_channel_major
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import ElementLinearPlan
+
+    g = torch.Generator().manual_seed(5)
+    Z, N = 5, 61
+    ref = o3.FullyConnectedTensorProduct(o3.Irreps(irr_in), o3.Irreps(f"{Z}x0e"), o3.Irreps(irr_out)).to(cuda)
+    plan = ElementLinearPlan(irr_in, Z, irr_out, out_layout=layout)
+    assert plan.weight_numel == ref.weight_numel
+    x = torch.randn(N, ref.irreps_in1.dim, generator=g).to(cuda).requires_grad_(True)
+    if onehot:
+        attrs = torch.nn.functional.one_hot(torch.randint(0, Z, (N,), generator=g), Z).float().to(cuda)
+    else:
+        attrs = torch.randn(N, Z, generator=g).to(cuda)
+    w = ref.weight.detach().clone().requires_grad_(True)
+    y = ops.element_linear(x, attrs, w, plan.handle)
+    yr = ref(x, attrs)
+    if layout == "channel":
+        yr = to_channel_major(yr, ref.irreps_out)
+    assert _rel(y, yr) < 1e-5
+    gy = torch.randn(y.shape, generator=g).to(cuda).requires_grad_(True)
+    gs = torch.autograd.grad([y], [x, w], [gy], create_graph=True)
+    gr = torch.autograd.grad([yr], [x, ref.weight], [gy], create_graph=True)
+    for a, b in zip(gs, gr):
+        assert _rel(a, b) < 2e-5
+    vs = [torch.randn(a.shape, generator=g).to(cuda) for a in gs]
+    g2 = torch.autograd.grad(sum((a * v).sum() for a, v in zip(gs, vs)), [x, w, gy])
+    g2r = torch.autograd.grad(sum((a * v).sum() for a, v in zip(gr, vs)), [x, ref.weight, gy])
+    for a, b in zip(g2, g2r):
+        assert _rel(a, b) < 2e-5
+
+
+# --------------------------------------------------------------------------------------------------------------------
+SYM_CASES = [(2, "4x0e+4x1o", 2, 4), (2, "4x0e", 2, 4), (2, "32x0e+32x1o", 3, 32), (3, "16x0e+16x1o", 3, 16),
+             (3, "128x0e", 3, 128), (3, "8x0e+8x1o+8x2e", 3, 8)]
+
+
+@pytest.mark.parametrize("lmax,hidden,corr,C", SYM_CASES)
+@pytest.mark.parametrize("onehot", [True, False])
+def test_sym_contract(cuda, lmax, hidden, corr, C, onehot):
+    from e3nn import o3
+    from oracle.ref_model import _SymContraction
+    from physicsml_b200.mace import SymmetricContraction
+
+    g = torch.Generator().manual_seed(13)
+    Z, N = 4, 23
+    inter = (o3.Irreps.spherical_harmonics(lmax) * C).sort().irreps.simplify()
+    torch.manual_seed(0)
+    ref = _SymContraction(inter, o3.Irreps(hidden), corr, Z).to(cuda)
+    mine = SymmetricContraction(str(inter), hidden, corr, Z).to(cuda)
+    mine.load_state_dict(ref.state_dict())
+    S = (lmax + 1) ** 2
+    x = torch.randn(N, C, S, generator=g).to(cuda).requires_grad_(True)
+    if onehot:
+        attrs = torch.nn.functional.one_hot(torch.randint(0, Z, (N,), generator=g), Z).float().to(cuda)
+    else:
+        attrs = torch.randn(N, Z, generator=g).to(cuda)
+    y, yr = mine(x, attrs), ref(x, attrs)
+    assert _rel(y, yr) < 2e-5
+    pm = [p for p in mine.parameters() if p.requires_grad]
+    pr = [p for p in ref.parameters() if p.requires_grad]
+    gy = torch.randn(y.shape, generator=g).to(cuda).requires_grad_(True)
+    gs = torch.autograd.grad([y], [x] + pm, [gy], create_graph=True)
+    gr = torch.autograd.grad([yr], [x] + pr, [gy], create_graph=True)
+    for a, b in zip(gs, gr):
+        assert _rel(a, b) < 5e-5
+    # second order through the x-cotangent (what force-matching training differentiates)
+    v = torch.randn(x.shape, generator=g).to(cuda)
+    g2 = torch.autograd.grad((gs[0] * v).sum(), [x, gy] + pm)
+    g2r = torch.autograd.grad((gr[0] * v).sum(), [x, gy] + pr)
+    for a, b in zip(g2, g2r):
+        assert _rel(a, b) < 1e-4
+
+
+def test_act_and_pool(cuda):
+    from physicsml_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    x = (3 * torch.randn(1000, generator=g)).to(cuda).requires_grad_(True)
+    c = 1.6791767923989418
+    y = ops.act(x, 0, c)
+    yr = c * torch.nn.functional.silu(x)
+    assert (y - yr).abs().max() < 1e-5
+    gy = torch.randn(1000, generator=g).to(cuda).requires_grad_(True)
+    (a,) = torch.autograd.grad(y, x, gy, create_graph=True)
+    (b,) = torch.autograd.grad(yr, x, gy, create_graph=True)
+    assert (a - b).abs().max() < 1e-5
+    v = torch.randn(1000, generator=g).to(cuda)
+    a2 = torch.autograd.grad((a * v).sum(), [x, gy])
+    b2 = torch.autograd.grad((b * v).sum(), [x, gy])
+    for p, q in zip(a2, b2):
+        assert (p - q).abs().max() < 1e-5
+    batch = torch.sort(torch.randint(0, 7, (200,), generator=g)).values.to(cuda)
+    f = torch.randn(200, 3, generator=g).to(cuda).requires_grad_(True)
+    out = ops.pool_sum(f, batch, 7)
+    ref = torch.zeros(7, 3, device=cuda).index_add_(0, batch, f)
+    assert (out - ref).abs().max() < 1e-5
+    (gf,) = torch.autograd.grad(out.pow(2).sum(), f)
+    (gfr,) = torch.autograd.grad(ref.pow(2).sum(), f)
+    assert (gf - gfr).abs().max() < 1e-4
+
+
+def test_cpu_tensors_fail_loudly():
+    from physicsml_b200 import ops
+
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.act(torch.randn(4), 0, 1.0)
