@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(128) el_bwd_x_kernel(const float* __restrict__
   }
 }
 
-// dW[u, v, w] = alpha * sum_n a[n, v] sum_m x[n, u, m] g[n, w, m]   — one CTA per (path, v, 16x16 tile of (u, w)),
-// looping over the nodes: deterministic, no atomics.
+// dW[u, v, w] = alpha * sum_n a[n, v] sum_m x[n, u, m] g[n, w, m]   — one CTA per (path, v, 16x16 tile of (u, w),
+// chunk of nodes); chunk partials are combined with fp32 atomics (dW zero-initialised by the caller).
 template <int D>
 __global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                        const float* __restrict__ attrs, pml_el_plan P,
-                                                       float* __restrict__ dW, int N, int Z, int accumulate) {
+                                                       float* __restrict__ dW, int N, int Z, int chunk) {
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
   if (P.d[p] != D) return;
   const int MI = P.mul_in[p], MO = P.mul_out[p];
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__
   const bool ok = (u < MI) && (w < MO);
   __shared__ float xs[16 * 7], gs[16 * 7];
   float acc = 0.f;
-  for (int n = 0; n < N; ++n) {
+  const int n_beg = blockIdx.y * chunk, n_end = min(N, n_beg + chunk);
+  for (int n = n_beg; n < n_end; ++n) {
     const float a = __ldg(attrs + (size_t)n * Z + v);
     if (a == 0.f) continue;  // uniform across the CTA
     __syncthreads();
@@ -153,17 +154,19 @@ __global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__
     for (int m = 0; m < D; ++m) s = fmaf(xs[(threadIdx.x >> 4) * D + m], gs[(threadIdx.x & 15) * D + m], s);
     acc = fmaf(a, s, acc);
   }
-  if (ok) {
-    float* o = dW + P.w_off[p] + ((size_t)u * Z + v) * MO + w;
-    const float r = P.alpha[p] * acc;
-    *o = accumulate ? *o + r : r;
-  }
+  if (ok && acc != 0.f) atomicAdd(dW + P.w_off[p] + ((size_t)u * Z + v) * MO + w, P.alpha[p] * acc);
 }
 
 }  // namespace pml
 
+static inline bool pml_el_has_d(const pml_el_plan* plan, int d) {
+  for (int p = 0; p < plan->npaths; ++p)
+    if (plan->d[p] == d) return true;
+  return false;
+}
 #define PML_EL_FOR_D(CALL) \
-  CALL(1) CALL(3) CALL(5) CALL(7)
+  if (pml_el_has_d(plan, 1)) { CALL(1) } if (pml_el_has_d(plan, 3)) { CALL(3) } \
+  if (pml_el_has_d(plan, 5)) { CALL(5) } if (pml_el_has_d(plan, 7)) { CALL(7) }
 
 extern "C" int pml_element_linear_fwd(const float* x, const float* attrs, const float* W, const pml_el_plan* plan,
                                       float* out, int N, int Z, int accumulate, cudaStream_t stream) {
@@ -191,16 +194,24 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
   return PML_OK;
 }
 
+// dW must be zero-initialised by the caller (node-chunk partials are accumulated atomically).
 extern "C" int pml_element_linear_bwd_w(const float* x, const float* g, const float* attrs, const pml_el_plan* plan,
                                         float* dW, int N, int Z, int accumulate, cudaStream_t stream) {
-  if (plan->npaths <= 0) return PML_OK;
+  (void)accumulate;
+  if (plan->npaths <= 0 || N <= 0) return PML_OK;
   int max_t = 0;
   for (int p = 0; p < plan->npaths; ++p) {
     const int t = ((plan->mul_in[p] + 15) / 16) * ((plan->mul_out[p] + 15) / 16);
     max_t = t > max_t ? t : max_t;
   }
-  dim3 grid(max_t, 1, plan->npaths * Z);
-#define CALL(D) pml::el_bwd_w_kernel<D><<<grid, 256, 0, stream>>>(x, g, attrs, *plan, dW, N, Z, accumulate);
+  // enough node chunks to fill the machine (~4 CTAs per SM), at least 32 nodes each
+  int chunks = (4 * 148 + max_t * plan->npaths * Z - 1) / (max_t * plan->npaths * Z);
+  if (chunks < 1) chunks = 1;
+  int chunk = (N + chunks - 1) / chunks;
+  if (chunk < 32) chunk = 32;
+  chunks = (N + chunk - 1) / chunk;
+  dim3 grid(max_t, chunks, plan->npaths * Z);
+#define CALL(D) pml::el_bwd_w_kernel<D><<<grid, 256, 0, stream>>>(x, g, attrs, *plan, dW, N, Z, chunk);
   PML_EL_FOR_D(CALL)
 #undef CALL
   PML_CHECK_LAUNCH();

@@ -37,9 +37,27 @@ def _f32c(t: Tensor) -> Tensor:
     return t.contiguous()
 
 
+# optional per-kernel device timing (bench.py): name -> list of (tag, start_event, end_event)
+KERNEL_TIMING: dict = {}
+
+
+def enable_kernel_timing(names) -> None:
+    KERNEL_TIMING.clear()
+    for n in names:
+        KERNEL_TIMING[n] = []
+
+
 def _call(name: str, *args, launches: int = 1) -> None:
     LAUNCHES[0] += launches
+    rec = KERNEL_TIMING.get(name)
+    if rec is None:
+        _lib.check(getattr(_lib.lib(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _lib.check(getattr(_lib.lib(), name)(*args), name)
+    e1.record()
+    rec.append((args[0], e0, e1))
 
 
 # ======================================================================================================================
@@ -277,8 +295,10 @@ tp_scatter_bwd.register_autograd(_tp_bwd_bwd, setup_context=_tp_bwd_setup)
 # ======================================================================================================================
 # per-irrep linear (grouped GEMM)
 # ======================================================================================================================
-def _splitk_for(n_rows: int) -> int:
-    return max(1, min(64, (n_rows + 2047) // 2048))
+def _splitk_for(k_extent: int, ctas_without_split: int) -> int:
+    """split the reduction so that ~4 CTAs per SM are in flight, keeping >= 4 k-tiles (of 16) per CTA"""
+    want = (4 * 148 + ctas_without_split - 1) // max(1, ctas_without_split)
+    return max(1, min(want, max(1, k_extent // 64), 4096))
 
 
 @torch.library.custom_op(f"{NS}::irrep_linear", mutates_args=(), device_types="cuda")
@@ -334,8 +354,9 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
     dw = x.new_zeros(pl.weight_numel)
     _, _, bw = pl.tables(x.device)
     if bw is not None and n > 0:
+        ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
         _call("pml_gemm_grouped", _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d,
-              _splitk_for(n), _stream())
+              _splitk_for(n, ctas), _stream())
     return dw
 
 
@@ -404,7 +425,7 @@ def element_linear(x: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tensor:
         S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
         shape = (n, pl.d_out // S, S)
     out = x.new_zeros(shape) if pl.has_unfed_output else x.new_empty(shape)
-    _call("pml_element_linear_fwd", _p(x), _p(attrs), _p(w), C.byref(pl.c_plan), _p(out), n, pl.Z, 0, _stream(), launches=4)
+    _call("pml_element_linear_fwd", _p(x), _p(attrs), _p(w), C.byref(pl.c_plan), _p(out), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return out
 
 
@@ -423,7 +444,7 @@ def element_linear_bwd_x(g: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tens
     g, attrs, w = _f32c(g), _f32c(attrs), _f32c(w)
     n = g.shape[0]
     dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else g.new_empty(n, pl.d_in)
-    _call("pml_element_linear_bwd_x", _p(g), _p(attrs), _p(w), C.byref(pl.c_plan), _p(dx), n, pl.Z, 0, _stream(), launches=4)
+    _call("pml_element_linear_bwd_x", _p(g), _p(attrs), _p(w), C.byref(pl.c_plan), _p(dx), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return dx
 
 
@@ -436,9 +457,9 @@ def _(g, attrs, w, plan):
 def element_linear_bwd_w(x: Tensor, g: Tensor, attrs: Tensor, plan: int) -> Tensor:
     pl = plans.get(plan)
     x, g, attrs = _f32c(x), _f32c(g), _f32c(attrs)
-    dw = x.new_empty(pl.weight_numel)
+    dw = x.new_zeros(pl.weight_numel)
     _call("pml_element_linear_bwd_w", _p(x), _p(g), _p(attrs), C.byref(pl.c_plan), _p(dw), x.shape[0], pl.Z, 0, _stream(),
-          launches=4)
+          launches=pl.n_launch)
     return dw
 
 

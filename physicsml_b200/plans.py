@@ -217,6 +217,7 @@ class ElementLinearPlan:
             p.alpha[k] = 1.0 / math.sqrt(fan[o])
         p.x_rs, p.o_rs = self.d_in, self.d_out
         self.c_plan = p
+        self.n_launch = len({2 * self.irreps_in[i][1] + 1 for i, _, _ in paths})
         self.handle = register(self)
 
 
