@@ -133,6 +133,7 @@ def main() -> None:
     ap.add_argument("--ref-molecules", type=int, default=4, help="bounded sample size of the CPU reference legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -163,7 +164,8 @@ def main() -> None:
     kw["avg_num_neighbours"] = wl.mean_degree(WORKLOAD)
     torch.manual_seed(0)
     model = PooledMACEModule(mlp_irreps=mlp, **kw).to(dev)
-    opt = wl.make_optimizer(model)
+    use_graph = not args.eager
+    opt = wl.make_optimizer(model, capturable=use_graph)
     params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
     n_atoms = data["coordinates"].shape[0]
     n_edges = data["edge_index"].shape[1]
@@ -197,10 +199,30 @@ def main() -> None:
         opt.step()
         return loss
 
+    graphed = None
+    if use_graph:
+        from physicsml_b200.graphs import GraphedStep
+
+        try:
+            graphed = GraphedStep(model, opt, d_dev, t_dev, wl.training_loss, after_backward=allreduce_grads, warmup=3)
+        except Exception as exc:  # capture is an optimisation: report and continue eagerly
+            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            graphed = None
+            opt = wl.make_optimizer(model, capturable=False)
+
+    def step_resident():
+        if graphed is not None:
+            return graphed()
+        return step(d_dev, t_dev)
+
     def step_e2e():
-        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()}
-        t = {k: v.to(dev, non_blocking=True) for k, v in host_t.items()}
-        loss = step(d, t)
+        if graphed is not None:
+            graphed.load(host, host_t)  # pinned host -> static device buffers
+            loss = graphed()
+        else:
+            d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()}
+            t = {k: v.to(dev, non_blocking=True) for k, v in host_t.items()}
+            loss = step(d, t)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
         return float(loss_host[0])
@@ -237,8 +259,15 @@ def main() -> None:
         return ms, launches
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, launches = timed(lambda: step(d_dev, t_dev), args.steps, args.warmup, with_kernel_timing=True)
+    ms_dev, launches = timed(step_resident, args.steps, args.warmup, with_kernel_timing=(graphed is None))
     clocks = sampler.stop() if sampler is not None else None
+    if graphed is not None:
+        # a replayed graph cannot carry per-kernel events: time the fused edge kernels in an eager pass of the SAME step
+        # (same inputs, same kernels), and count the kernels of one step the same way
+        opt_e = wl.make_optimizer(model, capturable=False)
+        opt_saved, opt = opt, opt_e
+        _, launches = timed(lambda: step(d_dev, t_dev), args.steps, 3, with_kernel_timing=True)
+        opt = opt_saved
     # per-kernel times of the fused edge kernels, recorded live inside the timed region
     ktimes: dict = {}
     for name, recs in ops.KERNEL_TIMING.items():
@@ -296,6 +325,7 @@ def main() -> None:
         "e2e": {"value": total_atoms / (ms_e2e * 1e-3), "unit": "atoms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": launches,
+        "cuda_graph": graphed is not None,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,

@@ -101,6 +101,11 @@ typedef struct {
 int pml_gemm_grouped(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                      int max_M, int max_N, int max_batch, int splitk, pml_stream_t stream);
 
+/* Same contract, executed on the 5th-gen tensor cores: tcgen05.mma kind::tf32 with TMEM accumulators and 3xTF32
+ * error compensation (fp32-accurate).  This is the radial-MLP path (K3). */
+int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
+                        int max_M, int max_N, int max_batch, int splitk, pml_stream_t stream);
+
 /* ---- K5b: element-indexed linear (FullyConnectedTensorProduct with one-hot node attributes) ------------------------
  * Replaces mix_layer / residual_connection_layer (models/mace/modules/blocks.py:183-188,72-78) and NequIP's
  * self_connection_layer (models/nequip/modules/interaction_block.py:73-82). */

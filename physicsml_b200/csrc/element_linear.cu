@@ -117,44 +117,70 @@ __global__ void __launch_bounds__(128) el_bwd_x_kernel(const float* __restrict__
   }
 }
 
-// dW[u, v, w] = alpha * sum_n a[n, v] sum_m x[n, u, m] g[n, w, m]   — one CTA per (path, v, 16x16 tile of (u, w),
-// chunk of nodes); chunk partials are combined with fp32 atomics (dW zero-initialised by the caller).
+// dW[u, v, w] = alpha * sum_n a[n, v] sum_m x[n, u, m] g[n, w, m]
+// One CTA per (path, element v, 16x16 tile of (u, w), chunk of 256 nodes): the chunk's nodes that carry element v are
+// compacted (deterministic ballot scan), then processed 8 at a time from shared memory.  Chunk partials are combined
+// with fp32 atomics (dW zero-initialised by the caller).
+constexpr int EL_CHUNK = 256, EL_NB = 8;
+
 template <int D>
 __global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                        const float* __restrict__ attrs, pml_el_plan P,
-                                                       float* __restrict__ dW, int N, int Z, int chunk) {
+                                                       float* __restrict__ dW, int N, int Z) {
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
   if (P.d[p] != D) return;
   const int MI = P.mul_in[p], MO = P.mul_out[p];
   const int tiles_w = (MO + 15) / 16;
   const int tu = blockIdx.x / tiles_w, tw = blockIdx.x - tu * tiles_w;
   if (tu * 16 >= MI) return;
-  const int w = tw * 16 + (threadIdx.x & 15), u = tu * 16 + (threadIdx.x >> 4);
-  const bool ok = (u < MI) && (w < MO);
-  __shared__ float xs[16 * 7], gs[16 * 7];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_list[EL_CHUNK];
+  __shared__ float s_coef[EL_CHUNK];
+  __shared__ int s_wcnt[8];
+  __shared__ float xs[EL_NB][16 * D], gs[EL_NB][16 * D];
+
+  const int n = blockIdx.y * EL_CHUNK + tid;
+  const float a = n < N ? __ldg(attrs + (size_t)n * Z + v) : 0.f;
+  const unsigned bal = __ballot_sync(0xffffffffu, a != 0.f);
+  if (lane == 0) s_wcnt[warp] = __popc(bal);
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int w8 = 0; w8 < 8; ++w8) {
+    if (w8 < warp) off += s_wcnt[w8];
+    total += s_wcnt[w8];
+  }
+  if (total == 0) return;  // uniform
+  if (a != 0.f) {
+    const int pos = off + __popc(bal & ((1u << lane) - 1u));
+    s_list[pos] = n;
+    s_coef[pos] = a;
+  }
+  __syncthreads();
+
+  const int ul = tid >> 4, wl = tid & 15;
   float acc = 0.f;
-  const int n_beg = blockIdx.y * chunk, n_end = min(N, n_beg + chunk);
-  for (int n = n_beg; n < n_end; ++n) {
-    const float a = __ldg(attrs + (size_t)n * Z + v);
-    if (a == 0.f) continue;  // uniform across the CTA
-    __syncthreads();
-    if (threadIdx.x < 16 * D) {
-      const int uu = threadIdx.x / D, m = threadIdx.x - uu * D;
-      const int gu = tu * 16 + uu;
-      xs[threadIdx.x] = gu < MI ? __ldg(x + (size_t)n * P.x_rs + P.x_off[p] + (size_t)gu * D + m) : 0.f;
-    } else if (threadIdx.x >= 128 && threadIdx.x < 128 + 16 * D) {
-      const int t = threadIdx.x - 128;
-      const int ww = t / D, m = t - ww * D;
-      const int gw = tw * 16 + ww;
-      gs[t] = gw < MO ? __ldg(g + (size_t)n * P.o_rs + P.o_off[p] + (size_t)gw * P.o_ws[p] + m) : 0.f;
+  for (int j0 = 0; j0 < total; j0 += EL_NB) {
+    const int nb = min(EL_NB, total - j0);
+    for (int i = tid; i < nb * 16 * D; i += 256) {
+      const int j = i / (16 * D), rem = i - j * (16 * D);
+      const int uu = rem / D, m = rem - uu * D;
+      const int node = s_list[j0 + j];
+      const int gu = tu * 16 + uu, gw = tw * 16 + uu;
+      xs[j][rem] = gu < MI ? __ldg(x + (size_t)node * P.x_rs + P.x_off[p] + (size_t)gu * D + m) : 0.f;
+      gs[j][rem] = gw < MO ? __ldg(g + (size_t)node * P.o_rs + P.o_off[p] + (size_t)gw * P.o_ws[p] + m) : 0.f;
     }
     __syncthreads();
-    float s = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      float s = 0.f;
 #pragma unroll
-    for (int m = 0; m < D; ++m) s = fmaf(xs[(threadIdx.x >> 4) * D + m], gs[(threadIdx.x & 15) * D + m], s);
-    acc = fmaf(a, s, acc);
+      for (int m = 0; m < D; ++m) s = fmaf(xs[j][ul * D + m], gs[j][wl * D + m], s);
+      acc = fmaf(s_coef[j0 + j], s, acc);
+    }
+    __syncthreads();
   }
-  if (ok && acc != 0.f) atomicAdd(dW + P.w_off[p] + ((size_t)u * Z + v) * MO + w, P.alpha[p] * acc);
+  const int u = tu * 16 + ul, w = tw * 16 + wl;
+  if (u < MI && w < MO && acc != 0.f) atomicAdd(dW + P.w_off[p] + ((size_t)u * Z + v) * MO + w, P.alpha[p] * acc);
 }
 
 }  // namespace pml
@@ -204,14 +230,8 @@ extern "C" int pml_element_linear_bwd_w(const float* x, const float* g, const fl
     const int t = ((plan->mul_in[p] + 15) / 16) * ((plan->mul_out[p] + 15) / 16);
     max_t = t > max_t ? t : max_t;
   }
-  // enough node chunks to fill the machine (~4 CTAs per SM), at least 32 nodes each
-  int chunks = (4 * 148 + max_t * plan->npaths * Z - 1) / (max_t * plan->npaths * Z);
-  if (chunks < 1) chunks = 1;
-  int chunk = (N + chunks - 1) / chunks;
-  if (chunk < 32) chunk = 32;
-  chunks = (N + chunk - 1) / chunk;
-  dim3 grid(max_t, chunks, plan->npaths * Z);
-#define CALL(D) pml::el_bwd_w_kernel<D><<<grid, 256, 0, stream>>>(x, g, attrs, *plan, dW, N, Z, chunk);
+  dim3 grid(max_t, (N + pml::EL_CHUNK - 1) / pml::EL_CHUNK, plan->npaths * Z);
+#define CALL(D) pml::el_bwd_w_kernel<D><<<grid, 256, 0, stream>>>(x, g, attrs, *plan, dW, N, Z);
   PML_EL_FOR_D(CALL)
 #undef CALL
   PML_CHECK_LAUNCH();

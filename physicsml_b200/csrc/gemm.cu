@@ -13,25 +13,7 @@
 // shapes.  TODO(round 2): tcgen05 3xTF32 path for the large-M problems.
 #include "pml_common.cuh"
 
-#define PML_GEMM_MAX_CHUNKS 8
-
-extern "C" {
-typedef struct {
-  long long a_off[PML_GEMM_MAX_CHUNKS];  // element offset of chunk's A block (from A base)
-  long long b_off[PML_GEMM_MAX_CHUNKS];  // element offset of chunk's B block (from B base)
-  int kc[PML_GEMM_MAX_CHUNKS];           // K extent of each chunk (< 0: use the runtime extent passed to the launcher)
-  float cscale[PML_GEMM_MAX_CHUNKS];     // per-chunk scale (multiplies alpha)
-  int nchunks;
-  long long c_off;
-  long long a_rs, a_cs, a_bs;  // A element strides: row, k, batch
-  long long b_rs, b_cs, b_bs;  // B element strides: k, col, batch
-  long long c_rs, c_cs, c_bs;  // C element strides: row, col, batch
-  int M, N;                    // M < 0: use the runtime extent passed to the launcher
-  int nbatch;
-  float alpha;
-  int accumulate;  // 0: C = result ; 1: C += result (plain RMW, single writer) ; split-K always uses atomics
-} pml_gemm_problem;
-}
+#include "gemm_problem.h"
 
 namespace pml {
 

@@ -1,0 +1,283 @@
+// Tensor-core (tcgen05, TMEM accumulators) version of the grouped strided GEMM, with 3xTF32 error compensation so the
+// result keeps fp32 accuracy (the parity bar is 1e-5 relative on energies, which single-pass TF32 cannot hold):
+//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi ,   X_hi = tf32(X), X_lo = tf32(X - X_hi)
+//
+// Used for the radial MLP (e3nn nn.FullyConnectedNet; reference blocks.py:157-160,211, interaction_block.py:61-64,85)
+// and for every other dense contraction large enough to fill 128-row MMA tiles.  Same problem table and semantics as
+// gemm.cu (general strides, K-chunks, batches, split-K) so both kernels are interchangeable and cross-checked.
+//
+// Structure per CTA (one 128 x BN output tile, 256 threads):
+//   * all threads stage A/B k-blocks: global (arbitrary strides) -> registers -> hi/lo split -> shared memory in the
+//     canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), 2-stage ring;
+//   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 3 products per k-step, accumulating in TMEM;
+//     tcgen05.commit arrives on the stage's mbarrier to hand the stage back to the loaders;
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> scale -> global (plain / accumulate / atomic).
+// No TMA: operands must pass through registers anyway for the hi/lo split.
+#include "gemm_problem.h"
+#include "pml_common.cuh"
+
+namespace pml {
+
+constexpr int TC_BM = 128, TC_BK = 16, TC_STAGES = 2, TC_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float r = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+
+// K-major, no swizzle: 16-byte unit (r, kc) of a [ROWS x 16] tile lives at  (r % 8) + 8 * kc + 32 * (r / 8)
+//   => leading (K) byte offset = 128, stride (M/N) byte offset = 512
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 16;  // leading_byte_offset
+  d |= (uint64_t)(512 >> 4) << 32;  // stride_byte_offset
+  d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
+  return d;                         // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Stage a [ROWS x 16] operand tile: element (row, k) at base + row*rs + k*cs ; rows >= nrows and k >= K read as 0.
+template <int ROWS>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ base, long long rs, long long cs, int row0, int nrows,
+                                           int k0, int K, float scale, float* __restrict__ s_hi, float* __restrict__ s_lo,
+                                           bool vec_ok) {
+  constexpr int UNITS = ROWS * (TC_BK / 4);
+  const bool kfast = (cs == 1);
+#pragma unroll
+  for (int it = 0; it < (UNITS + TC_THREADS - 1) / TC_THREADS; ++it) {
+    const int idx = threadIdx.x + it * TC_THREADS;
+    if (UNITS % TC_THREADS != 0 && idx >= UNITS) break;
+    int r, kc;
+    if (kfast) {
+      kc = idx % (TC_BK / 4);
+      r = idx / (TC_BK / 4);
+    } else {
+      r = idx % ROWS;
+      kc = idx / ROWS;
+    }
+    const int gr = row0 + r, gk = k0 + kc * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gr < nrows) {
+      const float* p = base + (long long)gr * rs + (long long)gk * cs;
+      if (vec_ok && gk + 3 < K) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gk + j < K) v[j] = __ldg(p + (long long)j * cs);
+      }
+    }
+    float4 hi, lo;
+    split_tf32(v[0] * scale, hi.x, lo.x);
+    split_tf32(v[1] * scale, hi.y, lo.y);
+    split_tf32(v[2] * scale, hi.z, lo.z);
+    split_tf32(v[3] * scale, hi.w, lo.w);
+    const int unit = (r & 7) + 8 * kc + 32 * (r >> 3);
+    reinterpret_cast<float4*>(s_hi)[unit] = hi;
+    reinterpret_cast<float4*>(s_lo)[unit] = lo;
+  }
+}
+
+template <int BN>
+struct __align__(128) TcSmem {
+  float a[TC_STAGES][2][TC_BM * TC_BK];
+  float b[TC_STAGES][2][BN * TC_BK];
+  unsigned long long bar[TC_STAGES];
+  uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                     float* __restrict__ C,
+                                                                     const pml_gemm_problem* __restrict__ probs,
+                                                                     int M_runtime, int splitk) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TcSmem<BN>& S = *reinterpret_cast<TcSmem<BN>*>(smem_raw);
+  const pml_gemm_problem& P = probs[blockIdx.y];
+  const int M = P.M < 0 ? M_runtime : P.M;
+  const int N = P.N;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int tm = blockIdx.x / tiles_n, tn = blockIdx.x - tm * tiles_n;
+  int zb = blockIdx.z;
+  const int ks = zb % splitk;
+  zb /= splitk;
+  if (tm * TC_BM >= M || zb >= P.nbatch) return;  // uniform per CTA, before any barrier / allocation
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) mbar_init(smem_u32(&S.bar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  const int row0 = tm * TC_BM, col0 = tn * BN;
+  int it = 0;  // global k-block counter (ring position)
+  for (int ch = 0; ch < P.nchunks; ++ch) {
+    const long long aoff = P.a_off[ch] + (long long)zb * P.a_bs;
+    const long long boff = P.b_off[ch] + (long long)zb * P.b_bs;
+    const float* Ab = A + aoff;
+    const float* Bb = B + boff;
+    const int K = P.kc[ch] < 0 ? M_runtime : P.kc[ch];
+    const bool vecA = (P.a_cs == 1) && ((aoff & 3) == 0) && ((P.a_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool vecB = (P.b_rs == 1) && ((boff & 3) == 0) && ((P.b_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    for (int k0 = ks * TC_BK; k0 < K; k0 += TC_BK * splitk, ++it) {
+      const int s = it % TC_STAGES;
+      if (it >= TC_STAGES) mbar_wait(smem_u32(&S.bar[s]), ((it / TC_STAGES) - 1) & 1);  // MMAs that read stage s retired
+      stage_tile<TC_BM>(Ab, P.a_rs, P.a_cs, row0, M, k0, K, P.cscale[ch], S.a[s][0], S.a[s][1], vecA);
+      // B operand as an [N x K] K-major tile: element (n, k) = Bb[k*b_rs + n*b_cs]
+      stage_tile<BN>(Bb, P.b_cs, P.b_rs, col0, N, k0, K, 1.f, S.b[s][0], S.b[s][1], vecB);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(S.a[s][0]), a_lo = smem_u32(S.a[s][1]);
+        const uint32_t b_hi = smem_u32(S.b[s][0]), b_lo = smem_u32(S.b[s][1]);
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          const uint32_t o = kk * 256;  // two 16-byte k-units = two core matrices of 128 B
+          umma_tf32(tmem, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, (it > 0 || kk > 0) ? 1u : 0u);
+          umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
+          umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[s]))
+                     : "memory");
+      }
+    }
+  }
+
+  if (it > 0) {
+    // the last commit covers every MMA issued before it
+    const int last = it - 1;
+    mbar_wait(smem_u32(&S.bar[last % TC_STAGES]), (last / TC_STAGES) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warp w reads TMEM lanes 32*(w%4).., columns [(w/4)*BN/2, +BN/2)
+    constexpr int COLS_PER_WARP = BN >= 64 ? BN / 2 : BN;
+    const int q = warp & 3, half = warp >> 2;
+    const int r = row0 + q * 32 + lane;
+    float* Cb = C + P.c_off + (long long)zb * P.c_bs;
+    const bool atomic = splitk > 1 || (P.c_bs == 0 && P.nbatch > 1);
+    if (BN >= 64 || half == 0) {
+#pragma unroll
+      for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+        const int cbase = (BN >= 64 ? half * COLS_PER_WARP : 0) + c0;
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase, v);
+        if (r < M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gc = col0 + cbase + j;
+            if (gc < N) {
+              float* p = Cb + (long long)r * P.c_rs + (long long)gc * P.c_cs;
+              const float val = P.alpha * v[j];
+              if (atomic) atomicAdd(p, val);
+              else if (P.accumulate) *p += val;
+              else *p = val;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN>
+static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
+                     int max_M, int max_N, int max_batch, int splitk, cudaStream_t stream) {
+  const int tiles_m = (max_M + TC_BM - 1) / TC_BM, tiles_n = (max_N + BN - 1) / BN;
+  const long long gz = (long long)max_batch * splitk;
+  if (gz > 65535 || nprobs > 65535) return PML_ERR_BAD_ARG;
+  const size_t smem = sizeof(TcSmem<BN>) + 128;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return PML_ERR_LAUNCH;
+    configured = true;
+  }
+  dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)nprobs, (unsigned)gz);
+  gemm_grouped_tc_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
+  return PML_OK;
+}
+
+}  // namespace pml
+
+// Same contract as pml_gemm_grouped (gemm.cu).
+extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
+                                   int M_runtime, int max_M, int max_N, int max_batch, int splitk, cudaStream_t stream) {
+  if (nprobs <= 0 || max_M <= 0 || max_N <= 0 || max_batch <= 0) return PML_OK;
+  if (splitk < 1) splitk = 1;
+  int rc;
+  if (max_N <= 32) rc = pml::launch_tc<32>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+  else if (max_N <= 64) rc = pml::launch_tc<64>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+  else rc = pml::launch_tc<128>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+  if (rc != PML_OK) return rc;
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}

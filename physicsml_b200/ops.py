@@ -10,6 +10,7 @@ tensors raises ``NotImplementedError`` from the dispatcher, and a missing shared
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -295,6 +296,17 @@ tp_scatter_bwd.register_autograd(_tp_bwd_bwd, setup_context=_tp_bwd_setup)
 # ======================================================================================================================
 # per-irrep linear (grouped GEMM)
 # ======================================================================================================================
+# "tc": tcgen05 3xTF32 kernel for every problem with >= TC_MIN_ROWS[0] runtime rows (the edge-sized radial-MLP GEMMs and
+# their weight gradients), FFMA kernel below that (node-sized per-irrep mixing, where K reaches 1280 and the tensor
+# core's truncating accumulation costs ~1e-5 relative); "ffma": FFMA only
+GEMM_MODE = [os.environ.get("PML_GEMM", "tc")]
+TC_MIN_ROWS = [int(os.environ.get("PML_TC_MIN_ROWS", "4096"))]
+
+
+def _gemm_name(n_runtime: int) -> str:
+    return "pml_gemm_grouped_tc" if (GEMM_MODE[0] == "tc" and n_runtime >= TC_MIN_ROWS[0]) else "pml_gemm_grouped"
+
+
 def _splitk_for(k_extent: int, ctas_without_split: int) -> int:
     """split the reduction so that ~4 CTAs per SM are in flight, keeping >= 4 k-tiles (of 16) per CTA"""
     want = (4 * 148 + ctas_without_split - 1) // max(1, ctas_without_split)
@@ -314,10 +326,10 @@ def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
         if pl.fwd_serial:
             sz = C.sizeof(_lib.GemmProblem)
             for k in range(nprob):
-                _call("pml_gemm_grouped", _p(x), _p(w), _p(out), fwd.data_ptr() + k * sz, 1, n, n, pl.max_mul_out,
+                _call(_gemm_name(n), _p(x), _p(w), _p(out), fwd.data_ptr() + k * sz, 1, n, n, pl.max_mul_out,
                       pl.max_d, 1, _stream())
         else:
-            _call("pml_gemm_grouped", _p(x), _p(w), _p(out), _p(fwd), nprob, n, n, pl.max_mul_out, pl.max_d, 1, _stream())
+            _call(_gemm_name(n), _p(x), _p(w), _p(out), _p(fwd), nprob, n, n, pl.max_mul_out, pl.max_d, 1, _stream())
     return out
 
 
@@ -337,7 +349,7 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
     dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else g.new_empty(n, pl.d_in)
     _, bx, _ = pl.tables(g.device)
     if bx is not None and n > 0:
-        _call("pml_gemm_grouped", _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, _stream())
+        _call(_gemm_name(n), _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, _stream())
     return dx
 
 
@@ -354,8 +366,13 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
     dw = x.new_zeros(pl.weight_numel)
     _, _, bw = pl.tables(x.device)
     if bw is not None and n > 0:
-        ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
-        _call("pml_gemm_grouped", _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d,
+        name = _gemm_name(n)
+        if name.endswith("_tc"):
+            bn = 32 if pl.max_mul_out <= 32 else (64 if pl.max_mul_out <= 64 else 128)
+            ctas = ((pl.max_mul_in + 127) // 128) * ((pl.max_mul_out + bn - 1) // bn) * len(pl._bwd_w) * pl.max_d
+        else:
+            ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
+        _call(name, _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d,
               _splitk_for(n, ctas), _stream())
     return dw
 

@@ -90,7 +90,7 @@ def training_loss(model, data: dict, targets: dict) -> torch.Tensor:
     return torch.nn.functional.mse_loss(e, targets["energy"]) + torch.nn.functional.mse_loss(-g, targets["forces"])
 
 
-def make_optimizer(model):
+def make_optimizer(model, capturable: bool = False):
     """reference default: Adam(lr=1e-2, amsgrad=True, weight_decay=5e-7) (mace/supervised/default_configs.py:25-33)"""
     params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
-    return torch.optim.Adam(params, lr=1e-2, amsgrad=True, weight_decay=5e-7)
+    return torch.optim.Adam(params, lr=1e-2, amsgrad=True, weight_decay=5e-7, capturable=capturable)

@@ -297,3 +297,44 @@ def test_cpu_tensors_fail_loudly():
 
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.act(torch.randn(4), 0, 1.0)
+
+
+@pytest.mark.parametrize("irr_in,irr_out", [("8x0e", "64x0e"), ("64x0e", "64x0e"), ("64x0e", "1280x0e"), ("64x0e", "96x0e"),
+                                            ("256x0e+384x1o+384x2e+256x3o", "128x0e+128x1o+128x2e+128x3o"),
+                                            ("40x0e+40x1o", "24x0e+24x1o")])
+@pytest.mark.parametrize("N", [64, 130, 4100])
+def test_tensor_core_gemm_matches_ffma(cuda, irr_in, irr_out, N):
+    """tcgen05 3xTF32 kernel and the FFMA kernel on the same problem tables (fwd, dx, dW), both against an fp64
+    evaluation of the oracle's Linear: the tensor-core path must stay at fp32-level accuracy (<= 2e-5 of the largest
+    output for reductions up to K = 1280; the FFMA kernel itself sits at ~2e-6 there)."""
+    from e3nn import o3
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import LinearPlan
+
+    g = torch.Generator().manual_seed(17)
+    plan = LinearPlan(irr_in, irr_out, scale=0.7)
+    x = torch.randn(N, plan.d_in, generator=g).to(cuda)
+    w = torch.randn(plan.weight_numel, generator=g).to(cuda)
+    gy = torch.randn(N, plan.d_out, generator=g).to(cuda)
+    ref = o3.Linear(o3.Irreps(irr_in), o3.Irreps(irr_out)).to(cuda).double()
+    ref.weight.data.copy_(w.double())
+    x64 = x.double().requires_grad_(True)
+    y64 = ref(x64) * 0.7
+    dx64, dw64 = torch.autograd.grad([y64], [x64, ref.weight], [gy.double()])
+    exact = (y64.detach(), dx64, dw64)
+    res = {}
+    old_rows = ops.TC_MIN_ROWS[0]
+    ops.TC_MIN_ROWS[0] = 1
+    try:
+        for mode in ("ffma", "tc"):
+            ops.GEMM_MODE[0] = mode
+            res[mode] = (ops.irrep_linear(x, w, plan.handle), ops.irrep_linear_bwd_x(gy, w, plan.handle),
+                         ops.irrep_linear_bwd_w(x, gy, plan.handle))
+    finally:
+        ops.GEMM_MODE[0] = "tc"
+        ops.TC_MIN_ROWS[0] = old_rows
+    for a, b, e, name in zip(res["tc"], res["ffma"], exact, ("fwd", "dx", "dw")):
+        err_tc, err_ff = _rel(a.double(), e), _rel(b.double(), e)
+        print(name, irr_in, irr_out, N, "rel err vs fp64: tc", err_tc, "ffma", err_ff)
+        assert err_tc < 2e-5, (name, err_tc)
+        assert err_ff < 2e-5, (name, err_ff)
