@@ -83,43 +83,68 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Stage a [ROWS x 16] operand tile: element (row, k) at base + row*rs + k*cs ; rows >= nrows and k >= K read as 0.
+// Operand staging is split in two so the global loads of k-block i+1 are in flight while k-block i is converted,
+// stored and multiplied (register double buffering):
+//   fetch : element (row, k) at base + row*rs + k*cs -> registers ; rows >= nrows and k >= K read as 0
+//   commit: registers -> hi/lo split -> canonical UMMA shared-memory layout
 template <int ROWS>
-__device__ __forceinline__ void stage_tile(const float* __restrict__ base, long long rs, long long cs, int row0, int nrows,
-                                           int k0, int K, float scale, float* __restrict__ s_hi, float* __restrict__ s_lo,
-                                           bool vec_ok) {
-  constexpr int UNITS = ROWS * (TC_BK / 4);
+struct TileRegs {
+  static constexpr int UNITS = ROWS * (TC_BK / 4);
+  static constexpr int PER_THREAD = (UNITS + TC_THREADS - 1) / TC_THREADS;
+  float v[PER_THREAD][4];
+};
+
+template <int ROWS>
+__device__ __forceinline__ void tile_coords(int idx, bool kfast, int& r, int& kc) {
+  if (kfast) {
+    kc = idx % (TC_BK / 4);
+    r = idx / (TC_BK / 4);
+  } else {
+    r = idx % ROWS;
+    kc = idx / ROWS;
+  }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void fetch_tile(const float* __restrict__ base, long long rs, long long cs, int row0, int nrows,
+                                           int k0, int K, bool vec_ok, TileRegs<ROWS>& t) {
   const bool kfast = (cs == 1);
 #pragma unroll
-  for (int it = 0; it < (UNITS + TC_THREADS - 1) / TC_THREADS; ++it) {
+  for (int it = 0; it < TileRegs<ROWS>::PER_THREAD; ++it) {
     const int idx = threadIdx.x + it * TC_THREADS;
-    if (UNITS % TC_THREADS != 0 && idx >= UNITS) break;
+    t.v[it][0] = t.v[it][1] = t.v[it][2] = t.v[it][3] = 0.f;
+    if (TileRegs<ROWS>::UNITS % TC_THREADS != 0 && idx >= TileRegs<ROWS>::UNITS) continue;
     int r, kc;
-    if (kfast) {
-      kc = idx % (TC_BK / 4);
-      r = idx / (TC_BK / 4);
-    } else {
-      r = idx % ROWS;
-      kc = idx / ROWS;
-    }
+    tile_coords<ROWS>(idx, kfast, r, kc);
     const int gr = row0 + r, gk = k0 + kc * 4;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (gr < nrows) {
       const float* p = base + (long long)gr * rs + (long long)gk * cs;
       if (vec_ok && gk + 3 < K) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        t.v[it][0] = q.x; t.v[it][1] = q.y; t.v[it][2] = q.z; t.v[it][3] = q.w;
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (gk + j < K) v[j] = __ldg(p + (long long)j * cs);
+          if (gk + j < K) t.v[it][j] = __ldg(p + (long long)j * cs);
       }
     }
+  }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void commit_tile(const TileRegs<ROWS>& t, bool kfast, float scale, float* __restrict__ s_hi,
+                                            float* __restrict__ s_lo) {
+#pragma unroll
+  for (int it = 0; it < TileRegs<ROWS>::PER_THREAD; ++it) {
+    const int idx = threadIdx.x + it * TC_THREADS;
+    if (TileRegs<ROWS>::UNITS % TC_THREADS != 0 && idx >= TileRegs<ROWS>::UNITS) continue;
+    int r, kc;
+    tile_coords<ROWS>(idx, kfast, r, kc);
     float4 hi, lo;
-    split_tf32(v[0] * scale, hi.x, lo.x);
-    split_tf32(v[1] * scale, hi.y, lo.y);
-    split_tf32(v[2] * scale, hi.z, lo.z);
-    split_tf32(v[3] * scale, hi.w, lo.w);
+    split_tf32(t.v[it][0] * scale, hi.x, lo.x);
+    split_tf32(t.v[it][1] * scale, hi.y, lo.y);
+    split_tf32(t.v[it][2] * scale, hi.z, lo.z);
+    split_tf32(t.v[it][3] * scale, hi.w, lo.w);
     const int unit = (r & 7) + 8 * kc + 32 * (r >> 3);
     reinterpret_cast<float4*>(s_hi)[unit] = hi;
     reinterpret_cast<float4*>(s_lo)[unit] = lo;
@@ -173,38 +198,66 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
   const int row0 = tm * TC_BM, col0 = tn * BN;
-  int it = 0;  // global k-block counter (ring position)
-  for (int ch = 0; ch < P.nchunks; ++ch) {
-    const long long aoff = P.a_off[ch] + (long long)zb * P.a_bs;
-    const long long boff = P.b_off[ch] + (long long)zb * P.b_bs;
-    const float* Ab = A + aoff;
-    const float* Bb = B + boff;
-    const int K = P.kc[ch] < 0 ? M_runtime : P.kc[ch];
+
+  // flattened (chunk, k0) iteration with one-step lookahead
+  struct KPos {
+    int ch, k0;
+  };
+  auto chunk_k = [&](int ch) { return P.kc[ch] < 0 ? M_runtime : P.kc[ch]; };
+  auto first_pos = [&](int ch_from) {
+    KPos q{ch_from, ks * TC_BK};
+    while (q.ch < P.nchunks && q.k0 >= chunk_k(q.ch)) ++q.ch;
+    return q;
+  };
+  auto next_pos = [&](KPos q) {
+    q.k0 += TC_BK * splitk;
+    if (q.k0 >= chunk_k(q.ch)) {
+      KPos n = first_pos(q.ch + 1);
+      return n;
+    }
+    return q;
+  };
+  auto fetch = [&](const KPos& q, TileRegs<TC_BM>& ra, TileRegs<BN>& rb) {
+    const long long aoff = P.a_off[q.ch] + (long long)zb * P.a_bs;
+    const long long boff = P.b_off[q.ch] + (long long)zb * P.b_bs;
+    const int K = chunk_k(q.ch);
     const bool vecA = (P.a_cs == 1) && ((aoff & 3) == 0) && ((P.a_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool vecB = (P.b_rs == 1) && ((boff & 3) == 0) && ((P.b_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-    for (int k0 = ks * TC_BK; k0 < K; k0 += TC_BK * splitk, ++it) {
-      const int s = it % TC_STAGES;
-      if (it >= TC_STAGES) mbar_wait(smem_u32(&S.bar[s]), ((it / TC_STAGES) - 1) & 1);  // MMAs that read stage s retired
-      stage_tile<TC_BM>(Ab, P.a_rs, P.a_cs, row0, M, k0, K, P.cscale[ch], S.a[s][0], S.a[s][1], vecA);
-      // B operand as an [N x K] K-major tile: element (n, k) = Bb[k*b_rs + n*b_cs]
-      stage_tile<BN>(Bb, P.b_cs, P.b_rs, col0, N, k0, K, 1.f, S.b[s][0], S.b[s][1], vecB);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(S.a[s][0]), a_lo = smem_u32(S.a[s][1]);
-        const uint32_t b_hi = smem_u32(S.b[s][0]), b_lo = smem_u32(S.b[s][1]);
+    fetch_tile<TC_BM>(A + aoff, P.a_rs, P.a_cs, row0, M, q.k0, K, vecA, ra);
+    // B operand as an [N x K] K-major tile: element (n, k) = B[k*b_rs + n*b_cs]
+    fetch_tile<BN>(B + boff, P.b_cs, P.b_rs, col0, N, q.k0, K, vecB, rb);
+  };
+
+  TileRegs<TC_BM> ra;
+  TileRegs<BN> rb;
+  KPos cur = first_pos(0);
+  if (cur.ch < P.nchunks) fetch(cur, ra, rb);
+  int it = 0;  // k-block counter (ring position)
+  while (cur.ch < P.nchunks) {
+    const KPos nxt = next_pos(cur);
+    const int s = it % TC_STAGES;
+    if (it >= TC_STAGES) mbar_wait(smem_u32(&S.bar[s]), ((it / TC_STAGES) - 1) & 1);  // MMAs that read stage s retired
+    commit_tile<TC_BM>(ra, P.a_cs == 1, P.cscale[cur.ch], S.a[s][0], S.a[s][1]);
+    commit_tile<BN>(rb, P.b_rs == 1, 1.f, S.b[s][0], S.b[s][1]);
+    if (nxt.ch < P.nchunks) fetch(nxt, ra, rb);  // in flight across the barrier, the MMA issue and the next wait
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(S.a[s][0]), a_lo = smem_u32(S.a[s][1]);
+      const uint32_t b_hi = smem_u32(S.b[s][0]), b_lo = smem_u32(S.b[s][1]);
 #pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; ++kk) {
-          const uint32_t o = kk * 256;  // two 16-byte k-units = two core matrices of 128 B
-          umma_tf32(tmem, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, (it > 0 || kk > 0) ? 1u : 0u);
-          umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
-          umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[s]))
-                     : "memory");
+      for (int kk = 0; kk < TC_BK / 8; ++kk) {
+        const uint32_t o = kk * 256;  // two 16-byte k-units = two core matrices of 128 B
+        umma_tf32(tmem, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, (it > 0 || kk > 0) ? 1u : 0u);
+        umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
+        umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
       }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[s]))
+                   : "memory");
     }
+    cur = nxt;
+    ++it;
   }
 
   if (it > 0) {
@@ -213,32 +266,41 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
     mbar_wait(smem_u32(&S.bar[last % TC_STAGES]), (last / TC_STAGES) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // epilogue: warp w reads TMEM lanes 32*(w%4).., columns [(w/4)*BN/2, +BN/2)
-    constexpr int COLS_PER_WARP = BN >= 64 ? BN / 2 : BN;
+    // epilogue: warp w reads TMEM lanes 32*(w%4).., columns [(w/4)*BN/2, +BN/2) in 32-column groups; every group is
+    // transposed through shared memory (the operand ring is free now) so global stores / atomics are coalesced rows
+    constexpr int NHALF = BN >= 64 ? 2 : 1;
+    constexpr int COLS_PER_WARP = BN / NHALF;
+    constexpr int PITCH = 32 * NHALF + 1;
+    float* stg = reinterpret_cast<float*>(S.a);  // [128][PITCH] floats <= 33.3 KB, inside the operand ring
+    static_assert(sizeof(float) * TC_BM * PITCH <= sizeof(S.a) + sizeof(S.b), "staging tile does not fit");
     const int q = warp & 3, half = warp >> 2;
-    const int r = row0 + q * 32 + lane;
     float* Cb = C + P.c_off + (long long)zb * P.c_bs;
     const bool atomic = splitk > 1 || (P.c_bs == 0 && P.nbatch > 1);
-    if (BN >= 64 || half == 0) {
-#pragma unroll
-      for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
-        const int cbase = (BN >= 64 ? half * COLS_PER_WARP : 0) + c0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+      if (half < NHALF) {
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase, v);
-        if (r < M) {
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gc = col0 + cbase + j;
-            if (gc < N) {
-              float* p = Cb + (long long)r * P.c_rs + (long long)gc * P.c_cs;
-              const float val = P.alpha * v[j];
-              if (atomic) atomicAdd(p, val);
-              else if (P.accumulate) *p += val;
-              else *p = val;
-            }
+        for (int j = 0; j < 32; ++j) stg[(q * 32 + lane) * PITCH + half * 32 + j] = v[j];
+      }
+      __syncthreads();
+      for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+        const int r = row0 + rr;
+        if (r >= M) break;
+#pragma unroll
+        for (int h = 0; h < NHALF; ++h) {
+          const int gc = col0 + h * COLS_PER_WARP + c0 + lane;
+          if (gc < N) {
+            float* p = Cb + (long long)r * P.c_rs + (long long)gc * P.c_cs;
+            const float val = P.alpha * stg[rr * PITCH + h * 32 + lane];
+            if (atomic) atomicAdd(p, val);
+            else if (P.accumulate) *p += val;
+            else *p = val;
           }
         }
       }
+      __syncthreads();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
