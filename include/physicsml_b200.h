@@ -142,6 +142,36 @@ int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int 
 /* [N, C*S] irreps layout <-> [N, C, S] (models/mace/modules/irreps_tools.py:47-67) */
 int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse, pml_stream_t stream);
 
+int pml_scan_i32(const int* counts, int* out, int n, pml_stream_t stream);
+
+/* ---- K1: radius-graph neighbour list ------------------------------------------------------------------------------
+ * Replaces compute_neighborlist_n2_no_cell / construct_edge_indices_and_attrs (lightning/graph_datasets/
+ * neighbourhood_list_torch.py:33-96) and the vendored linked-cell list (torch_nl_vendored/neighbor_list.py:8-48,108-164,
+ * linked_cell.py:129-355).  Two-phase (E is data dependent): *_count -> deg[N]; caller scans to rowptr[N+1], reads
+ * E = rowptr[N], allocates; *_fill -> packed keys; sort_segments; emit.  Output sorted by (sender, receiver, shift);
+ * PBC predicate d^2 < rc^2, open-boundary predicate d^2 <= rc^2; shifts refer to the unwrapped coordinates. */
+typedef struct {
+  double inv[9]; /* inverse cell (row-major): frac = pos . inv */
+  float cell[9]; /* lattice vectors as rows */
+  int nb[3];     /* bins per axis in fractional space */
+  int R[3];      /* stencil half-width per axis */
+  float rc2;
+} pml_nl_cell;
+int pml_nl_pbc_bin(const float* pos, const pml_nl_cell* cell, float* wpos, int* fl, int* bin, int* bincount, int N,
+                   pml_stream_t stream);
+int pml_nl_pbc_fill_bins(const int* bin, const int* binptr, int* cursor, int* sorted, int N, pml_stream_t stream);
+int pml_nl_pbc_count(const float* wpos, const int* bin, const int* binptr, const int* sorted, const pml_nl_cell* cell,
+                     int self_interaction, int* deg, int N, pml_stream_t stream);
+int pml_nl_pbc_fill(const float* wpos, const int* bin, const int* binptr, const int* sorted, const pml_nl_cell* cell,
+                    int self_interaction, const int* rowptr, unsigned long long* keys, int N, pml_stream_t stream);
+int pml_nl_open_count(const float* pos, const long long* batch, const int* gptr, float rc2, int self_interaction, int* deg,
+                      int N, pml_stream_t stream);
+int pml_nl_open_fill(const float* pos, const long long* batch, const int* gptr, float rc2, int self_interaction,
+                     const int* rowptr, unsigned long long* keys, int N, pml_stream_t stream);
+int pml_nl_sort_segments(unsigned long long* keys, const int* rowptr, int N, int* err, pml_stream_t stream);
+int pml_nl_emit(const unsigned long long* keys, const int* rowptr, const int* fl, long long* edge_index, float* shift,
+                int* snd32, int* rcv32, int* perm, int N, int E, pml_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,10 @@ class ElPlan(C.Structure):
     ]
 
 
+class NLCell(C.Structure):
+    _fields_ = [("inv", C.c_double * 9), ("cell", C.c_float * 9), ("nb", C.c_int * 3), ("R", C.c_int * 3), ("rc2", C.c_float)]
+
+
 class SymWeights(C.Structure):
     _fields_ = [
         ("w", (C.c_void_p * SYM_MAX_NU) * SYM_MAX_OUT),
@@ -94,6 +98,15 @@ SIGNATURES = {
     "pml_csr_rowptr": [_P, _P, _P, _I, _I, _P],
     "pml_split_edge_index": [_P, _P, _P, _I, _P],
     "pml_irreps_to_channel": [_P, _P, _LL, _I, _I, _I, _P],
+    "pml_scan_i32": [_P, _P, _I, _P],
+    "pml_nl_pbc_bin": [_P, C.POINTER(NLCell), _P, _P, _P, _P, _I, _P],
+    "pml_nl_pbc_fill_bins": [_P, _P, _P, _P, _I, _P],
+    "pml_nl_pbc_count": [_P, _P, _P, _P, C.POINTER(NLCell), _I, _P, _I, _P],
+    "pml_nl_pbc_fill": [_P, _P, _P, _P, C.POINTER(NLCell), _I, _P, _P, _I, _P],
+    "pml_nl_open_count": [_P, _P, _P, _F, _I, _P, _I, _P],
+    "pml_nl_open_fill": [_P, _P, _P, _F, _I, _P, _P, _I, _P],
+    "pml_nl_sort_segments": [_P, _P, _I, _P, _P],
+    "pml_nl_emit": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
 }
 
 _lib = None

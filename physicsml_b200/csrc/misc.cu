@@ -158,6 +158,13 @@ extern "C" int pml_csr_rowptr(const long long* idx, int* counts, int* rowptr, in
   return PML_OK;
 }
 
+// exclusive scan of int32 counts[n] into out[n+1] (single CTA)
+extern "C" int pml_scan_i32(const int* counts, int* out, int n, cudaStream_t stream) {
+  pml::csr_scan_kernel<<<1, 1024, 0, stream>>>(counts, out, n);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
 extern "C" int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int E, cudaStream_t stream) {
   if (E <= 0) return PML_OK;
   pml::split_edge_index_kernel<<<pml::ceil_div(E, 256), 256, 0, stream>>>(edge_index, row0, row1, E);

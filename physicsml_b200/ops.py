@@ -795,7 +795,8 @@ irreps_to_channel.register_autograd(
 # ======================================================================================================================
 class EdgePlan:
     """int32 copies of the edge list and the CSR over the scatter index, built once per batch and shared by every
-    layer's forward and backward kernels."""
+    layer's forward and backward kernels.  ``gather`` / ``rowptr`` / ``perm`` are the view for MACE's convention
+    (gather at edge_index[0], scatter to edge_index[1]); ``view(0)`` gives NequIP's (gather [1], scatter [0])."""
 
     def __init__(self, edge_index: Tensor, num_nodes: int, scatter_row: int = 1, assume_grouped: bool = False) -> None:
         E = edge_index.shape[1]
@@ -805,12 +806,33 @@ class EdgePlan:
         self.snd = torch.empty(E, dtype=torch.int32, device=dev)
         self.rcv = torch.empty(E, dtype=torch.int32, device=dev)
         _call("pml_split_edge_index", _p(ei), _p(self.snd), _p(self.rcv), E, _stream())
-        self.scatter = self.rcv if scatter_row == 1 else self.snd
-        self.gather = self.snd if scatter_row == 1 else self.rcv
-        counts = torch.zeros(num_nodes, dtype=torch.int32, device=dev)
-        self.rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
-        _call("pml_csr_rowptr", _p(ei[scatter_row]), _p(counts), _p(self.rowptr), E, num_nodes, _stream(), launches=2)
-        if assume_grouped:
-            self.perm = None
-        else:
-            self.perm = torch.argsort(ei[scatter_row], stable=True).to(torch.int32)
+        self._views = {}
+        self._ei = ei
+        self._assume_grouped = assume_grouped
+        self.scatter_row = scatter_row
+        self.gather, self.rowptr, self.perm = self.view(scatter_row)
+
+    @classmethod
+    def from_sorted(cls, snd: Tensor, rcv: Tensor, rowptr: Tensor, perm_by_receiver: Tensor, num_nodes: int) -> "EdgePlan":
+        """From the neighbour-list kernel: edges sorted by sender, symmetric set => one row pointer serves both views."""
+        self = cls.__new__(cls)
+        self.E, self.N = snd.numel(), num_nodes
+        self.snd, self.rcv = snd, rcv
+        self._views = {1: (snd, rowptr, perm_by_receiver), 0: (rcv, rowptr, None)}
+        self._ei = None
+        self._assume_grouped = False
+        self.scatter_row = 1
+        self.gather, self.rowptr, self.perm = self._views[1]
+        return self
+
+    def view(self, scatter_row: int):
+        """(gather index, CSR row pointer over the scatter index, edge ids grouped by scatter index or None)"""
+        if scatter_row not in self._views:
+            ei, dev = self._ei, self._ei.device
+            counts = torch.zeros(self.N, dtype=torch.int32, device=dev)
+            rowptr = torch.empty(self.N + 1, dtype=torch.int32, device=dev)
+            _call("pml_csr_rowptr", _p(ei[scatter_row]), _p(counts), _p(rowptr), self.E, self.N, _stream(), launches=2)
+            perm = None if self._assume_grouped else torch.argsort(ei[scatter_row], stable=True).to(torch.int32)
+            gather = self.snd if scatter_row == 1 else self.rcv
+            self._views[scatter_row] = (gather, rowptr, perm)
+        return self._views[scatter_row]

@@ -1,0 +1,130 @@
+"""Host-side logic that needs no GPU: irreps / path tables / plans against the oracle's e3nn restatement, state-dict
+compatibility with the reference layout, generated-kernel registry coverage, loud failure without CUDA."""
+import numpy as np
+import pytest
+import torch
+
+import helpers  # noqa: F401
+
+
+def test_tp_path_table_matches_oracle_instructions():
+    from e3nn import o3
+    from oracle.ref_model import uvu_instructions
+    from physicsml_b200 import so3
+
+    for node, lmax in [("4x0e", 2), ("4x0e+4x1o", 2), ("128x0e+128x1o", 3), ("256x0e+256x1o+256x2e", 3)]:
+        C = int(node.split("x")[0])
+        sh = o3.Irreps.spherical_harmonics(lmax)
+        target = (sh * C).sort().irreps.simplify()
+        irr, ins = uvu_instructions(o3.Irreps(node), sh, target)
+        spec = so3.build_tp_spec(node, lmax, str(target))
+        assert spec.n_paths == len(ins)
+        assert [(q.i_in, q.l2, q.i_out) for q in spec.paths] == [(i, j, k) for i, j, k, _, _ in ins]
+        assert spec.d_out * C == irr.dim and spec.d_in * C == o3.Irreps(node).dim
+
+
+def test_tp_sparse_terms_equal_dense_oracle():
+    """the generated code's term list evaluated in numpy == oracle o3.TensorProduct (dense einsum over w3j)"""
+    from e3nn import o3
+    from oracle.ref_model import uvu_instructions
+    from physicsml_b200 import so3
+
+    node, lmax, C = "2x0e+2x1o", 3, 2
+    sh = o3.Irreps.spherical_harmonics(lmax)
+    target = (sh * C).sort().irreps.simplify()
+    irr, ins = uvu_instructions(o3.Irreps(node), sh, target)
+    tp = o3.TensorProduct(o3.Irreps(node), sh, irr, instructions=ins, shared_weights=False, internal_weights=False)
+    spec = so3.build_tp_spec(node, lmax, str(target))
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(1, C * spec.d_in, generator=g, dtype=torch.float64)
+    Y = torch.randn(1, spec.n_sh, generator=g, dtype=torch.float64)
+    R = torch.randn(1, spec.n_paths * C, generator=g, dtype=torch.float64)
+    ref = tp(h, Y, R)[0].numpy()
+    out = np.zeros(C * spec.d_out)
+    in_l = [l for l, _ in spec.node_ls]
+    out_l = [l for l, _ in spec.out_ls]
+    in_blk_off = np.concatenate([[0], np.cumsum([2 * l + 1 for l in in_l])])
+    out_blk_off = np.concatenate([[0], np.cumsum([2 * l + 1 for l in out_l])])
+    for p, o, i, j, c in so3.tp_terms(spec):
+        bi = np.searchsorted(in_blk_off, i, side="right") - 1
+        bo = np.searchsorted(out_blk_off, o, side="right") - 1
+        di, do = 2 * in_l[bi] + 1, 2 * out_l[bo] + 1
+        for u in range(C):
+            hv = h[0, C * in_blk_off[bi] + u * di + (i - in_blk_off[bi])].item()
+            out[C * out_blk_off[bo] + u * do + (o - out_blk_off[bo])] += R[0, p * C + u].item() * c * hv * Y[0, j].item()
+    assert np.abs(out - ref).max() < 1e-12
+
+
+def test_contraction_monomials_equal_dense_oracle():
+    from e3nn import o3
+    from oracle.ref_model import _SymContraction
+    from physicsml_b200 import so3
+
+    lmax, C, Z, corr = 2, 2, 3, 3
+    inter = (o3.Irreps.spherical_harmonics(lmax) * C).sort().irreps.simplify()
+    torch.manual_seed(0)
+    ref = _SymContraction(inter, o3.Irreps("2x0e+2x1o"), corr, Z).double()
+    S = (lmax + 1) ** 2
+    x = torch.randn(1, C, S, dtype=torch.float64)
+    y = torch.nn.functional.one_hot(torch.tensor([1]), Z).double()
+    want = ref(x, y)[0].detach().numpy()
+    coup = tuple((l, (-1) ** l) for l in range(lmax + 1))
+    got, off = np.zeros_like(want), 0
+    for a, out in enumerate([(0, 1), (1, -1)]):
+        con = ref.contractions[a]
+        ws = {corr: con.weights_max}
+        for i, w in enumerate(con.weights):
+            ws[corr - 1 - i] = w
+        d = 2 * out[0] + 1
+        for nu in range(1, corr + 1):
+            for (k, M, idx), c in so3.contraction_monomials(coup, out, nu).items():
+                for ch in range(C):
+                    got[off + ch * d + M] += ws[nu][1, k, ch].item() * c * np.prod([x[0, ch, i].item() for i in idx])
+        off += C * d
+    assert np.abs(got - want).max() < 1e-6 * max(1.0, np.abs(want).max())  # U is built in fp32 by the reference
+
+
+def test_generated_registry_covers_baseline_configs():
+    from physicsml_b200 import _lib, so3
+
+    reg = _lib.registry()
+    for node, lmax in [("32x0e", 2), ("32x0e+32x1o", 2), ("128x0e", 3), ("128x0e+128x1o", 3), ("256x0e", 3), ("256x0e+256x1o+256x2e", 3)]:
+        tgt = so3.irreps_str([(1, l, (-1) ** l) for l in range(lmax + 1)])
+        assert so3.build_tp_spec(node, lmax, tgt).key in reg["tp"]
+    for key in ("l2__o0e_1o__c3", "l2__o0e__c3", "l3__o0e_1o__c3", "l3__o0e__c3", "l3__o0e_1o_2e__c3", "l2__o0e_1o__c2"):
+        assert key in reg["sym"]
+
+
+def test_product_state_dict_is_reference_layout():
+    from oracle.ref_model import RefPooledMACE
+    from physicsml_b200.mace import PooledMACEModule
+
+    kw = dict(cut_off=5.0, num_bessel=8, num_polynomial_cutoff=5, max_ell=3, num_interactions=2, num_node_feats=10,
+              num_edge_feats=0, hidden_irreps="16x0e + 16x1o", avg_num_neighbours=10.0, correlation=3)
+    a, b = PooledMACEModule(mlp_irreps="16x0e", **kw), RefPooledMACE(mlp_irreps="16x0e", **kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert set(sa) == set(sb)
+    assert all(sa[k].shape == sb[k].shape for k in sa)
+    a.load_state_dict(sb, strict=True)
+    for k in sa:
+        if "U_matrices" in k:
+            assert (sa[k] - sb[k]).abs().max() < 1e-6
+
+
+def test_linear_plan_matches_oracle_layout():
+    from e3nn import o3
+    from physicsml_b200.plans import ElementLinearPlan, LinearPlan
+
+    for a, b in [("64x0e+96x1o+64x2e", "32x0e+32x1o+32x2e"), ("32x0e+32x1o", "1x0e"), ("4x0e", "4x0e")]:
+        assert LinearPlan(a, b).weight_numel == o3.Linear(o3.Irreps(a), o3.Irreps(b)).weight_numel
+    ref = o3.FullyConnectedTensorProduct(o3.Irreps("4x0e+4x1o+4x2e"), o3.Irreps("4x0e"), o3.Irreps("4x0e+4x1o+4x2e"))
+    assert ElementLinearPlan("4x0e+4x1o+4x2e", 4, "4x0e+4x1o+4x2e").weight_numel == ref.weight_numel == 192
+
+
+def test_no_cpu_fallback():
+    from physicsml_b200 import neighbour_list, ops
+
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.act(torch.randn(4), 0, 1.0)
+    with pytest.raises(RuntimeError):
+        neighbour_list.radius_graph(torch.randn(4, 3), 5.0)
