@@ -21,6 +21,25 @@ CONFIGS = {
 }
 
 
+def water_box(n_mol: int = 8000, box: float = 62.14, seed: int = 404):
+    """configs[3]: n_mol water molecules on a jittered cubic lattice in a periodic box (rho = 0.1 atoms/A^3 at the
+    defaults), O-H 0.96 A, H-O-H 104.5 deg, random orientation.  -> (pos [3 n_mol, 3], species idx (O=3, H=0), cell)"""
+    rng = np.random.default_rng(seed)
+    m = int(np.ceil(n_mol ** (1.0 / 3.0)))
+    a = box / m
+    idx = np.stack(np.meshgrid(np.arange(m), np.arange(m), np.arange(m), indexing="ij"), -1).reshape(-1, 3)[:n_mol]
+    centres = (idx + 0.5) * a + rng.uniform(-0.25, 0.25, size=(n_mol, 3)) * (a - 2.6)
+    # random rotations (QR of gaussian matrices)
+    q, r = np.linalg.qr(rng.normal(size=(n_mol, 3, 3)))
+    q = q * np.sign(np.diagonal(r, axis1=1, axis2=2))[:, None, :]
+    th = np.deg2rad(104.5) / 2
+    h1 = 0.96 * np.array([np.sin(th), np.cos(th), 0.0])
+    h2 = 0.96 * np.array([-np.sin(th), np.cos(th), 0.0])
+    pos = np.stack([centres, centres + q @ h1, centres + q @ h2], axis=1).reshape(-1, 3)
+    z = np.tile(np.array([3, 0, 0]), n_mol)
+    return torch.tensor(pos, dtype=torch.float32), torch.tensor(z, dtype=torch.long), torch.eye(3) * box
+
+
 def random_molecules(n_mol, n_lo, n_hi, n_species, seed, min_dist=0.95, probs=None):
     rng = np.random.default_rng(seed)
     pos, z, batch = [], [], []
