@@ -59,6 +59,11 @@ int pml_tp_fwd(int spec, const float* h, const float* Y, const float* R, const i
  * (zero-initialised when C > 32), dR [E,NP*C] may be NULL to skip it. g [N, C*DOUT]. */
 int pml_tp_bwd(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
                const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, pml_stream_t stream);
+/* Kernel selection for K4 (diagnostics): by default the TMA-pipelined persistent kernels run whenever NP*C and DIN*C
+ * are multiples of 4 floats (16-byte rows), h / R are 16-byte aligned and DOUT <= 48.  Bit 0 of v forces the
+ * register-streaming kernels that also serve every other shape; bits 1 / 2 flip the producer placement of the
+ * pipelined forward / cotangent kernel.  Returns the previous setting (initially env PML_TP_SIMPLE). */
+int pml_tp_set_simple(int v);
 
 /* ---- K6: symmetric contraction ------------------------------------------------------------------------------------
  * Replaces SymmetricContraction.forward (models/mace/modules/symmetric_contraction.py:75-77,218-239).

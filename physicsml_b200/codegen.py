@@ -86,6 +86,15 @@ def _emit_tp(spec: so3.TPSpec, ident: int) -> str:
             L.append(f"    h[{off + i}] = __ldg(hrow + (size_t)C * {off} + (size_t)u * {d} + {i});")
         off += d
     L.append("  }")
+    L.append("  // same gather from a row staged in shared memory (pipelined kernels)")
+    L.append("  __device__ __forceinline__ static void load_h_smem(const float* hrow, int C, int u, float (&h)[DIN]) {")
+    off = 0
+    for l, _ in spec.node_ls:
+        d = 2 * l + 1
+        for i in range(d):
+            L.append(f"    h[{off + i}] = hrow[C * {off} + u * {d} + {i}];")
+        off += d
+    L.append("  }")
     L.append("  __device__ __forceinline__ static void atomic_add_h(float* __restrict__ hrow, int C, int u, const float (&h)[DIN]) {")
     off = 0
     for l, _ in spec.node_ls:
@@ -151,8 +160,149 @@ def _emit_tp(spec: so3.TPSpec, ident: int) -> str:
         L.append("      }")
         L.append("    }")
     L.append("  }")
+    _emit_tp_packed(spec, by_path, L)
     L.append("};")
     return "\n".join(L)
+
+
+def _f32_is(c: float, v: float) -> bool:
+    import numpy as np
+
+    return float(np.float32(c)) == v
+
+
+def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
+    """Two channels per thread on the packed fp32x2 pipe (FFMA2 / FMUL2, sm_100): every operand is a float2 holding
+    the same quantity for channels (2t, 2t+1); Y arrives as duplicated pairs (Y_j, Y_j).  The arithmetic is factored
+    to ~1 packed instruction per non-zero 3j entry and cotangent:
+      fwd : rh_i = R_p h_i ;  acc_k += (|c| rh_i) (+-Y_j)
+      bwd : a = |c| g_k ;  dh'_i += a Y_j ;  dY'_j += a h_i ;  then per path  dR_p = sum_i h_i dh'_i,
+            dh_i += R_p dh'_i,  dY_j += R_p . dY'_j  (the two channels are summed here: dY is per edge)."""
+    NP, DIN, DOUT, NSH = spec.n_paths, spec.d_in, spec.d_out, spec.n_sh
+
+    def scaled(cache, tag, c, base, lines, indent):
+        """name of |c|*base (a float2 expression name), emitting the multiply once per distinct (|c|, base)"""
+        a = abs(c)
+        if _f32_is(a, 1.0):
+            return base
+        key = (float(__import__("numpy").float32(a)), base)
+        if key not in cache:
+            name = f"{tag}{len(cache)}"
+            lines.append(f"{indent}const float2 {name} = f2mul(f2dup({_f(a)}), {base});")
+            cache[key] = name
+        return cache[key]
+
+    # ---------------- forward
+    L.append("  // packed: h, R, acc hold channels (2t, 2t+1); Y[j] = (Y_j, Y_j)")
+    L.append("  __device__ __forceinline__ static void fwd2(const float2 (&h)[DIN], const float2 (&Y)[NSH], const float2 (&R)[NP], float2 (&acc)[DOUT]) {")
+    for p in range(NP):
+        terms = by_path[p]
+        L.append("    {")
+        ins = sorted({i for _, i, _, _ in terms})
+        for i in ins:
+            L.append(f"      const float2 rh{i} = f2mul(R[{p}], h[{i}]);")
+        cache = {}
+        for o, i, j, c in terms:
+            sname = scaled(cache, "s", c, f"rh{i}", L, "      ")
+            y = f"Y[{j}]" if c > 0 else f"f2neg(Y[{j}])"
+            L.append(f"      acc[{o}] = f2fma({sname}, {y}, acc[{o}]);")
+        L.append("    }")
+    L.append("  }")
+
+    # ---------------- backward
+    L.append("  // dY (per edge) receives the sum over this thread's two channels; dh, dR stay packed")
+    L.append("  template <bool WANT_H, bool WANT_Y, bool WANT_R, int NY>")
+    L.append("  __device__ __forceinline__ static void bwd2(const float2 (&h)[DIN], const float2 (&Y)[NSH], const float2 (&R)[NP], const float2 (&g)[DOUT],")
+    L.append("                                              float2 (&dh)[DIN], float (&dY)[NY], float2 (&dR)[NP]) {")
+    for p in range(NP):
+        terms = by_path[p]
+        ins = sorted({i for _, i, _, _ in terms})
+        js = sorted({j for _, _, j, _ in terms})
+        L.append("    {")
+        cache = {}
+        pre = []
+        names = {}
+        for o, i, j, c in terms:
+            names[(o, i, j)] = scaled(cache, "a", c, f"g[{o}]", pre, "      ")
+        L.extend(pre)
+        L.append("      if (WANT_H || WANT_R) {")
+        seen = set()
+        for o, i, j, c in terms:
+            y = f"Y[{j}]" if c > 0 else f"f2neg(Y[{j}])"
+            a = names[(o, i, j)]
+            if i not in seen:
+                L.append(f"        float2 dhp{i} = f2mul({a}, {y});")
+                seen.add(i)
+            else:
+                L.append(f"        dhp{i} = f2fma({a}, {y}, dhp{i});")
+        if True:
+            L.append("        if (WANT_R) {")
+            expr = None
+            for n, i in enumerate(ins):
+                if n == 0:
+                    L.append(f"          float2 r = f2mul(h[{i}], dhp{i});")
+                else:
+                    L.append(f"          r = f2fma(h[{i}], dhp{i}, r);")
+            L.append(f"          dR[{p}] = r;")
+            L.append("        }")
+            L.append("        if (WANT_H) {")
+            for i in ins:
+                L.append(f"          dh[{i}] = f2fma(R[{p}], dhp{i}, dh[{i}]);")
+            L.append("        }")
+        L.append("      }")
+        L.append("      if (WANT_Y) {")
+        seen = set()
+        for o, i, j, c in terms:
+            hh = f"h[{i}]" if c > 0 else f"f2neg(h[{i}])"
+            a = names[(o, i, j)]
+            if j not in seen:
+                L.append(f"        float2 dyp{j} = f2mul({a}, {hh});")
+                seen.add(j)
+            else:
+                L.append(f"        dyp{j} = f2fma({a}, {hh}, dyp{j});")
+        for j in js:
+            L.append(f"        dY[{j}] = fmaf(R[{p}].x, dyp{j}.x, fmaf(R[{p}].y, dyp{j}.y, dY[{j}]));")
+        L.append("      }")
+        L.append("    }")
+    L.append("  }")
+
+    # ---------------- packed row access: channels (u, u+1), u even
+    L.append("  __device__ __forceinline__ static void load_h2_smem(const float* hrow, int C, int u, float2 (&h)[DIN]) {")
+    off = 0
+    for l, _ in spec.node_ls:
+        d = 2 * l + 1
+        for i in range(d):
+            L.append(f"    h[{off + i}] = make_float2(hrow[C * {off} + u * {d} + {i}], hrow[C * {off} + (u + 1) * {d} + {i}]);")
+        off += d
+    L.append("  }")
+    L.append("  __device__ __forceinline__ static void load_out2(const float* __restrict__ row, int C, int u, float2 (&a)[DOUT]) {")
+    off = 0
+    for l, _ in spec.out_ls:
+        d = 2 * l + 1
+        for m in range(d):
+            L.append(f"    a[{off + m}] = make_float2(__ldg(row + (size_t)C * {off} + (size_t)u * {d} + {m}), __ldg(row + (size_t)C * {off} + (size_t)(u + 1) * {d} + {m}));")
+        off += d
+    L.append("  }")
+    L.append("  __device__ __forceinline__ static void store_out2(float* __restrict__ row, int C, int u, const float2 (&a)[DOUT]) {")
+    off = 0
+    for l, _ in spec.out_ls:
+        d = 2 * l + 1
+        for m in range(d):
+            L.append(f"    row[(size_t)C * {off} + (size_t)u * {d} + {m}] = a[{off + m}].x;")
+            L.append(f"    row[(size_t)C * {off} + (size_t)(u + 1) * {d} + {m}] = a[{off + m}].y;")
+        off += d
+    L.append("  }")
+    # fp32 reductions into dh[s]: the 2(2l+1) floats of channels (u, u+1) of one block are contiguous and 8-byte
+    # aligned (u even) -> (2l+1) vector reds instead of 2(2l+1) scalar ones
+    L.append("  __device__ __forceinline__ static void atomic_add_h2(float* __restrict__ hrow, int C, int u, const float2 (&h)[DIN]) {")
+    off = 0
+    for l, _ in spec.node_ls:
+        d = 2 * l + 1
+        flat = [f"h[{off + i}].x" for i in range(d)] + [f"h[{off + i}].y" for i in range(d)]
+        for v in range(d):
+            L.append(f"    red_add_f32x2(hrow + (size_t)C * {off} + (size_t)u * {d} + {2 * v}, {flat[2 * v]}, {flat[2 * v + 1]});")
+        off += d
+    L.append("  }")
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -345,7 +495,9 @@ def generate(out_dir: str = GEN_DIR) -> dict:
     sym_specs = default_sym_specs()
     registry = {"tp": {}, "sym": {}}
 
-    parts = ["// GENERATED by physicsml_b200/codegen.py — do not edit.", "#pragma once", "template <int ID> struct TPCode;"]
+    parts = ["// GENERATED by physicsml_b200/codegen.py — do not edit.", "#pragma once",
+             "using pml::f2mul; using pml::f2fma; using pml::f2dup; using pml::f2neg; using pml::red_add_f32x2;",
+             "template <int ID> struct TPCode;"]
     for ident, spec in enumerate(tp_specs):
         parts.append(_emit_tp(spec, ident))
         registry["tp"][spec.key] = {"id": ident, "np": spec.n_paths, "din": spec.d_in, "dout": spec.d_out, "nsh": spec.n_sh}

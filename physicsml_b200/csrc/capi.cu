@@ -25,6 +25,25 @@ PML_SYM_FOREACH(DECL_SYM)
 #undef DECL_SYM
 
 extern "C" int pml_abi_version(void) { return 1; }
+
+// K4 kernel selection (A/B measurements, tests of the path taken when rows are not 16-byte multiples).  Bit 0: use the
+// register-streaming kernels; bit 1 / bit 2: flip the producer placement of the pipelined forward / cotangent kernel
+// (default: dedicated producer warp in the forward, warp 0 doubles as producer in the cotangent kernel).
+// Initial value: env PML_TP_SIMPLE (integer).
+#include <stdlib.h>
+static int g_tp_mode = -1;
+extern "C" int pml_tp_force_simple(void) {
+  if (g_tp_mode < 0) {
+    const char* e = getenv("PML_TP_SIMPLE");
+    g_tp_mode = e ? atoi(e) & 7 : 0;
+  }
+  return g_tp_mode;
+}
+extern "C" int pml_tp_set_simple(int v) {
+  const int old = pml_tp_force_simple();
+  g_tp_mode = v & 7;
+  return old;
+}
 extern "C" int pml_num_tp_specs(void) { return PML_TP_NUM_SPECS; }
 extern "C" int pml_num_sym_specs(void) { return PML_SYM_NUM_SPECS; }
 

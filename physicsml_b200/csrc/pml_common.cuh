@@ -37,6 +37,21 @@ __device__ __forceinline__ void st_stream(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v));
 }
 
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): one instruction, two channels
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2dup(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+
+// *(float2*)p += (a, b) without a return value (p 8-byte aligned)
+__device__ __forceinline__ void red_add_f32x2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ void st_stream2(float* p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y));
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace pml

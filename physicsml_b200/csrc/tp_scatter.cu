@@ -184,16 +184,436 @@ __global__ void __launch_bounds__(128) tp_bwd_kernel(const float* __restrict__ h
   }
 }
 
+
+// =====================================================================================================================
+// Pipelined variants (the ones that run whenever the row sizes are 16-byte multiples): persistent CTAs, each owning a
+// contiguous range of scatter nodes holding ~E/grid edges.  Every edge's operands — the R row (NP*C floats) and the
+// gathered h row (DIN*C floats) by `cp.async.bulk` (TMA 1-D bulk copies), the Y row by 4-byte cp.async — are streamed
+// into an NSTAGE-deep shared-memory ring guarded by full/empty mbarriers, several edges ahead of the arithmetic, so no
+// thread ever waits on a global load.  The ring runs across node boundaries (no per-node ramp-up): bytes in flight
+// per SM = resident CTAs x NSTAGE x row bytes (~200 KB at C=128, lmax 3) instead of what the register file of the
+// load-compute-load loop above can hold (~20 KB) — the bound of a latency-limited stream.  Each thread owns two
+// channels and computes on the packed fp32x2 pipe (FFMA2), with the 3j contraction factored to about one packed
+// instruction per non-zero coefficient; without that the kernels are issue-bound, not HBM-bound.
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int kPipeMaxStages = 8;
+
+// first index i in [0, n] with a[i] >= v   (a non-decreasing, n+1 entries)
+__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int n, long long v) {
+  int lo = 0, hi = n + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int ID>
+struct PipeLayout {
+  using T = TPCode<ID>;
+  static constexpr int YPAD = (2 * T::NSH + 3) & ~3;  // Y is staged as duplicated pairs (Y_j, Y_j): packed operands
+  __host__ __device__ static int r_floats(int C) { return T::NP * C; }
+  __host__ __device__ static int h_floats(int C) { return T::DIN * C; }
+  __host__ __device__ static int stage_floats(int C) { return r_floats(C) + h_floats(C) + YPAD + 4; }  // + {edge id, gather id}
+  __host__ __device__ static bool supported(int C) {
+    // DOUT <= 48: two channels of accumulators (or of the cotangent row) must fit the register file without spilling
+    return (r_floats(C) % 4 == 0) && (h_floats(C) % 4 == 0) && (C % 2 == 0) && C <= 1984 && 2 * T::NSH <= 32 && T::DOUT <= 48;
+  }
+  __host__ __device__ static int consumer_threads(int C) { return ((C / 2 + 31) / 32) * 32; }
+};
+
+// The CTA's node range: node n belongs to CTA b iff  E*b/G <= rowptr[n] < E*(b+1)/G  (last CTA: <= E), so every node,
+// including the ones without edges, has exactly one owner and the owners' edge ranges tile [0, E).
+__device__ __forceinline__ void pipe_node_range(const int* __restrict__ rowptr, int N, int* sh_range) {
+  if (threadIdx.x < 2) {
+    const int E = __ldg(rowptr + N);
+    const long long G = gridDim.x, b = blockIdx.x + threadIdx.x;
+    const long long v = (b >= G) ? (long long)E + 1 : ((long long)E * b) / G;
+    int n = lower_bound_i32(rowptr, N, v);
+    sh_range[threadIdx.x] = n < N ? n : N;
+  }
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Producer state, carried by warp 0 of the CTA next to its consumer work (no dedicated warp: a third warp would hold
+// a third of the CTA's registers just to issue copies).  Walks edges [q_lo, q_hi) of the CTA; the (edge id, gather
+// id) pairs are fetched 32 edges at a time, one chunk ahead, and broadcast with shuffles.
+template <int ID, bool LOAD_R>
+struct PipeProducer {
+  using L = PipeLayout<ID>;
+  using T = TPCode<ID>;
+  const float *h, *Y, *R;
+  const int *gather, *perm;
+  float* stages;
+  uint64_t *full, *empty;
+  int q_hi, C, nstage;
+  int qp;     // next edge to issue
+  int pos;    // its position inside the current 32-edge index chunk
+  int stage;  // ring slot it goes to
+  uint32_t phase;
+  int e_cur, s_cur, e_nxt, s_nxt;
+
+  __device__ __forceinline__ void fetch(int q0, int lane, int& e, int& s) const {
+    const int q = q0 + lane;
+    e = 0, s = 0;
+    if (q < q_hi) {
+      e = perm ? __ldg(perm + q) : q;
+      s = __ldg(gather + e);
+    }
+  }
+  __device__ __forceinline__ void start(int q_lo, int lane) {
+    qp = q_lo, pos = 0, stage = 0, phase = 0;
+    fetch(q_lo, lane, e_cur, s_cur);
+    fetch(q_lo + 32, lane, e_nxt, s_nxt);
+  }
+  // issue up to `limit` edges, at most up to edge index `bound` (exclusive); a slot still being read by another
+  // consumer warp ends the attempt unless `blocking`
+  __device__ __forceinline__ void issue(int limit, int bound, bool blocking, int lane) {
+    const int rfl = L::r_floats(C), hfl = L::h_floats(C), sfl = L::stage_floats(C);
+    if (bound > q_hi) bound = q_hi;
+    for (int n = 0; n < limit && qp < bound; ++n) {
+      const uint32_t eb = smem_u32(empty + stage);
+      if (blocking)
+        mbar_wait(eb, phase ^ 1u);
+      else if (!mbar_test(eb, phase ^ 1u))
+        break;
+      const int e = __shfl_sync(0xffffffffu, e_cur, pos);
+      const int s = __shfl_sync(0xffffffffu, s_cur, pos);
+      float* st = stages + (size_t)stage * sfl;
+      const uint32_t fb = smem_u32(full + stage);
+      if (lane == 0) {
+        reinterpret_cast<int2*>(st + rfl + hfl + L::YPAD)[0] = make_int2(e, s);  // released by the arrive below
+        mbar_expect_tx(fb, (LOAD_R ? (uint32_t)rfl * 4u : 0u) + (uint32_t)hfl * 4u);
+        if (LOAD_R) bulk_g2s(smem_u32(st), R + (size_t)e * rfl, (uint32_t)rfl * 4u, fb);
+        bulk_g2s(smem_u32(st + rfl), h + (size_t)s * hfl, (uint32_t)hfl * 4u, fb);
+      }
+      if (lane < 2 * T::NSH) cp_async4(smem_u32(st + rfl + hfl + lane), Y + (size_t)e * T::NSH + (lane >> 1));
+      cp_async_mbar_arrive_noinc(fb);
+      ++qp;
+      if (++stage == nstage) {
+        stage = 0;
+        phase ^= 1u;
+      }
+      if (++pos == 32) {
+        pos = 0;
+        e_cur = e_nxt, s_cur = s_nxt;
+        fetch(qp + 32, lane, e_nxt, s_nxt);
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ void pipe_init(uint64_t* full, uint64_t* empty, int nstage, int consumer_warps) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      mbar_init(smem_u32(full + s), 33);               // 32 cp.async arrivals + the expect_tx arrival
+      mbar_init(smem_u32(empty + s), consumer_warps);  // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+}
+
+// Y pairs from shared memory: (Y_j, Y_j) sits at float offset 2j (16-byte vector loads)
+template <int NSH, int YPAD>
+__device__ __forceinline__ void load_y2_smem(const float* ys, float2 (&Yv)[NSH]) {
+  float tmp[YPAD];
+#pragma unroll
+  for (int j = 0; j < YPAD / 4; ++j) {
+    const float4 v = reinterpret_cast<const float4*>(ys)[j];
+    tmp[4 * j] = v.x, tmp[4 * j + 1] = v.y, tmp[4 * j + 2] = v.z, tmp[4 * j + 3] = v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < NSH; ++j) Yv[j] = make_float2(tmp[2 * j], tmp[2 * j + 1]);
+}
+
+// blockDim.x = 32*ceil(C/64) consumer threads: two channels each, packed fp32x2 arithmetic.  The copies are issued by
+// a dedicated extra warp (DEDICATED: the ring is refilled the moment a slot is released, independent of anybody's
+// arithmetic) or by warp 0 between its own edges (no extra warp: a third more CTAs fit when registers bound occupancy).
+template <int ID, bool DEDICATED>
+__global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
+                                   const int* __restrict__ gather, const int* __restrict__ rowptr,
+                                   const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage) {
+  using T = TPCode<ID>;
+  using L = PipeLayout<ID>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + kPipeMaxStages;
+  int* sh_range = reinterpret_cast<int*>(empty + kPipeMaxStages);
+  float* stages = reinterpret_cast<float*>(smem_raw + 256);
+
+  const int nthr_c = blockDim.x - (DEDICATED ? 32 : 0);
+  const int consumer_warps = nthr_c >> 5;
+  pipe_init(full, empty, nstage, consumer_warps);
+  pipe_node_range(rowptr, N, sh_range);
+  __syncthreads();
+  const int n_begin = sh_range[0], n_end = sh_range[1];
+  if (n_begin >= n_end) return;
+
+  const int u = 2 * threadIdx.x;  // channels (u, u+1)
+  const bool active = u < C;
+  const int uc = active ? u : C - 2;
+  const int lane = threadIdx.x & 31;
+  const bool is_producer = !DEDICATED && threadIdx.x < 32;
+  const int rfl = L::r_floats(C), hfl = L::h_floats(C), sfl = L::stage_floats(C);
+  int stage = 0;
+  uint32_t phase = 0;
+  int q = __ldg(rowptr + n_begin);
+  int end = __ldg(rowptr + n_begin + 1);
+  PipeProducer<ID, true> prod{h, Y, R, gather, perm, stages, full, empty, __ldg(rowptr + n_end), C, nstage};
+  if (DEDICATED && (int)threadIdx.x >= nthr_c) {
+    prod.start(q, lane);
+    while (prod.qp < prod.q_hi) prod.issue(1 << 30, prod.q_hi, true, lane);
+    return;
+  }
+  if (is_producer) {
+    prod.start(q, lane);
+    prod.issue(nstage, q + nstage, true, lane);
+  }
+  for (int n = n_begin; n < n_end; ++n) {
+    const int end_next = (n + 2 <= N) ? __ldg(rowptr + n + 2) : end;  // prefetched one node ahead
+    float2 acc[T::DOUT];
+#pragma unroll
+    for (int k = 0; k < T::DOUT; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (; q < end; ++q) {
+      const float* st = stages + (size_t)stage * sfl;
+      if (is_producer && prod.qp <= q) prod.issue(1, q + 1, true, lane);  // never wait for an edge nobody requested
+      mbar_wait(smem_u32(full + stage), phase);
+      float2 Rv[T::NP], Yv[T::NSH], hv[T::DIN];
+#pragma unroll
+      for (int p = 0; p < T::NP; ++p) Rv[p] = *reinterpret_cast<const float2*>(st + p * C + uc);
+      T::load_h2_smem(st + rfl, C, uc, hv);
+      load_y2_smem<T::NSH, L::YPAD>(st + rfl + hfl, Yv);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(empty + stage));
+      if (++stage == nstage) {
+        stage = 0;
+        phase ^= 1u;
+      }
+      if (is_producer) prod.issue(2, q + 1 + nstage, false, lane);
+      T::fwd2(hv, Yv, Rv, acc);
+    }
+    if (active) T::store_out2(out + (size_t)n * T::DOUT * C, C, u, acc);
+    end = end_next;
+  }
+}
+
+template <int ID, bool DEDICATED, bool WANT_H, bool WANT_Y, bool WANT_R>
+__global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
+                                   const float* __restrict__ g, const int* __restrict__ gather,
+                                   const int* __restrict__ rowptr, const int* __restrict__ perm, float* __restrict__ dh,
+                                   float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage) {
+  using T = TPCode<ID>;
+  using L = PipeLayout<ID>;
+  constexpr int NV = next_pow2(T::NSH);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + kPipeMaxStages;
+  int* sh_range = reinterpret_cast<int*>(empty + kPipeMaxStages);
+  float* stages = reinterpret_cast<float*>(smem_raw + 256);
+
+  const int nthr_c = blockDim.x - (DEDICATED ? 32 : 0);
+  const int consumer_warps = nthr_c >> 5;
+  pipe_init(full, empty, nstage, consumer_warps);
+  pipe_node_range(rowptr, N, sh_range);
+  __syncthreads();
+  const int n_begin = sh_range[0], n_end = sh_range[1];
+  if (n_begin >= n_end) return;
+
+  const int u = 2 * threadIdx.x;
+  const bool active = u < C;
+  const int uc = active ? u : C - 2;
+  const int lane = threadIdx.x & 31;
+  const bool is_producer = !DEDICATED && threadIdx.x < 32;
+  const int rfl = L::r_floats(C), hfl = L::h_floats(C), sfl = L::stage_floats(C);
+  const size_t rstride = (size_t)rfl, hstride = (size_t)hfl;
+  int stage = 0;
+  uint32_t phase = 0;
+  int q = __ldg(rowptr + n_begin);
+  int end = __ldg(rowptr + n_begin + 1);
+  PipeProducer<ID, (WANT_H || WANT_Y)> prod{h, Y, R, gather, perm, stages, full, empty, __ldg(rowptr + n_end), C, nstage};
+  if (DEDICATED && (int)threadIdx.x >= nthr_c) {
+    prod.start(q, lane);
+    while (prod.qp < prod.q_hi) prod.issue(1 << 30, prod.q_hi, true, lane);
+    return;
+  }
+  if (is_producer) {
+    prod.start(q, lane);
+    prod.issue(nstage, q + nstage, true, lane);
+  }
+  for (int n = n_begin; n < n_end; ++n) {
+    const int end_next = (n + 2 <= N) ? __ldg(rowptr + n + 2) : end;
+    float2 gv[T::DOUT];
+    if (q < end) {
+      T::load_out2(g + (size_t)n * T::DOUT * C, C, uc, gv);
+      if (!active) {
+#pragma unroll
+        for (int k = 0; k < T::DOUT; ++k) gv[k] = make_float2(0.f, 0.f);
+      }
+    }
+    for (; q < end; ++q) {
+      const float* st = stages + (size_t)stage * sfl;
+      if (is_producer && prod.qp <= q) prod.issue(1, q + 1, true, lane);
+      mbar_wait(smem_u32(full + stage), phase);
+      const int2 es = reinterpret_cast<const int2*>(st + rfl + hfl + L::YPAD)[0];  // {edge id, gather id}
+      const int e = es.x;
+      float2 Rv[T::NP], Yv[T::NSH], hv[T::DIN];
+#pragma unroll
+      for (int p = 0; p < T::NP; ++p)
+        Rv[p] = (WANT_H || WANT_Y) ? *reinterpret_cast<const float2*>(st + p * C + uc) : make_float2(0.f, 0.f);
+      T::load_h2_smem(st + rfl, C, uc, hv);
+      load_y2_smem<T::NSH, L::YPAD>(st + rfl + hfl, Yv);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(empty + stage));
+      if (++stage == nstage) {
+        stage = 0;
+        phase ^= 1u;
+      }
+      if (is_producer) prod.issue(2, q + 1 + nstage, false, lane);
+
+      float2 dhv[T::DIN], dRv[T::NP];
+      float dYv[NV];
+#pragma unroll
+      for (int i = 0; i < T::DIN; ++i) dhv[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) dYv[j] = 0.f;
+      T::template bwd2<WANT_H, WANT_Y, WANT_R, NV>(hv, Yv, Rv, gv, dhv, dYv, dRv);
+
+      if (WANT_R && active) {
+#pragma unroll
+        for (int p = 0; p < T::NP; ++p) st_stream2(dR + (size_t)e * rstride + (size_t)p * C + u, dRv[p]);
+      }
+      if (WANT_H) {
+        if (active) T::atomic_add_h2(dh + (size_t)es.y * hstride, C, u, dhv);
+      }
+      if (WANT_Y) {
+        warp_reduce_vec<NV>(dYv, lane);
+        constexpr int sh = 5 - Log2<NV>::value;
+        const int j = lane >> sh;
+        if ((lane & ((1 << sh) - 1)) == 0 && j < T::NSH) {
+          if (consumer_warps == 1)
+            dY[(size_t)e * T::NSH + j] = dYv[0];
+          else
+            atomicAdd(dY + (size_t)e * T::NSH + j, dYv[0]);
+        }
+      }
+    }
+    end = end_next;
+  }
+}
+
+struct PipeCfg {
+  int nstage, smem, grid;
+};
+
+// stage count and persistent grid for a kernel instantiation (cached per C; queries only, no allocation / sync)
+template <auto kernel>  // one cache per kernel instantiation
+static bool pipe_config(int threads, int stage_bytes, int C, PipeCfg* cfg) {
+  static int cached_C = -1;
+  static PipeCfg cached;
+  static bool cached_ok = false;
+  if (C == cached_C) {
+    *cfg = cached;
+    return cached_ok;
+  }
+  int dev = 0, sms = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int nstage = (56 * 1024) / stage_bytes;
+  if (nstage > kPipeMaxStages) nstage = kPipeMaxStages;
+  if (nstage < 3) nstage = 3;
+  int smem = 256 + nstage * stage_bytes;
+  bool ok = smem <= max_optin;
+  int per_sm = 0;
+  if (ok) ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+  if (ok) ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) == cudaSuccess && per_sm > 0;
+  if (!ok) cudaGetLastError();
+  cached_C = C;
+  cached = PipeCfg{nstage, smem, per_sm * sms};
+  cached_ok = ok;
+  *cfg = cached;
+  return ok;
+}
+
+__host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 }  // namespace pml
 
 #define PML_CAT_(a, b) a##b
 #define PML_CAT(a, b) PML_CAT_(a, b)
+
+// test / profiling hook (capi.cu): PML_TP_SIMPLE=1 in the environment selects the non-pipelined kernels
+extern "C" int pml_tp_force_simple(void);
 
 // Launchers (one pair per compiled signature; dispatched by id in capi.cu).  Streams are the caller's.
 extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const float* Y, const float* R, const int* gather,
                                                        const int* rowptr, const int* perm, float* out, int N, int C,
                                                        cudaStream_t stream) {
   if (N <= 0) return PML_OK;
+  using PL = pml::PipeLayout<PML_TP_ID>;
+  const int mode = pml_tp_force_simple();  // bit0: streaming kernels; bit1 / bit2: flip the fwd / bwd producer placement
+  if (PL::supported(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
+    pml::PipeCfg cfg;
+    const bool dedicated = !(mode & 2);
+    const int threads = PL::consumer_threads(C) + (dedicated ? 32 : 0);
+    const int sbytes = PL::stage_floats(C) * 4;
+    if (dedicated) {
+      if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, true>>(threads, sbytes, C, &cfg)) {
+        pml::tp_fwd_pipe_kernel<PML_TP_ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage);
+        PML_CHECK_LAUNCH();
+        return PML_OK;
+      }
+    } else if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, false>>(threads, sbytes, C, &cfg)) {
+      pml::tp_fwd_pipe_kernel<PML_TP_ID, false><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage);
+      PML_CHECK_LAUNCH();
+      return PML_OK;
+    }
+  }
   const int nslab = (C + 31) / 32;
   const int wpb = 4;
   const long long items = (long long)N * nslab;
@@ -207,11 +627,49 @@ extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const floa
                                                        const int* gather, const int* rowptr, const int* perm, float* dh,
                                                        float* dY, float* dR, int N, int C, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
+  const int mask = (dh ? 1 : 0) | (dY ? 2 : 0) | (dR ? 4 : 0);
+  using PL = pml::PipeLayout<PML_TP_ID>;
+  const int mode = pml_tp_force_simple();
+  if (mask != 0 && PL::supported(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
+    const bool dedicated = (mode & 4) != 0;
+    const int threads = PL::consumer_threads(C) + (dedicated ? 32 : 0);
+    const int sbytes = PL::stage_floats(C) * 4;
+    pml::PipeCfg cfg;
+    bool done = false;
+#define PML_TP_BWD_PIPE_D(D_, H_, Y_, R_)                                                                               \
+  if (pml::pipe_config<pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_>>(threads, sbytes, C, &cfg)) {                  \
+    pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(                         \
+        h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, cfg.nstage);                                                \
+    done = true;                                                                                                        \
+  }
+#define PML_TP_BWD_PIPE(M, H_, Y_, R_)           \
+  case M:                                        \
+    if (dedicated) {                             \
+      PML_TP_BWD_PIPE_D(true, H_, Y_, R_)        \
+    } else {                                     \
+      PML_TP_BWD_PIPE_D(false, H_, Y_, R_)       \
+    }                                            \
+    break;
+    switch (mask) {
+      PML_TP_BWD_PIPE(1, true, false, false)
+      PML_TP_BWD_PIPE(2, false, true, false)
+      PML_TP_BWD_PIPE(3, true, true, false)
+      PML_TP_BWD_PIPE(4, false, false, true)
+      PML_TP_BWD_PIPE(5, true, false, true)
+      PML_TP_BWD_PIPE(6, false, true, true)
+      PML_TP_BWD_PIPE(7, true, true, true)
+    }
+#undef PML_TP_BWD_PIPE_D
+#undef PML_TP_BWD_PIPE
+    if (done) {
+      PML_CHECK_LAUNCH();
+      return PML_OK;
+    }
+  }
   const int nslab = (C + 31) / 32;
   const int wpb = 4;
   const long long items = (long long)N * nslab;
   const int grid = pml::ceil_div(items, wpb);
-  const int mask = (dh ? 1 : 0) | (dY ? 2 : 0) | (dR ? 4 : 0);
 #define PML_TP_BWD_CASE(M, H_, Y_, R_)                                                                              \
   case M:                                                                                                           \
     pml::tp_bwd_kernel<PML_TP_ID, H_, Y_, R_><<<grid, wpb * 32, 0, stream>>>(h, Y, R, g, gather, rowptr, perm, dh, dY, \

@@ -66,6 +66,7 @@ def test_edge_featurise(cuda, lmax, pbc):
 TP_CASES = [
     ("4x0e", 2, 4), ("4x0e+4x1o", 2, 4), ("32x0e+32x1o", 2, 32), ("8x0e+8x1o", 3, 8),
     ("128x0e+128x1o", 3, 128), ("40x0e", 3, 40), ("16x0e+16x1o+16x2e", 3, 16),
+    ("6x0e+6x1o", 2, 6),  # NP*C = 42 floats: rows are not 16-byte multiples -> register-streaming kernels
 ]
 
 
@@ -118,6 +119,45 @@ def test_tp_scatter(cuda, node_irreps, lmax, C):
     g2r = torch.autograd.grad(sr, [h, Y, R, w])
     for a, b in zip(g2, g2r):
         assert _rel(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("node_irreps,lmax,C,N,deg", [("128x0e+128x1o", 3, 128, 300, 33), ("40x0e", 3, 40, 1000, 5),
+                                                      ("32x0e+32x1o", 2, 32, 513, 17), ("16x0e+16x1o+16x2e", 3, 16, 64, 100)])
+def test_tp_pipelined_matches_streaming(cuda, node_irreps, lmax, C, N, deg):
+    """The TMA-pipelined persistent kernels (packed fp32x2 arithmetic, factored differently) and the register-streaming
+    kernels agree to fp32 rounding (1e-5 of the largest entry).  Includes isolated nodes and a node range long enough
+    that every persistent CTA owns several nodes."""
+    from physicsml_b200 import _lib, ops
+    from physicsml_b200.plans import TPPlan
+
+    g = torch.Generator().manual_seed(11)
+    ei = _edges(N, deg, g, cuda)
+    ei = ei[:, (ei[1] % 7) != 3]  # nodes 3, 10, 17, ... receive nothing
+    E = ei.shape[1]
+    _, target = _ref_tp(node_irreps, lmax, C)
+    plan = TPPlan(node_irreps, lmax, str(target))
+    h = torch.randn(N, plan.C * plan.DIN, generator=g).to(cuda)
+    Y = torch.randn(E, (lmax + 1) ** 2, generator=g).to(cuda)
+    R = torch.randn(E, plan.NP * C, generator=g).to(cuda)
+    w = torch.randn(N, plan.C * plan.DOUT, generator=g).to(cuda)
+    ep = ops.EdgePlan(ei, N)
+    res = {}
+    for simple in (0, 1):
+        old = _lib.lib().pml_tp_set_simple(simple)
+        try:
+            out = ops.tp_scatter(h, Y, R, ep.gather, ep.rowptr, ep.perm, plan.handle)
+            grads = ops.tp_scatter_bwd(h, Y, R, w, ep.gather, ep.rowptr, ep.perm, plan.handle, True, True, True)
+            only_r = ops.tp_scatter_bwd(h, Y, R, w, ep.gather, ep.rowptr, ep.perm, plan.handle, False, False, True)[2]
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().pml_tp_set_simple(old)
+        res[simple] = (out, grads, only_r)
+    assert _rel(res[0][0], res[1][0]) < 1e-5
+    assert res[0][0][3].abs().max() == 0 and res[0][0][10].abs().max() == 0
+    assert _rel(res[0][1][2], res[1][1][2]) < 1e-5  # dR
+    assert _rel(res[0][2], res[1][2]) < 1e-5  # dR alone (R itself is not read)
+    assert _rel(res[0][1][0], res[1][1][0]) < 1e-5  # dh: fp32 atomics
+    assert _rel(res[0][1][1], res[1][1][1]) < 1e-5  # dY
 
 
 def test_tp_scatter_grouped_edges(cuda):
