@@ -294,13 +294,13 @@ def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
     L.append("  }")
     # fp32 reductions into dh[s]: the 2(2l+1) floats of channels (u, u+1) of one block are contiguous and 8-byte
     # aligned (u even) -> (2l+1) vector reds instead of 2(2l+1) scalar ones
-    L.append("  __device__ __forceinline__ static void atomic_add_h2(float* __restrict__ hrow, int C, int u, const float2 (&h)[DIN]) {")
+    L.append("  __device__ __forceinline__ static void atomic_add_h2(float* __restrict__ hrow, int C, int u, const float2 (&h)[DIN], uint64_t pol) {")
     off = 0
     for l, _ in spec.node_ls:
         d = 2 * l + 1
         flat = [f"h[{off + i}].x" for i in range(d)] + [f"h[{off + i}].y" for i in range(d)]
         for v in range(d):
-            L.append(f"    red_add_f32x2(hrow + (size_t)C * {off} + (size_t)u * {d} + {2 * v}, {flat[2 * v]}, {flat[2 * v + 1]});")
+            L.append(f"    red_add_f32x2(hrow + (size_t)C * {off} + (size_t)u * {d} + {2 * v}, {flat[2 * v]}, {flat[2 * v + 1]}, pol);")
         off += d
     L.append("  }")
 

@@ -43,9 +43,9 @@ __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return _
 __device__ __forceinline__ float2 f2dup(float s) { return make_float2(s, s); }
 __device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
 
-// *(float2*)p += (a, b) without a return value (p 8-byte aligned)
-__device__ __forceinline__ void red_add_f32x2(float* p, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+// *(float2*)p += (a, b) without a return value (p 8-byte aligned), with an L2 eviction policy (createpolicy)
+__device__ __forceinline__ void red_add_f32x2(float* p, float a, float b, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(a), "f"(b), "l"(pol) : "memory");
 }
 
 __device__ __forceinline__ void st_stream2(float* p, float2 v) {

@@ -223,6 +223,29 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// L2 eviction policies: R / dR are touched exactly once (evict-first) so that the gathered node rows, the dh rows
+// under reduction and Y stay resident; without them ncu shows 13.8 GB (fwd) / 30.8 GB (cotangent) of DRAM traffic for
+// 11.1 / 21.7 GB of algorithmic bytes at config 4 — the stream keeps flushing the 49 MB of node rows out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void st_stream2_hint(float* p, float2 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -231,16 +254,6 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 }
 
 constexpr int kPipeMaxStages = 8;
-
-// first index i in [0, n] with a[i] >= v   (a non-decreasing, n+1 entries)
-__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int n, long long v) {
-  int lo = 0, hi = n + 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if ((long long)__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 template <int ID>
 struct PipeLayout {
@@ -256,16 +269,28 @@ struct PipeLayout {
   __host__ __device__ static int consumer_threads(int C) { return ((C / 2 + 31) / 32) * 32; }
 };
 
-// The CTA's node range: node n belongs to CTA b iff  E*b/G <= rowptr[n] < E*(b+1)/G  (last CTA: <= E), so every node,
-// including the ones without edges, has exactly one owner and the owners' edge ranges tile [0, E).
-__device__ __forceinline__ void pipe_node_range(const int* __restrict__ rowptr, int N, int* sh_range) {
-  if (threadIdx.x < 2) {
-    const int E = __ldg(rowptr + N);
-    const long long G = gridDim.x, b = blockIdx.x + threadIdx.x;
-    const long long v = (b >= G) ? (long long)E + 1 : ((long long)E * b) / G;
-    int n = lower_bound_i32(rowptr, N, v);
-    sh_range[threadIdx.x] = n < N ? n : N;
-  }
+// Work distribution: the node range is cut into tiles of TN consecutive scatter nodes (~kTileEdges edges each) and
+// CTA b takes tiles b, b+G, b+2G, ...  All CTAs advance at about the same pace, so at any moment the grid works on one
+// window of ~G consecutive tiles: the node rows it gathers (h) and reduces into (dh) are shared through L2 while they
+// are hot instead of being spread over the whole kernel duration (with one contiguous block of nodes per CTA the
+// cotangent kernel moved 29 GB through DRAM for 21.7 GB of algorithmic traffic: dh rows were evicted between reds).
+constexpr int kTileEdges = 512;
+
+struct TileSched {
+  int TN, ntiles, G;  // nodes per tile, number of tiles, CTAs that take part (the others exit)
+};
+
+__device__ __forceinline__ TileSched tile_schedule(const int* __restrict__ rowptr, int N) {
+  const int E = __ldg(rowptr + N);
+  long long want = (long long)E / kTileEdges;  // tiles of ~kTileEdges edges ...
+  if (want < (long long)gridDim.x) want = gridDim.x;  // ... but at least one per CTA
+  TileSched t;
+  t.TN = (int)((long long)N / want);
+  if (t.TN < 1) t.TN = 1;
+  t.ntiles = (N + t.TN - 1) / t.TN;
+  const int waves = (t.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  t.G = (t.ntiles + waves - 1) / waves;  // same number of waves with an even share per CTA
+  return t;
 }
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -280,43 +305,66 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Producer state, carried by warp 0 of the CTA next to its consumer work (no dedicated warp: a third warp would hold
-// a third of the CTA's registers just to issue copies).  Walks edges [q_lo, q_hi) of the CTA; the (edge id, gather
-// id) pairs are fetched 32 edges at a time, one chunk ahead, and broadcast with shuffles.
+// Producer: walks the CTA's tiles edge by edge.  The (edge id, gather id) pairs are fetched 32 edges at a time, one
+// chunk ahead (the chunk after the current one may already belong to the next tile), the bounds of the next tile one
+// tile ahead, so no load is ever waited for right after it was issued; edges are handed out with shuffles.
+constexpr int kPipeHeaderBytes = 256;  // 16 mbarriers (128 B) + spare, then the stage ring
+
 template <int ID, bool LOAD_R>
 struct PipeProducer {
   using L = PipeLayout<ID>;
   using T = TPCode<ID>;
   const float *h, *Y, *R;
-  const int *gather, *perm;
+  const int *gather, *perm, *rowptr;
   float* stages;
   uint64_t *full, *empty;
-  int q_hi, C, nstage;
-  int qp;     // next edge to issue
-  int pos;    // its position inside the current 32-edge index chunk
-  int stage;  // ring slot it goes to
+  int N, C, nstage;
+  TileSched ts;
+  int ftile, fq, fq_hi;  // fetch cursor: tile being fetched and its remaining edge range
+  int nq, nq_hi;         // edge range of the CTA's next tile (prefetched)
+  int issued;            // edges issued so far
+  int pos;               // position inside the current chunk
+  int stage;             // ring slot the next edge goes to
   uint32_t phase;
-  int e_cur, s_cur, e_nxt, s_nxt;
+  int e_cur, s_cur, cnt_cur, e_nxt, s_nxt, cnt_nxt;
 
-  __device__ __forceinline__ void fetch(int q0, int lane, int& e, int& s) const {
-    const int q = q0 + lane;
-    e = 0, s = 0;
-    if (q < q_hi) {
+  __device__ __forceinline__ void tile_bounds(int tile, int& q, int& q_hi) const {
+    q = 0, q_hi = 0;
+    if (tile < ts.ntiles) {
+      const int n0 = tile * ts.TN, n1 = min(N, n0 + ts.TN);
+      q = __ldg(rowptr + n0), q_hi = __ldg(rowptr + n1);
+    }
+  }
+  __device__ __forceinline__ void fetch(int lane, int& e, int& s, int& cnt) {
+    while (fq >= fq_hi && ftile < ts.ntiles) {  // next non-empty tile of this CTA
+      ftile += ts.G;
+      fq = nq, fq_hi = nq_hi;
+      tile_bounds(ftile + ts.G, nq, nq_hi);
+    }
+    e = 0, s = 0, cnt = 0;
+    if (ftile >= ts.ntiles) return;
+    cnt = min(32, fq_hi - fq);
+    if (lane < cnt) {
+      const int q = fq + lane;
       e = perm ? __ldg(perm + q) : q;
       s = __ldg(gather + e);
     }
+    fq += cnt;
   }
-  __device__ __forceinline__ void start(int q_lo, int lane) {
-    qp = q_lo, pos = 0, stage = 0, phase = 0;
-    fetch(q_lo, lane, e_cur, s_cur);
-    fetch(q_lo + 32, lane, e_nxt, s_nxt);
+  __device__ __forceinline__ void start(int lane) {
+    issued = 0, pos = 0, stage = 0, phase = 0;
+    ftile = blockIdx.x;
+    tile_bounds(ftile, fq, fq_hi);
+    tile_bounds(ftile + ts.G, nq, nq_hi);
+    fetch(lane, e_cur, s_cur, cnt_cur);
+    fetch(lane, e_nxt, s_nxt, cnt_nxt);
   }
-  // issue up to `limit` edges, at most up to edge index `bound` (exclusive); a slot still being read by another
-  // consumer warp ends the attempt unless `blocking`
-  __device__ __forceinline__ void issue(int limit, int bound, bool blocking, int lane) {
+  __device__ __forceinline__ bool done() const { return cnt_cur == 0; }
+  // issue up to `limit` edges while fewer than `max_ahead` edges are in flight beyond `consumed`; a slot still being
+  // read by another consumer warp ends the attempt unless `blocking`
+  __device__ __forceinline__ void issue(int limit, int consumed, int max_ahead, bool blocking, int lane) {
     const int rfl = L::r_floats(C), hfl = L::h_floats(C), sfl = L::stage_floats(C);
-    if (bound > q_hi) bound = q_hi;
-    for (int n = 0; n < limit && qp < bound; ++n) {
+    for (int n = 0; n < limit && cnt_cur > 0 && issued - consumed < max_ahead; ++n) {
       const uint32_t eb = smem_u32(empty + stage);
       if (blocking)
         mbar_wait(eb, phase ^ 1u);
@@ -329,20 +377,20 @@ struct PipeProducer {
       if (lane == 0) {
         reinterpret_cast<int2*>(st + rfl + hfl + L::YPAD)[0] = make_int2(e, s);  // released by the arrive below
         mbar_expect_tx(fb, (LOAD_R ? (uint32_t)rfl * 4u : 0u) + (uint32_t)hfl * 4u);
-        if (LOAD_R) bulk_g2s(smem_u32(st), R + (size_t)e * rfl, (uint32_t)rfl * 4u, fb);
-        bulk_g2s(smem_u32(st + rfl), h + (size_t)s * hfl, (uint32_t)hfl * 4u, fb);
+        if (LOAD_R) bulk_g2s_hint(smem_u32(st), R + (size_t)e * rfl, (uint32_t)rfl * 4u, fb, l2_policy_evict_first());
+        bulk_g2s_hint(smem_u32(st + rfl), h + (size_t)s * hfl, (uint32_t)hfl * 4u, fb, l2_policy_evict_last());
       }
       if (lane < 2 * T::NSH) cp_async4(smem_u32(st + rfl + hfl + lane), Y + (size_t)e * T::NSH + (lane >> 1));
       cp_async_mbar_arrive_noinc(fb);
-      ++qp;
+      ++issued;
       if (++stage == nstage) {
         stage = 0;
         phase ^= 1u;
       }
-      if (++pos == 32) {
+      if (++pos == cnt_cur) {
         pos = 0;
-        e_cur = e_nxt, s_cur = s_nxt;
-        fetch(qp + 32, lane, e_nxt, s_nxt);
+        e_cur = e_nxt, s_cur = s_nxt, cnt_cur = cnt_nxt;
+        if (cnt_cur > 0) fetch(lane, e_nxt, s_nxt, cnt_nxt);
       }
     }
   }
@@ -374,71 +422,76 @@ __device__ __forceinline__ void load_y2_smem(const float* ys, float2 (&Yv)[NSH])
 // blockDim.x = 32*ceil(C/64) consumer threads: two channels each, packed fp32x2 arithmetic.  The copies are issued by
 // a dedicated extra warp (DEDICATED: the ring is refilled the moment a slot is released, independent of anybody's
 // arithmetic) or by warp 0 between its own edges (no extra warp: a third more CTAs fit when registers bound occupancy).
+#define PML_PIPE_PROLOGUE(LOAD_R_)                                                                                     \
+  extern __shared__ __align__(128) unsigned char smem_raw[];                                                           \
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                                              \
+  uint64_t* empty = full + kPipeMaxStages;                                                                             \
+  float* stages = reinterpret_cast<float*>(smem_raw + kPipeHeaderBytes);                                               \
+  const int nthr_c = blockDim.x - (DEDICATED ? 32 : 0);                                                                \
+  const int consumer_warps = nthr_c >> 5;                                                                              \
+  const TileSched ts = tile_schedule(rowptr, N);                                                                       \
+  if ((int)blockIdx.x >= ts.G) return;                                                                                 \
+  pipe_init(full, empty, nstage, consumer_warps);                                                                      \
+  __syncthreads();                                                                                                     \
+  const int lane = threadIdx.x & 31;                                                                                   \
+  const bool is_producer = !DEDICATED && threadIdx.x < 32;                                                             \
+  PipeProducer<ID, LOAD_R_> prod;                                                                                      \
+  prod.h = h, prod.Y = Y, prod.R = R, prod.gather = gather, prod.perm = perm, prod.rowptr = rowptr;                    \
+  prod.stages = stages, prod.full = full, prod.empty = empty, prod.N = N, prod.C = C, prod.nstage = nstage, prod.ts = ts; \
+  if (DEDICATED && (int)threadIdx.x >= nthr_c) {                                                                       \
+    prod.start(lane);                                                                                                  \
+    while (!prod.done()) prod.issue(1 << 30, 0, 1 << 30, true, lane);                                                  \
+    return;                                                                                                            \
+  }                                                                                                                    \
+  if (is_producer) {                                                                                                   \
+    prod.start(lane);                                                                                                  \
+    prod.issue(nstage, 0, nstage, true, lane);                                                                         \
+  }                                                                                                                    \
+  const int u = 2 * threadIdx.x; /* channels (u, u+1) */                                                               \
+  const bool active = u < C;                                                                                           \
+  const int uc = active ? u : C - 2;                                                                                   \
+  const int rfl = L::r_floats(C), hfl = L::h_floats(C), sfl = L::stage_floats(C);                                      \
+  int stage = 0, consumed = 0;                                                                                         \
+  uint32_t phase = 0;
+
 template <int ID, bool DEDICATED>
 __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                    const int* __restrict__ gather, const int* __restrict__ rowptr,
                                    const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage) {
   using T = TPCode<ID>;
   using L = PipeLayout<ID>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + kPipeMaxStages;
-  int* sh_range = reinterpret_cast<int*>(empty + kPipeMaxStages);
-  float* stages = reinterpret_cast<float*>(smem_raw + 256);
-
-  const int nthr_c = blockDim.x - (DEDICATED ? 32 : 0);
-  const int consumer_warps = nthr_c >> 5;
-  pipe_init(full, empty, nstage, consumer_warps);
-  pipe_node_range(rowptr, N, sh_range);
-  __syncthreads();
-  const int n_begin = sh_range[0], n_end = sh_range[1];
-  if (n_begin >= n_end) return;
-
-  const int u = 2 * threadIdx.x;  // channels (u, u+1)
-  const bool active = u < C;
-  const int uc = active ? u : C - 2;
-  const int lane = threadIdx.x & 31;
-  const bool is_producer = !DEDICATED && threadIdx.x < 32;
-  const int rfl = L::r_floats(C), hfl = L::h_floats(C), sfl = L::stage_floats(C);
-  int stage = 0;
-  uint32_t phase = 0;
-  int q = __ldg(rowptr + n_begin);
-  int end = __ldg(rowptr + n_begin + 1);
-  PipeProducer<ID, true> prod{h, Y, R, gather, perm, stages, full, empty, __ldg(rowptr + n_end), C, nstage};
-  if (DEDICATED && (int)threadIdx.x >= nthr_c) {
-    prod.start(q, lane);
-    while (prod.qp < prod.q_hi) prod.issue(1 << 30, prod.q_hi, true, lane);
-    return;
-  }
-  if (is_producer) {
-    prod.start(q, lane);
-    prod.issue(nstage, q + nstage, true, lane);
-  }
-  for (int n = n_begin; n < n_end; ++n) {
-    const int end_next = (n + 2 <= N) ? __ldg(rowptr + n + 2) : end;  // prefetched one node ahead
-    float2 acc[T::DOUT];
+  PML_PIPE_PROLOGUE(true)
+  for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
+    const int n0 = tile * ts.TN, n1 = min(N, n0 + ts.TN);
+    int q = __ldg(rowptr + n0);
+    int end = __ldg(rowptr + n0 + 1);
+    for (int n = n0; n < n1; ++n) {
+      const int end_next = (n + 2 <= N) ? __ldg(rowptr + n + 2) : end;  // prefetched one node ahead
+      float2 acc[T::DOUT];
 #pragma unroll
-    for (int k = 0; k < T::DOUT; ++k) acc[k] = make_float2(0.f, 0.f);
-    for (; q < end; ++q) {
-      const float* st = stages + (size_t)stage * sfl;
-      if (is_producer && prod.qp <= q) prod.issue(1, q + 1, true, lane);  // never wait for an edge nobody requested
-      mbar_wait(smem_u32(full + stage), phase);
-      float2 Rv[T::NP], Yv[T::NSH], hv[T::DIN];
+      for (int k = 0; k < T::DOUT; ++k) acc[k] = make_float2(0.f, 0.f);
+      for (; q < end; ++q) {
+        const float* st = stages + (size_t)stage * sfl;
+        if (is_producer && prod.issued == consumed) prod.issue(1, consumed, 1, true, lane);  // never wait for an edge nobody requested
+        mbar_wait(smem_u32(full + stage), phase);
+        float2 Rv[T::NP], Yv[T::NSH], hv[T::DIN];
 #pragma unroll
-      for (int p = 0; p < T::NP; ++p) Rv[p] = *reinterpret_cast<const float2*>(st + p * C + uc);
-      T::load_h2_smem(st + rfl, C, uc, hv);
-      load_y2_smem<T::NSH, L::YPAD>(st + rfl + hfl, Yv);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(empty + stage));
-      if (++stage == nstage) {
-        stage = 0;
-        phase ^= 1u;
+        for (int p = 0; p < T::NP; ++p) Rv[p] = *reinterpret_cast<const float2*>(st + p * C + uc);
+        T::load_h2_smem(st + rfl, C, uc, hv);
+        load_y2_smem<T::NSH, L::YPAD>(st + rfl + hfl, Yv);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty + stage));
+        if (++stage == nstage) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        ++consumed;
+        if (is_producer) prod.issue(2, consumed, nstage, false, lane);
+        T::fwd2(hv, Yv, Rv, acc);
       }
-      if (is_producer) prod.issue(2, q + 1 + nstage, false, lane);
-      T::fwd2(hv, Yv, Rv, acc);
+      if (active) T::store_out2(out + (size_t)n * T::DOUT * C, C, u, acc);
+      end = end_next;
     }
-    if (active) T::store_out2(out + (size_t)n * T::DOUT * C, C, u, acc);
-    end = end_next;
   }
 }
 
@@ -450,101 +503,77 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
   using T = TPCode<ID>;
   using L = PipeLayout<ID>;
   constexpr int NV = next_pow2(T::NSH);
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + kPipeMaxStages;
-  int* sh_range = reinterpret_cast<int*>(empty + kPipeMaxStages);
-  float* stages = reinterpret_cast<float*>(smem_raw + 256);
-
-  const int nthr_c = blockDim.x - (DEDICATED ? 32 : 0);
-  const int consumer_warps = nthr_c >> 5;
-  pipe_init(full, empty, nstage, consumer_warps);
-  pipe_node_range(rowptr, N, sh_range);
-  __syncthreads();
-  const int n_begin = sh_range[0], n_end = sh_range[1];
-  if (n_begin >= n_end) return;
-
-  const int u = 2 * threadIdx.x;
-  const bool active = u < C;
-  const int uc = active ? u : C - 2;
-  const int lane = threadIdx.x & 31;
-  const bool is_producer = !DEDICATED && threadIdx.x < 32;
-  const int rfl = L::r_floats(C), hfl = L::h_floats(C), sfl = L::stage_floats(C);
+  PML_PIPE_PROLOGUE((WANT_H || WANT_Y))
   const size_t rstride = (size_t)rfl, hstride = (size_t)hfl;
-  int stage = 0;
-  uint32_t phase = 0;
-  int q = __ldg(rowptr + n_begin);
-  int end = __ldg(rowptr + n_begin + 1);
-  PipeProducer<ID, (WANT_H || WANT_Y)> prod{h, Y, R, gather, perm, stages, full, empty, __ldg(rowptr + n_end), C, nstage};
-  if (DEDICATED && (int)threadIdx.x >= nthr_c) {
-    prod.start(q, lane);
-    while (prod.qp < prod.q_hi) prod.issue(1 << 30, prod.q_hi, true, lane);
-    return;
-  }
-  if (is_producer) {
-    prod.start(q, lane);
-    prod.issue(nstage, q + nstage, true, lane);
-  }
-  for (int n = n_begin; n < n_end; ++n) {
-    const int end_next = (n + 2 <= N) ? __ldg(rowptr + n + 2) : end;
-    float2 gv[T::DOUT];
-    if (q < end) {
-      T::load_out2(g + (size_t)n * T::DOUT * C, C, uc, gv);
-      if (!active) {
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
+    const int n0 = tile * ts.TN, n1 = min(N, n0 + ts.TN);
+    int q = __ldg(rowptr + n0);
+    int end = __ldg(rowptr + n0 + 1);
+    for (int n = n0; n < n1; ++n) {
+      const int end_next = (n + 2 <= N) ? __ldg(rowptr + n + 2) : end;
+      float2 gv[T::DOUT];
+      if (q < end) {
+        T::load_out2(g + (size_t)n * T::DOUT * C, C, uc, gv);
+        if (!active) {
 #pragma unroll
-        for (int k = 0; k < T::DOUT; ++k) gv[k] = make_float2(0.f, 0.f);
-      }
-    }
-    for (; q < end; ++q) {
-      const float* st = stages + (size_t)stage * sfl;
-      if (is_producer && prod.qp <= q) prod.issue(1, q + 1, true, lane);
-      mbar_wait(smem_u32(full + stage), phase);
-      const int2 es = reinterpret_cast<const int2*>(st + rfl + hfl + L::YPAD)[0];  // {edge id, gather id}
-      const int e = es.x;
-      float2 Rv[T::NP], Yv[T::NSH], hv[T::DIN];
-#pragma unroll
-      for (int p = 0; p < T::NP; ++p)
-        Rv[p] = (WANT_H || WANT_Y) ? *reinterpret_cast<const float2*>(st + p * C + uc) : make_float2(0.f, 0.f);
-      T::load_h2_smem(st + rfl, C, uc, hv);
-      load_y2_smem<T::NSH, L::YPAD>(st + rfl + hfl, Yv);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(empty + stage));
-      if (++stage == nstage) {
-        stage = 0;
-        phase ^= 1u;
-      }
-      if (is_producer) prod.issue(2, q + 1 + nstage, false, lane);
-
-      float2 dhv[T::DIN], dRv[T::NP];
-      float dYv[NV];
-#pragma unroll
-      for (int i = 0; i < T::DIN; ++i) dhv[i] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < NV; ++j) dYv[j] = 0.f;
-      T::template bwd2<WANT_H, WANT_Y, WANT_R, NV>(hv, Yv, Rv, gv, dhv, dYv, dRv);
-
-      if (WANT_R && active) {
-#pragma unroll
-        for (int p = 0; p < T::NP; ++p) st_stream2(dR + (size_t)e * rstride + (size_t)p * C + u, dRv[p]);
-      }
-      if (WANT_H) {
-        if (active) T::atomic_add_h2(dh + (size_t)es.y * hstride, C, u, dhv);
-      }
-      if (WANT_Y) {
-        warp_reduce_vec<NV>(dYv, lane);
-        constexpr int sh = 5 - Log2<NV>::value;
-        const int j = lane >> sh;
-        if ((lane & ((1 << sh) - 1)) == 0 && j < T::NSH) {
-          if (consumer_warps == 1)
-            dY[(size_t)e * T::NSH + j] = dYv[0];
-          else
-            atomicAdd(dY + (size_t)e * T::NSH + j, dYv[0]);
+          for (int k = 0; k < T::DOUT; ++k) gv[k] = make_float2(0.f, 0.f);
         }
       }
+      for (; q < end; ++q) {
+        const float* st = stages + (size_t)stage * sfl;
+        if (is_producer && prod.issued == consumed) prod.issue(1, consumed, 1, true, lane);
+        mbar_wait(smem_u32(full + stage), phase);
+        const int2 es = reinterpret_cast<const int2*>(st + rfl + hfl + L::YPAD)[0];  // {edge id, gather id}
+        const int e = es.x;
+        float2 Rv[T::NP], Yv[T::NSH], hv[T::DIN];
+#pragma unroll
+        for (int p = 0; p < T::NP; ++p)
+          Rv[p] = (WANT_H || WANT_Y) ? *reinterpret_cast<const float2*>(st + p * C + uc) : make_float2(0.f, 0.f);
+        T::load_h2_smem(st + rfl, C, uc, hv);
+        load_y2_smem<T::NSH, L::YPAD>(st + rfl + hfl, Yv);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty + stage));
+        if (++stage == nstage) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        ++consumed;
+        if (is_producer) prod.issue(2, consumed, nstage, false, lane);
+
+        float2 dhv[T::DIN], dRv[T::NP];
+        float dYv[NV];
+#pragma unroll
+        for (int i = 0; i < T::DIN; ++i) dhv[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) dYv[j] = 0.f;
+        T::template bwd2<WANT_H, WANT_Y, WANT_R, NV>(hv, Yv, Rv, gv, dhv, dYv, dRv);
+
+        if (WANT_R && active) {
+          float* drow = dR + (size_t)e * rstride + u;
+#pragma unroll
+          for (int p = 0; p < T::NP; ++p) st_stream2_hint(drow + p * C, dRv[p], pol_stream);
+        }
+        if (WANT_H) {
+          if (active) T::atomic_add_h2(dh + (size_t)es.y * hstride, C, u, dhv, pol_keep);
+        }
+        if (WANT_Y) {
+          warp_reduce_vec<NV>(dYv, lane);
+          constexpr int sh = 5 - Log2<NV>::value;
+          const int j = lane >> sh;
+          if ((lane & ((1 << sh) - 1)) == 0 && j < T::NSH) {
+            if (consumer_warps == 1)
+              dY[(size_t)e * T::NSH + j] = dYv[0];
+            else
+              atomicAdd(dY + (size_t)e * T::NSH + j, dYv[0]);
+          }
+        }
+      }
+      end = end_next;
     }
-    end = end_next;
   }
 }
+#undef PML_PIPE_PROLOGUE
 
 struct PipeCfg {
   int nstage, smem, grid;
@@ -567,7 +596,7 @@ static bool pipe_config(int threads, int stage_bytes, int C, PipeCfg* cfg) {
   int nstage = (56 * 1024) / stage_bytes;
   if (nstage > kPipeMaxStages) nstage = kPipeMaxStages;
   if (nstage < 3) nstage = 3;
-  int smem = 256 + nstage * stage_bytes;
+  int smem = kPipeHeaderBytes + nstage * stage_bytes;
   bool ok = smem <= max_optin;
   int per_sm = 0;
   if (ok) ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
