@@ -138,6 +138,25 @@ int pml_element_linear_bwd_w(const float* x, const float* g, const float* attrs,
 /* kind 0 SiLU / 1 tanh; order 0: y=c f(x); 1: y=g c f'(x); 2: y=g v c f''(x)   (normalize2mom activations) */
 int pml_act(const float* x, const float* g, const float* v, float c, int kind, int order, float* y, long long n,
             pml_stream_t stream);
+/* ---- NequIP gate non-linearity -------------------------------------------------------------------------------------
+ * Replaces Gate.forward (models/nequip/modules/_gate.py:131-152; built in convnet_layer.py:44-77): e3nn nn.Extract
+ * slicing + Activation (normalize2mom SiLU / tanh) + o3.ElementwiseTensorProduct + concatenation in one pass over the
+ * sorted convolution-output row.  mode 0: out0 = y [N,d_out]; mode 1: out0 = dx [N,d_in] given dy; mode 2: given v
+ * (cotangent of dx) out0 = ddy [N,d_out], out1 = ddx [N,d_in]. */
+#define PML_GATE_MAX_SEG 8
+typedef struct {
+  int n_scal;
+  int s_in[PML_GATE_MAX_SEG], s_out[PML_GATE_MAX_SEG], s_mul[PML_GATE_MAX_SEG], s_kind[PML_GATE_MAX_SEG];
+  float s_c[PML_GATE_MAX_SEG];
+  int n_gated;
+  int g_x[PML_GATE_MAX_SEG], g_gate[PML_GATE_MAX_SEG], g_out[PML_GATE_MAX_SEG], g_mul[PML_GATE_MAX_SEG];
+  int g_d[PML_GATE_MAX_SEG], g_kind[PML_GATE_MAX_SEG];
+  float g_c[PML_GATE_MAX_SEG];
+  int d_in, d_out, items;
+} pml_gate_plan;
+int pml_gate(const float* x, const float* dy, const float* v, const pml_gate_plan* plan, int mode, float* out0,
+             float* out1, int N, pml_stream_t stream);
+
 /* per-graph pooled readout (models/mace/modules/mace.py:252-258): out[batch[n],f] += x[n,f]; out zero-initialised */
 int pml_pool_sum(const float* x, const long long* batch, float* out, int N, int F, pml_stream_t stream);
 int pml_pool_gather(const float* g, const long long* batch, float* out, int N, int F, pml_stream_t stream);

@@ -57,6 +57,22 @@ class ElPlan(C.Structure):
     ]
 
 
+GATE_MAX_SEG = 8
+
+
+class GatePlanStruct(C.Structure):
+    _fields_ = [
+        ("n_scal", C.c_int),
+        ("s_in", C.c_int * GATE_MAX_SEG), ("s_out", C.c_int * GATE_MAX_SEG), ("s_mul", C.c_int * GATE_MAX_SEG),
+        ("s_kind", C.c_int * GATE_MAX_SEG), ("s_c", C.c_float * GATE_MAX_SEG),
+        ("n_gated", C.c_int),
+        ("g_x", C.c_int * GATE_MAX_SEG), ("g_gate", C.c_int * GATE_MAX_SEG), ("g_out", C.c_int * GATE_MAX_SEG),
+        ("g_mul", C.c_int * GATE_MAX_SEG), ("g_d", C.c_int * GATE_MAX_SEG), ("g_kind", C.c_int * GATE_MAX_SEG),
+        ("g_c", C.c_float * GATE_MAX_SEG),
+        ("d_in", C.c_int), ("d_out", C.c_int), ("items", C.c_int),
+    ]
+
+
 class NLCell(C.Structure):
     _fields_ = [("inv", C.c_double * 9), ("cell", C.c_float * 9), ("nb", C.c_int * 3), ("R", C.c_int * 3), ("rc2", C.c_float)]
 
@@ -94,6 +110,7 @@ SIGNATURES = {
     "pml_element_linear_bwd_x": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
     "pml_element_linear_bwd_w": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
     "pml_act": [_P, _P, _P, _F, _I, _I, _P, _LL, _P],
+    "pml_gate": [_P, _P, _P, C.POINTER(GatePlanStruct), _I, _P, _P, _I, _P],
     "pml_pool_sum": [_P, _P, _P, _I, _I, _P],
     "pml_pool_gather": [_P, _P, _P, _I, _I, _P],
     "pml_csr_rowptr": [_P, _P, _P, _I, _I, _P],

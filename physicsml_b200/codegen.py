@@ -46,23 +46,26 @@ def default_tp_specs() -> list[so3.TPSpec]:
         add("1x0e+1x1o", lmax, tgt)
         if lmax >= 2:
             add("1x0e+1x1o+1x2e", lmax, tgt)
-    # NequIP (parity=True): hidden = F x {0e,0o,1e,1o,2e,2o} restricted to what is reachable layer by layer
-    for lmax in (1, 2):
-        hidden = [(1, l, p) for l in range(lmax + 1) for p in (1, -1)]
-        hidden, _ = so3.sort_irreps(hidden)
-        node = [(1, 0, 1)]
-        for _layer in range(4):
-            # conv_irreps_out = scalars + gates + gated that are reachable (convnet_layer.py:45-81)
-            reach = set()
-            for _, l1, p1 in node:
-                for l2 in range(lmax + 1):
-                    for l3 in range(abs(l1 - l2), l1 + l2 + 1):
-                        reach.add((l3, p1 * (-1) ** l2))
-            out = [(1, l, p) for _, l, p in hidden if (l, p) in reach]
-            gate_ir = (0, 1) if (0, 1) in reach else (0, -1)
-            tgt = sorted(set([(l, p) for _, l, p in out] + [gate_ir]))
-            add(so3.irreps_str(node), lmax, so3.irreps_str([(1, l, p) for l, p in tgt]))
-            node = out
+    # NequIP: hidden = F x {l e} (+ {l o} when parity=True), restricted to what is reachable layer by layer
+    # (nequip.py:68-100, convnet_layer.py:44-81); sh parity -1 (parity=True) or +1 (parity=False)
+    for sh_parity in (-1, 1):
+        for lmax in (1, 2):
+            hidden = [(1, l, 1) for l in range(lmax + 1)]
+            if sh_parity == -1:
+                hidden += [(1, l, -1) for l in range(lmax + 1)]
+            hidden, _ = so3.sort_irreps(hidden)
+            node = [(1, 0, 1)]
+            for _layer in range(4):
+                reach = set()
+                for _, l1, p1 in node:
+                    for l2 in range(lmax + 1):
+                        for l3 in range(abs(l1 - l2), l1 + l2 + 1):
+                            reach.add((l3, p1 * sh_parity**l2))
+                out = [(1, l, p) for _, l, p in hidden if (l, p) in reach]
+                gate_ir = (0, 1) if (0, 1) in reach else (0, -1)
+                tgt = sorted(set([(l, p) for _, l, p in out] + [gate_ir]))
+                add(so3.irreps_str(node), lmax, so3.irreps_str([(1, l, p) for l, p in tgt]), sh_parity)
+                node = out
     return list(specs.values())
 
 

@@ -283,7 +283,7 @@ struct TileSched {
 __device__ __forceinline__ TileSched tile_schedule(const int* __restrict__ rowptr, int N) {
   const int E = __ldg(rowptr + N);
   long long want = (long long)E / kTileEdges;  // tiles of ~kTileEdges edges ...
-  if (want < (long long)gridDim.x) want = gridDim.x;  // ... but at least one per CTA
+  if (want < 3ll * gridDim.x) want = 3ll * gridDim.x;  // ... but at least three per CTA (evens out the tile sizes)
   TileSched t;
   t.TN = (int)((long long)N / want);
   if (t.TN < 1) t.TN = 1;

@@ -723,6 +723,73 @@ def _act_bwd_bwd(ctx, v):
 act_bwd.register_autograd(_act_bwd_bwd, setup_context=_act_bwd_setup)
 
 
+# NequIP gate (reference nequip/modules/_gate.py:131-152): value, cotangent map, derivative of the cotangent map
+@torch.library.custom_op(f"{NS}::gate", mutates_args=(), device_types="cuda")
+def gate(x: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    x = _f32c(x)
+    y = x.new_empty(x.shape[0], pl.d_out)
+    _call("pml_gate", _p(x), None, None, C.byref(pl.c_plan), 0, _p(y), None, x.shape[0], _stream())
+    return y
+
+
+@gate.register_fake
+def _(x, plan):
+    return x.new_empty(x.shape[0], plans.get(plan).d_out)
+
+
+@torch.library.custom_op(f"{NS}::gate_bwd", mutates_args=(), device_types="cuda")
+def gate_bwd(x: Tensor, dy: Tensor, plan: int) -> Tensor:
+    pl = plans.get(plan)
+    x, dy = _f32c(x), _f32c(dy)
+    dx = torch.empty_like(x)
+    _call("pml_gate", _p(x), _p(dy), None, C.byref(pl.c_plan), 1, _p(dx), None, x.shape[0], _stream())
+    return dx
+
+
+@gate_bwd.register_fake
+def _(x, dy, plan):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op(f"{NS}::gate_bwd2", mutates_args=(), device_types="cuda")
+def gate_bwd2(x: Tensor, dy: Tensor, v: Tensor, plan: int) -> Tuple[Tensor, Tensor]:
+    """(ddy, ddx): gradients of <v, gate_bwd(x, dy)> w.r.t. dy and x"""
+    pl = plans.get(plan)
+    x, dy, v = _f32c(x), _f32c(dy), _f32c(v)
+    ddy, ddx = torch.empty_like(dy), torch.empty_like(x)
+    _call("pml_gate", _p(x), _p(dy), _p(v), C.byref(pl.c_plan), 2, _p(ddy), _p(ddx), x.shape[0], _stream())
+    return ddy, ddx
+
+
+@gate_bwd2.register_fake
+def _(x, dy, v, plan):
+    return torch.empty_like(dy), torch.empty_like(x)
+
+
+def _gate_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+    ctx.plan = inputs[1]
+
+
+gate.register_autograd(lambda ctx, g: (gate_bwd(ctx.saved_tensors[0], g, ctx.plan), None), setup_context=_gate_setup)
+
+
+def _gate_bwd_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.plan = inputs[2]
+
+
+def _gate_bwd_bwd(ctx, v):
+    x, dy = ctx.saved_tensors
+    nx, ng = ctx.needs_input_grad[:2]
+    ddy, ddx = gate_bwd2(x, dy, v, ctx.plan)
+    return (ddx if nx else None, ddy if ng else None, None)
+
+
+gate_bwd.register_autograd(_gate_bwd_bwd, setup_context=_gate_bwd_setup)
+
+
 @torch.library.custom_op(f"{NS}::pool_sum", mutates_args=(), device_types="cuda")
 def pool_sum(x: Tensor, batch: Tensor, num_graphs: int) -> Tensor:
     x = _f32c(x)

@@ -267,3 +267,57 @@ class SymPlan:
                 st.K[a][nu] = self.K[a][nu]
                 k += 1
         return st
+
+
+SILU_2MOM = 1.6791767923989418  # e3nn normalize2mom constants
+TANH_2MOM = 1.5937334472592692
+
+
+class GatePlan:
+    """NequIP ``Gate`` (reference models/nequip/modules/_gate.py:88-152 as configured in convnet_layer.py:44-77):
+    input row = sort(scalars + gates + gated).simplify(), output row = scalars + gated.  SiLU on even scalars / gates,
+    tanh on odd ones, each scaled by its normalize2mom constant; gated block b (mul, l) is multiplied channelwise by
+    the activated gate scalars b."""
+
+    def __init__(self, irreps_scalars, irreps_gates, irreps_gated) -> None:
+        sc = so3.parse_irreps(irreps_scalars)
+        gt = so3.parse_irreps(irreps_gates)
+        gd = so3.parse_irreps(irreps_gated)
+        if any(l != 0 for _, l, _ in sc + gt):
+            raise ValueError("gate scalars / gates must be l = 0")
+        if any(p != 1 for _, _, p in gt):
+            raise NotImplementedError("odd (0o) gates flip the parity of the gated irreps; not supported")
+        if [m for m, _, _ in gt] != [m for m, _, _ in gd]:
+            raise ValueError("one gate scalar per gated channel is required")
+        # the reference's _Sortcut: concatenate, stable-sort by (l, p), remember where every piece went
+        pieces = [("s", i, ir) for i, ir in enumerate(sc)] + [("g", i, ir) for i, ir in enumerate(gt)] + [
+            ("x", i, ir) for i, ir in enumerate(gd)]
+        srt, _ = so3.sort_irreps([ir for _, _, ir in pieces])
+        order = sorted(range(len(pieces)), key=lambda i: ((pieces[i][2][1], pieces[i][2][2]), i))
+        off, where = 0, {}
+        for idx in order:
+            kind, i, (m, l, _p) = pieces[idx]
+            where[(kind, i)] = off
+            off += m * (2 * l + 1)
+        self.irreps_in = so3.simplify_irreps(srt)
+        self.irreps_out = so3.simplify_irreps(sc + gd)
+        self.d_in, self.d_out = off, so3.irreps_dim(sc + gd)
+        st = _lib.GatePlanStruct()
+        if len(sc) > _lib.GATE_MAX_SEG or len(gd) > _lib.GATE_MAX_SEG:
+            raise NotImplementedError("too many gate segments")
+        out_off, items = 0, 0
+        st.n_scal = len(sc)
+        for i, (m, _l, p) in enumerate(sc):
+            st.s_in[i], st.s_out[i], st.s_mul[i] = where[("s", i)], out_off, m
+            st.s_kind[i], st.s_c[i] = (0, SILU_2MOM) if p == 1 else (1, TANH_2MOM)
+            out_off += m
+            items += m
+        st.n_gated = len(gd)
+        for i, (m, l, _p) in enumerate(gd):
+            st.g_x[i], st.g_gate[i], st.g_out[i], st.g_mul[i], st.g_d[i] = where[("x", i)], where[("g", i)], out_off, m, 2 * l + 1
+            st.g_kind[i], st.g_c[i] = 0, SILU_2MOM
+            out_off += m * (2 * l + 1)
+            items += m
+        st.d_in, st.d_out, st.items = self.d_in, self.d_out, items
+        self.c_plan = st
+        self.handle = register(self)

@@ -6,6 +6,7 @@ Only runs in the build container (needs /root/reference).  Outputs (all small, f
                      (tests/data/{mace,nequip}_model/model_artefacts/module_checkpoint.ckpt) — the e3nn-convention pins
   mace_*.pt          inputs, state dict, energies and autograd forces of the reference MACE (models/mace/modules/mace.py)
                      + PooledReadoutHead on seeded synthetic molecules
+  nequip_*.pt        the same for the reference NequIP (models/nequip/modules/nequip.py) + PooledReadoutHead
   nl_*.pt            inputs and sorted edge sets of the reference construct_edge_indices_and_attrs
                      (lightning/graph_datasets/neighbourhood_list_torch.py:53)
   gdb9_edges.pt      first six molecules of the reference's tests/data/gdb9.sdf with the edge counts its tests assert
@@ -28,6 +29,7 @@ from oracle import import_reference as ir  # noqa: E402
 
 assert ir.available(), "/root/reference is required to (re)generate the golden fixtures"
 mace_mod = ir.load("physicsml.models.mace.modules.mace")
+nequip_mod = ir.load("physicsml.models.nequip.modules.nequip")
 nl_mod = ir.load("physicsml.lightning.graph_datasets.neighbourhood_list_torch")
 from e3nn import o3  # noqa: E402  (oracle restatement)
 
@@ -46,6 +48,20 @@ class RefPooled(torch.nn.Module):
 
     def forward(self, data):
         return {"y_graph_scalars": self.graph_scalars_head(self.mace(data))}
+
+
+class RefPooledNequip(torch.nn.Module):
+    """backbone + graph-scalar head as PooledNequipModule wires them (nequip/supervised/nequip_module.py:37-80,102-113)"""
+
+    def __init__(self, mlp_irreps, **kw):
+        super().__init__()
+        self.nequip = nequip_mod.Nequip(**kw)
+        self.graph_scalars_head = nequip_mod.PooledReadoutHead(
+            irrreps_in=self.nequip.out_irreps[-1], mlp_irreps=o3.Irreps(mlp_irreps), out_irreps=o3.Irreps("1x0e"),
+            scaling_std=1.0, scaling_mean=0.0)
+
+    def forward(self, data):
+        return {"y_graph_scalars": self.graph_scalars_head(self.nequip(data))}
 
 
 def energy_forces(model, data):
@@ -101,6 +117,35 @@ def main():
         torch.save({"kw": c["kw"], "mlp": c["mlp"], "state_dict": sd, "coordinates": pos, "z": z, "batch": batch,
                     "edge_index": data["edge_index"], "energy": e, "forces": f}, os.path.join(HERE, name + ".pt"))
         print(name, "E", e.flatten().tolist()[:3], "|F|max", f.abs().max().item(), "edges", data["edge_index"].shape[1])
+
+    # ---- 2b. reference NequIP energies / forces
+    ncases = {
+        "nequip_fixture_ckpt": dict(mlp="8x0e", Z=4, ckpt=True, kw=dict(
+            cut_off=5.0, num_layers=2, max_ell=2, parity=True, num_features=4, num_bessel=8, bessel_basis_trainable=True,
+            num_polynomial_cutoff=6, self_connection=True, resnet=True, num_node_feats=4, num_edge_feats=0, avg_num_neighbours=10.0)),
+        "nequip_l2_f8_4layers": dict(mlp="16x0e", Z=5, ckpt=False, kw=dict(
+            cut_off=4.5, num_layers=4, max_ell=2, parity=True, num_features=8, num_bessel=8, bessel_basis_trainable=False,
+            num_polynomial_cutoff=6, self_connection=True, resnet=True, num_node_feats=5, num_edge_feats=0, avg_num_neighbours=11.0)),
+        "nequip_l1_f16_noparity": dict(mlp="8x0e", Z=3, ckpt=False, kw=dict(
+            cut_off=4.0, num_layers=3, max_ell=1, parity=False, num_features=16, num_bessel=8, bessel_basis_trainable=False,
+            num_polynomial_cutoff=6, self_connection=False, resnet=False, num_node_feats=3, num_edge_feats=0, avg_num_neighbours=8.0)),
+    }
+    for name, c in ncases.items():
+        torch.manual_seed(0)
+        model = RefPooledNequip(c["mlp"], **c["kw"])
+        if c["ckpt"]:
+            sd = torch.load("/root/reference/tests/data/nequip_model/model_artefacts/module_checkpoint.ckpt", map_location="cpu",
+                            weights_only=False)["state_dict"]
+            model.load_state_dict(sd, strict=True)
+        pos, z, batch = helpers.random_molecules(5, 8, 16, c["Z"], seed=303)
+        data = helpers.make_batch(pos, z, batch, c["Z"], c["kw"]["cut_off"])
+        e, f = energy_forces(model, data)
+        sd = {k: v.clone() for k, v in model.state_dict().items() if "_w3j_" not in k and "output_mask" not in k}
+        torch.save({"kw": c["kw"], "mlp": c["mlp"], "state_dict": sd, "coordinates": pos, "z": z, "batch": batch,
+                    "edge_index": data["edge_index"], "energy": e, "forces": f, "resnet_layers": [bool(l.resnet) for l in model.nequip.conv_layers]},
+                   os.path.join(HERE, name + ".pt"))
+        print(name, "E", e.flatten().tolist()[:3], "|F|max", f.abs().max().item(), "edges", data["edge_index"].shape[1],
+              "resnet", [bool(l.resnet) for l in model.nequip.conv_layers])
 
     # ---- 3. reference neighbour lists
     g = torch.Generator().manual_seed(404)

@@ -128,3 +128,51 @@ def test_no_cpu_fallback():
         ops.act(torch.randn(4), 0, 1.0)
     with pytest.raises(RuntimeError):
         neighbour_list.radius_graph(torch.randn(4, 3), 5.0)
+
+
+def test_nequip_mirror_loads_reference_checkpoint_strict():
+    """every parameter / buffer name and shape of the reference's NequIP fixture checkpoint
+    (tests/data/nequip_model/...ckpt, copied into tests/golden/nequip_fixture_ckpt.pt) exists in the mirror"""
+    import os
+
+    from physicsml_b200.nequip import PooledNequipModule
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "nequip_fixture_ckpt.pt"), weights_only=False)
+    model = PooledNequipModule(mlp_irreps=g["mlp"], **g["kw"])
+    res = model.load_state_dict(g["state_dict"], strict=False)
+    assert not res.unexpected_keys
+    assert all(("_w3j_" in k) or ("output_mask" in k) for k in res.missing_keys)
+    own = model.state_dict()
+    for k, v in g["state_dict"].items():
+        assert own[k].shape == v.shape, k
+    # layer structure of the reference: conv outputs 12x0e+4x1o+4x2e then 20x0e+4x1o+4x1e+4x2o+4x2e
+    assert [l.equivariant_nonlin.plan.d_in for l in model.nequip.conv_layers] == [44, 84]
+    assert model.nequip.out_irreps == ["4x0e+4x1o+4x2e", "4x0e+4x1o+4x1e+4x2o+4x2e"]
+
+
+def test_gate_plan_matches_oracle_gate_layout():
+    """GatePlan's offsets reproduce the reference Gate's sort-cut: evaluate the plan in numpy against the oracle module"""
+    from e3nn import o3
+    from oracle.ref_nequip import _Gate
+    from physicsml_b200.plans import SILU_2MOM, TANH_2MOM, GatePlan
+
+    for scal, gates, gated in [("8x0o+8x0e", "8x0e+8x0e+8x0e+8x0e", "8x1o+8x1e+8x2o+8x2e"), ("4x0e", "4x0e+4x0e", "4x1o+4x2e"),
+                               ("3x0e", "", "")]:
+        ref = _Gate(o3.Irreps(scal), o3.Irreps(gates), o3.Irreps(gated))
+        plan = GatePlan(scal, gates, gated)
+        assert plan.d_in == ref.irreps_in.dim and plan.d_out == ref.irreps_out.dim
+        x = torch.randn(5, plan.d_in, generator=torch.Generator().manual_seed(1))
+        y_ref = ref(x)
+        st = plan.c_plan
+        y = torch.zeros(5, plan.d_out)
+        act = lambda kind, c, t: c * (torch.nn.functional.silu(t) if kind == 0 else torch.tanh(t))  # noqa: E731
+        for i in range(st.n_scal):
+            m = st.s_mul[i]
+            y[:, st.s_out[i]:st.s_out[i] + m] = act(st.s_kind[i], st.s_c[i], x[:, st.s_in[i]:st.s_in[i] + m])
+        for i in range(st.n_gated):
+            m, d = st.g_mul[i], st.g_d[i]
+            gate = act(st.g_kind[i], st.g_c[i], x[:, st.g_gate[i]:st.g_gate[i] + m])
+            blk = x[:, st.g_x[i]:st.g_x[i] + m * d].reshape(5, m, d) * gate[:, :, None]
+            y[:, st.g_out[i]:st.g_out[i] + m * d] = blk.reshape(5, m * d)
+        assert (y - y_ref).abs().max() < 1e-6
+        assert abs(SILU_2MOM - 1.6791767923989418) < 1e-12 and abs(TANH_2MOM - 1.5937334472592692) < 1e-12

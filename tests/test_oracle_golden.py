@@ -10,6 +10,7 @@ import helpers  # noqa: F401
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 MACE_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLD, "mace_*.pt")))
+NEQUIP_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLD, "nequip_*.pt")))
 NL_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLD, "nl_*.pt")))
 
 
@@ -22,6 +23,26 @@ def test_oracle_reproduces_reference_energy_and_forces(name):
     missing = model.load_state_dict(g["state_dict"], strict=False)
     assert not missing.unexpected_keys
     assert all(("U_matrices" in k) or ("_w3j_" in k) or ("output_mask" in k) for k in missing.missing_keys)
+    Z = g["kw"]["num_node_feats"]
+    data = {"coordinates": g["coordinates"], "edge_index": g["edge_index"], "batch": g["batch"],
+            "node_attrs": torch.nn.functional.one_hot(g["z"], Z).float(), "num_graphs": torch.tensor(int(g["batch"].max()) + 1)}
+    e, f = energy_and_forces(model, data)
+    assert (e - g["energy"]).abs().max() <= 1e-6 * g["energy"].abs().max()
+    assert (f - g["forces"]).abs().max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", NEQUIP_CASES)
+def test_oracle_reproduces_reference_nequip(name):
+    """oracle/ref_nequip.py against the unmodified reference nequip.py (over the shims), incl. the fixture checkpoint"""
+    from oracle.ref_model import energy_and_forces
+    from oracle.ref_nequip import RefPooledNequip
+
+    g = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+    model = RefPooledNequip(mlp_irreps=g["mlp"], **g["kw"])
+    missing = model.load_state_dict(g["state_dict"], strict=False)
+    assert not missing.unexpected_keys
+    assert all(("_w3j_" in k) or ("output_mask" in k) for k in missing.missing_keys)
+    assert [bool(l.resnet) for l in model.nequip.conv_layers] == g["resnet_layers"]
     Z = g["kw"]["num_node_feats"]
     data = {"coordinates": g["coordinates"], "edge_index": g["edge_index"], "batch": g["batch"],
             "node_attrs": torch.nn.functional.one_hot(g["z"], Z).float(), "num_graphs": torch.tensor(int(g["batch"].max()) + 1)}
