@@ -155,18 +155,52 @@ template <int BN>
 struct __align__(128) TcSmem {
   float a[TC_STAGES][2][TC_BM * TC_BK];
   float b[TC_STAGES][2][BN * TC_BK];
-  unsigned long long bar[TC_STAGES];
+  unsigned long long bar[TC_STAGES];  // ring: the MMAs that read a stage have retired
+  unsigned long long accbar[2];       // an accumulation period has retired into TMEM buffer 0 / 1
   uint32_t tmem_base;
+  pml_gemm_problem prob;              // this CTA's problem descriptor (copied once: the table lives in global memory and
+                                      // every "memory"-clobbering barrier op would otherwise force its fields to be re-read)
 };
 
-template <int BN>
+// tcgen05 accumulates in fp32 but aligns and TRUNCATES every partial sum, a bias of ~2^-24 of the running sum per MMA
+// (1e-5 relative after the 480 MMAs of K = 1280).  With PROMOTE the K loop is cut into periods of kPromoBlocks
+// k-blocks (K = 128): each period accumulates into one of two TMEM buffers from zero and is then added, with ordinary
+// round-to-nearest fp32 adds, into per-thread register accumulators while the next period's MMAs run into the other
+// buffer.  The result is deterministic and keeps ~1e-6 relative accuracy at any K.
+constexpr int kPromoBlocks = 8;
+
+template <int N32>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+#pragma unroll
+  for (int c = 0; c < N32; ++c) {
+    float t[32];
+    tmem_ld32(taddr + 32 * c, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[32 * c + j] = t[j];
+  }
+}
+
+template <int BN, bool PROMOTE>
 __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                      float* __restrict__ C,
                                                                      const pml_gemm_problem* __restrict__ probs,
                                                                      int M_runtime, int splitk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem<BN>& S = *reinterpret_cast<TcSmem<BN>*>(smem_raw);
-  const pml_gemm_problem& P = probs[blockIdx.y];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const pml_gemm_problem& Pg = probs[blockIdx.y];
+    const int Mg = Pg.M < 0 ? M_runtime : Pg.M;
+    const int tiles_ng = (Pg.N + BN - 1) / BN;
+    const int tmg = blockIdx.x / tiles_ng;
+    if (tmg * TC_BM >= Mg || (int)(blockIdx.z / splitk) >= Pg.nbatch) return;  // uniform per CTA, before any barrier / allocation
+    static_assert(sizeof(pml_gemm_problem) % 4 == 0, "descriptor is copied word by word");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&Pg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&S.prob);
+    for (int i = tid; i < (int)(sizeof(pml_gemm_problem) / 4); i += TC_THREADS) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const pml_gemm_problem& P = S.prob;
   const int M = P.M < 0 ? M_runtime : P.M;
   const int N = P.N;
   const int tiles_n = (N + BN - 1) / BN;
@@ -174,10 +208,16 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   int zb = blockIdx.z;
   const int ks = zb % splitk;
   zb /= splitk;
-  if (tm * TC_BM >= M || zb >= P.nbatch) return;  // uniform per CTA, before any barrier / allocation
+  // loop-invariant descriptor fields, held in registers
+  const long long a_rs = P.a_rs, a_cs = P.a_cs, b_rs = P.b_rs, b_cs = P.b_cs;
+  const int nchunks = P.nchunks;
+  const long long a_boff = (long long)zb * P.a_bs, b_boff = (long long)zb * P.b_bs;
+  const bool a_kfast = a_cs == 1, b_kfast = b_rs == 1;
+  const bool a_vec_base = a_kfast && ((a_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool b_vec_base = b_kfast && ((b_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int NBUF = PROMOTE ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = (NBUF * BN) < 32 ? 32 : (NBUF * BN);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
                  "r"(TMEM_COLS)
@@ -187,6 +227,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < TC_STAGES; ++s) mbar_init(smem_u32(&S.bar[s]), 1);
+    mbar_init(smem_u32(&S.accbar[0]), 1);
+    mbar_init(smem_u32(&S.accbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -199,14 +241,14 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
 
   const int row0 = tm * TC_BM, col0 = tn * BN;
 
-  // flattened (chunk, k0) iteration with one-step lookahead
+  // flattened (chunk, k0) iteration
   struct KPos {
     int ch, k0;
   };
   auto chunk_k = [&](int ch) { return P.kc[ch] < 0 ? M_runtime : P.kc[ch]; };
   auto first_pos = [&](int ch_from) {
     KPos q{ch_from, ks * TC_BK};
-    while (q.ch < P.nchunks && q.k0 >= chunk_k(q.ch)) ++q.ch;
+    while (q.ch < nchunks && q.k0 >= chunk_k(q.ch)) ++q.ch;
     return q;
   };
   auto next_pos = [&](KPos q) {
@@ -218,89 +260,178 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
     return q;
   };
   auto fetch = [&](const KPos& q, TileRegs<TC_BM>& ra, TileRegs<BN>& rb) {
-    const long long aoff = P.a_off[q.ch] + (long long)zb * P.a_bs;
-    const long long boff = P.b_off[q.ch] + (long long)zb * P.b_bs;
+    const long long aoff = P.a_off[q.ch] + a_boff;
+    const long long boff = P.b_off[q.ch] + b_boff;
     const int K = chunk_k(q.ch);
-    const bool vecA = (P.a_cs == 1) && ((aoff & 3) == 0) && ((P.a_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    const bool vecB = (P.b_rs == 1) && ((boff & 3) == 0) && ((P.b_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-    fetch_tile<TC_BM>(A + aoff, P.a_rs, P.a_cs, row0, M, q.k0, K, vecA, ra);
+    fetch_tile<TC_BM>(A + aoff, a_rs, a_cs, row0, M, q.k0, K, a_vec_base && ((aoff & 3) == 0), ra);
     // B operand as an [N x K] K-major tile: element (n, k) = B[k*b_rs + n*b_cs]
-    fetch_tile<BN>(B + boff, P.b_cs, P.b_rs, col0, N, q.k0, K, vecB, rb);
+    fetch_tile<BN>(B + boff, b_cs, b_rs, col0, N, q.k0, K, b_vec_base && ((boff & 3) == 0), rb);
   };
 
-  TileRegs<TC_BM> ra;
-  TileRegs<BN> rb;
-  KPos cur = first_pos(0);
-  if (cur.ch < P.nchunks) fetch(cur, ra, rb);
+  // this thread's slice of the output tile: TMEM lane quadrant q (rows 32q + lane), column half `half`
+  constexpr int NHALF = BN >= 64 ? 2 : 1;
+  constexpr int COLS_PER_WARP = BN / NHALF;
+  const int q = warp & 3, half = warp >> 2;
+  float acc[PROMOTE ? COLS_PER_WARP : 1];
+  if (PROMOTE) {
+#pragma unroll
+    for (int j = 0; j < COLS_PER_WARP; ++j) acc[j] = 0.f;
+  }
+  auto promote = [&](int period) {  // add the retired period's TMEM buffer into the register accumulators
+    const int buf = period & 1;
+    mbar_wait(smem_u32(&S.accbar[buf]), (period >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (half < NHALF) {
+      float v[COLS_PER_WARP];
+      tmem_ld_cols<COLS_PER_WARP / 32>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * COLS_PER_WARP), v);
+#pragma unroll
+      for (int j = 0; j < COLS_PER_WARP; ++j) acc[PROMOTE ? j : 0] += v[j];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
+  // two k-blocks of register prefetch: the loads of k-block i+2 are issued while block i is converted and multiplied
+  TileRegs<TC_BM> ra[2];
+  TileRegs<BN> rb[2];
+  KPos pos[3];
+  pos[0] = first_pos(0);
+  pos[1] = pos[0].ch < nchunks ? next_pos(pos[0]) : pos[0];
+  if (pos[0].ch < nchunks) fetch(pos[0], ra[0], rb[0]);
+  if (pos[1].ch < nchunks) fetch(pos[1], ra[1], rb[1]);
   int it = 0;  // k-block counter (ring position)
-  while (cur.ch < P.nchunks) {
-    const KPos nxt = next_pos(cur);
+  int to_promote = -1;
+#pragma unroll 1
+  while (pos[0].ch < nchunks) {
+    pos[2] = pos[1].ch < nchunks ? next_pos(pos[1]) : pos[1];
     const int s = it % TC_STAGES;
     if (it >= TC_STAGES) mbar_wait(smem_u32(&S.bar[s]), ((it / TC_STAGES) - 1) & 1);  // MMAs that read stage s retired
-    commit_tile<TC_BM>(ra, P.a_cs == 1, P.cscale[cur.ch], S.a[s][0], S.a[s][1]);
-    commit_tile<BN>(rb, P.b_rs == 1, 1.f, S.b[s][0], S.b[s][1]);
-    if (nxt.ch < P.nchunks) fetch(nxt, ra, rb);  // in flight across the barrier, the MMA issue and the next wait
+    const int rsel = it & 1;
+    if (rsel == 0) {
+      commit_tile<TC_BM>(ra[0], a_kfast, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
+      commit_tile<BN>(rb[0], b_kfast, 1.f, S.b[s][0], S.b[s][1]);
+      if (pos[2].ch < nchunks) fetch(pos[2], ra[0], rb[0]);
+    } else {
+      commit_tile<TC_BM>(ra[1], a_kfast, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
+      commit_tile<BN>(rb[1], b_kfast, 1.f, S.b[s][0], S.b[s][1]);
+      if (pos[2].ch < nchunks) fetch(pos[2], ra[1], rb[1]);
+    }
+    if (PROMOTE && to_promote >= 0) {  // the period closed one k-block ago: its MMAs have had an iteration to retire
+      promote(to_promote);
+      to_promote = -1;
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
     __syncthreads();
+    const int period = PROMOTE ? it / kPromoBlocks : 0;
+    const bool opens = PROMOTE ? (it % kPromoBlocks == 0) : (it == 0);
+    const bool closes = PROMOTE ? ((it % kPromoBlocks == kPromoBlocks - 1) || pos[1].ch >= nchunks) : (pos[1].ch >= nchunks);
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(S.a[s][0]), a_lo = smem_u32(S.a[s][1]);
       const uint32_t b_hi = smem_u32(S.b[s][0]), b_lo = smem_u32(S.b[s][1]);
+      const uint32_t d = tmem + (uint32_t)((period & 1) * BN);
 #pragma unroll
       for (int kk = 0; kk < TC_BK / 8; ++kk) {
         const uint32_t o = kk * 256;  // two 16-byte k-units = two core matrices of 128 B
-        umma_tf32(tmem, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, (it > 0 || kk > 0) ? 1u : 0u);
-        umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
-        umma_tf32(tmem, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
+        umma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, (!opens || kk > 0) ? 1u : 0u);
+        umma_tf32(d, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
+        umma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[s]))
                    : "memory");
+      if (closes)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&S.accbar[period & 1]))
+                     : "memory");
     }
-    cur = nxt;
+    if (PROMOTE && closes) to_promote = period;
+    pos[0] = pos[1];
+    pos[1] = pos[2];
     ++it;
   }
 
   if (it > 0) {
-    // the last commit covers every MMA issued before it
-    const int last = it - 1;
-    mbar_wait(smem_u32(&S.bar[last % TC_STAGES]), (last / TC_STAGES) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: warp w reads TMEM lanes 32*(w%4).., columns [(w/4)*BN/2, +BN/2) in 32-column groups; every group is
-    // transposed through shared memory (the operand ring is free now) so global stores / atomics are coalesced rows
-    constexpr int NHALF = BN >= 64 ? 2 : 1;
-    constexpr int COLS_PER_WARP = BN / NHALF;
-    constexpr int PITCH = 32 * NHALF + 1;
-    float* stg = reinterpret_cast<float*>(S.a);  // [128][PITCH] floats <= 33.3 KB, inside the operand ring
-    static_assert(sizeof(float) * TC_BM * PITCH <= sizeof(S.a) + sizeof(S.b), "staging tile does not fit");
-    const int q = warp & 3, half = warp >> 2;
     float* Cb = C + P.c_off + (long long)zb * P.c_bs;
     const bool atomic = splitk > 1 || (P.c_bs == 0 && P.nbatch > 1);
-#pragma unroll 1
-    for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+    const bool direct = !atomic && P.c_cs == 1 && ((P.c_rs & 3) == 0) && (((P.c_off + (long long)zb * P.c_bs) & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (N % 4 == 0);
+    if (PROMOTE) {
+      if (to_promote >= 0) promote(to_promote);
+    } else {
+      mbar_wait(smem_u32(&S.accbar[0]), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const int r = row0 + q * 32 + lane;
+    const float alpha = P.alpha;
+    const bool accumulate = P.accumulate != 0;
+    const long long c_rs = P.c_rs, c_cs = P.c_cs;
+    if (direct) {
+      // row-major C: every thread owns 32-column (128-byte) runs of its row -> 16-byte vector stores, no staging, no
+      // block-wide synchronisation; the eight stores of a run complete one line in L2
       if (half < NHALF) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
+#pragma unroll 1
+        for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+          float v[32];
+          if (PROMOTE) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[(q * 32 + lane) * PITCH + half * 32 + j] = v[j];
-      }
-      __syncthreads();
-      for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
-        const int r = row0 + rr;
-        if (r >= M) break;
+            for (int j = 0; j < 32; ++j) v[j] = acc[PROMOTE ? (c0 + j) : 0];
+          } else {
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
+          }
+          const int gc0 = col0 + half * COLS_PER_WARP + c0;
+          if (r < M) {
+            float* prow = Cb + (long long)r * c_rs + gc0;
 #pragma unroll
-        for (int h = 0; h < NHALF; ++h) {
-          const int gc = col0 + h * COLS_PER_WARP + c0 + lane;
-          if (gc < N) {
-            float* p = Cb + (long long)r * P.c_rs + (long long)gc * P.c_cs;
-            const float val = P.alpha * stg[rr * PITCH + h * 32 + lane];
-            if (atomic) atomicAdd(p, val);
-            else if (P.accumulate) *p += val;
-            else *p = val;
+            for (int j = 0; j < 32; j += 4) {
+              if (gc0 + j < N) {
+                float4 o = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+                if (accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(prow + j);
+                  o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(prow + j) = o;
+              }
+            }
           }
         }
       }
-      __syncthreads();
+    } else {
+      // general strides / atomics: every 32-column group is transposed through shared memory (the operand ring is free
+      // now) so that global stores / atomics run along the columns of a row
+      constexpr int PITCH = 32 * NHALF + 1;
+      float* stg = reinterpret_cast<float*>(S.a);  // [128][PITCH] floats <= 33.3 KB, inside the operand ring
+      static_assert(sizeof(float) * TC_BM * PITCH <= sizeof(S.a) + sizeof(S.b), "staging tile does not fit");
+      __syncthreads();  // every MMA has retired (waited above), nobody still converts into the ring
+#pragma unroll 1
+      for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+        if (half < NHALF) {
+          float v[32];
+          if (PROMOTE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = acc[PROMOTE ? (c0 + j) : 0];
+          } else {
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[(q * 32 + lane) * PITCH + half * 32 + j] = v[j];
+        }
+        __syncthreads();
+        for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+          const int gr = row0 + rr;
+          if (gr >= M) break;
+#pragma unroll
+          for (int h = 0; h < NHALF; ++h) {
+            const int gc = col0 + h * COLS_PER_WARP + c0 + lane;
+            if (gc < N) {
+              float* p = Cb + (long long)gr * c_rs + (long long)gc * c_cs;
+              const float val = alpha * stg[rr * PITCH + h * 32 + lane];
+              if (atomic) atomicAdd(p, val);
+              else if (accumulate) *p += val;
+              else *p = val;
+            }
+          }
+        }
+        __syncthreads();
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -310,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   }
 }
 
-template <int BN>
+template <int BN, bool PROMOTE>
 static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                      int max_M, int max_N, int max_batch, int splitk, cudaStream_t stream) {
   const int tiles_m = (max_M + TC_BM - 1) / TC_BM, tiles_n = (max_N + BN - 1) / BN;
@@ -319,26 +450,35 @@ static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_pr
   const size_t smem = sizeof(TcSmem<BN>) + 128;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return PML_ERR_LAUNCH;
     configured = true;
   }
   dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)nprobs, (unsigned)gz);
-  gemm_grouped_tc_kernel<BN><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
+  gemm_grouped_tc_kernel<BN, PROMOTE><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
   return PML_OK;
 }
 
 }  // namespace pml
 
-// Same contract as pml_gemm_grouped (gemm.cu).
+// Same contract as pml_gemm_grouped (gemm.cu) plus max_k: an upper bound of the reduction length one CTA sees (sum of
+// the chunk extents of a problem, divided by splitk); <= 0 means unknown.  Reductions longer than 128 run the kernel
+// variant that promotes the TMEM accumulators into registers every 128 k (see kPromoBlocks).
 extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
-                                   int M_runtime, int max_M, int max_N, int max_batch, int splitk, cudaStream_t stream) {
+                                   int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k,
+                                   cudaStream_t stream) {
   if (nprobs <= 0 || max_M <= 0 || max_N <= 0 || max_batch <= 0) return PML_OK;
   if (splitk < 1) splitk = 1;
+  const bool promote = max_k <= 0 || max_k > pml::kPromoBlocks * pml::TC_BK;
   int rc;
-  if (max_N <= 32) rc = pml::launch_tc<32>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
-  else if (max_N <= 64) rc = pml::launch_tc<64>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
-  else rc = pml::launch_tc<128>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+  if (promote) {
+    if (max_N <= 32) rc = pml::launch_tc<32, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    else rc = pml::launch_tc<64, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+  } else {
+    if (max_N <= 32) rc = pml::launch_tc<32, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    else if (max_N <= 64) rc = pml::launch_tc<64, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    else rc = pml::launch_tc<128, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+  }
   if (rc != PML_OK) return rc;
   PML_CHECK_LAUNCH();
   return PML_OK;

@@ -296,15 +296,24 @@ tp_scatter_bwd.register_autograd(_tp_bwd_bwd, setup_context=_tp_bwd_setup)
 # ======================================================================================================================
 # per-irrep linear (grouped GEMM)
 # ======================================================================================================================
-# "tc": tcgen05 3xTF32 kernel for every problem with >= TC_MIN_ROWS[0] runtime rows (the edge-sized radial-MLP GEMMs and
-# their weight gradients), FFMA kernel below that (node-sized per-irrep mixing, where K reaches 1280 and the tensor
-# core's truncating accumulation costs ~1e-5 relative); "ffma": FFMA only
+# "tc": tcgen05 3xTF32 kernel for every problem with >= TC_MIN_ROWS[0] runtime rows (the edge-sized radial-MLP GEMMs,
+# their weight gradients and the node-sized per-irrep mixing of a batch; reductions longer than 128 promote the TMEM
+# accumulators into fp32 registers so the tensor core's truncating accumulation stays below 1e-6 relative), FFMA
+# kernel below that (a handful of rows cannot fill a 128-row MMA tile); "ffma": FFMA only
 GEMM_MODE = [os.environ.get("PML_GEMM", "tc")]
-TC_MIN_ROWS = [int(os.environ.get("PML_TC_MIN_ROWS", "4096"))]
+TC_MIN_ROWS = [int(os.environ.get("PML_TC_MIN_ROWS", "256"))]
 
 
 def _gemm_name(n_runtime: int) -> str:
     return "pml_gemm_grouped_tc" if (GEMM_MODE[0] == "tc" and n_runtime >= TC_MIN_ROWS[0]) else "pml_gemm_grouped"
+
+
+def _gemm(name: str, a, b, c, table, nprob: int, m_runtime: int, max_m: int, max_n: int, max_batch: int, splitk: int,
+          max_k: int) -> None:
+    if name.endswith("_tc"):
+        _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, max_k, _stream())
+    else:
+        _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, _stream())
 
 
 def _splitk_for(k_extent: int, ctas_without_split: int) -> int:
@@ -326,10 +335,10 @@ def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
         if pl.fwd_serial:
             sz = C.sizeof(_lib.GemmProblem)
             for k in range(nprob):
-                _call(_gemm_name(n), _p(x), _p(w), _p(out), fwd.data_ptr() + k * sz, 1, n, n, pl.max_mul_out,
-                      pl.max_d, 1, _stream())
+                _gemm(_gemm_name(n), _p(x), _p(w), _p(out), fwd.data_ptr() + k * sz, 1, n, n, pl.max_mul_out, pl.max_d, 1,
+                      pl.max_k_fwd)
         else:
-            _call(_gemm_name(n), _p(x), _p(w), _p(out), _p(fwd), nprob, n, n, pl.max_mul_out, pl.max_d, 1, _stream())
+            _gemm(_gemm_name(n), _p(x), _p(w), _p(out), _p(fwd), nprob, n, n, pl.max_mul_out, pl.max_d, 1, pl.max_k_fwd)
     return out
 
 
@@ -349,7 +358,7 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
     dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else g.new_empty(n, pl.d_in)
     _, bx, _ = pl.tables(g.device)
     if bx is not None and n > 0:
-        _call(_gemm_name(n), _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, _stream())
+        _gemm(_gemm_name(n), _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, pl.max_k_bwd_x)
     return dx
 
 
@@ -372,8 +381,9 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
             ctas = ((pl.max_mul_in + 127) // 128) * ((pl.max_mul_out + bn - 1) // bn) * len(pl._bwd_w) * pl.max_d
         else:
             ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
-        _call(name, _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d,
-              _splitk_for(n, ctas), _stream())
+        sk = _splitk_for(n, ctas)
+        _gemm(name, _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d, sk,
+              (n + sk - 1) // sk + 16)
     return dw
 
 

@@ -138,6 +138,9 @@ class LinearPlan:
             p.M, p.N, p.nbatch, p.alpha, p.accumulate = -1, mi, d, 1.0, 0
             bx.append(p)
         self.has_unfed_input = len(bx) < len(self.irreps_in)
+        # longest reduction of any problem (selects the accumulator-promoting tensor-core kernel above 128)
+        self.max_k_fwd = max([sum(p.kc[c] for c in range(p.nchunks)) for p in fwd] + [1])
+        self.max_k_bwd_x = max([sum(p.kc[c] for c in range(p.nchunks)) for p in bx] + [1])
         self._bwd_x = bx
         # ---- dW: one problem per path, K = nodes (runtime), the (2l+1) batches reduce into the same C (atomic epilogue)
         bw = []
