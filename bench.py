@@ -284,9 +284,26 @@ def main() -> None:
         dist.all_reduce(t)
         total_atoms = float(t[0])
 
+    def shutdown():
+        """Leave the process group without hanging: the captured step holds NCCL work, so drop the graph first; a
+        watchdog forces the exit if the communicator teardown still blocks (the JSON line is already flushed)."""
+        nonlocal graphed
+        if world == 1:
+            return
+        import gc
+        import threading
+
+        sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        graphed = None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     # roofline of the dominant fused edge kernel (forward, the layer with the most traffic)
@@ -305,13 +322,22 @@ def main() -> None:
     if best is not None:
         byts, avg_ms, n, key = best
         ach = byts / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": f"tp_fwd_kernel<{key}>", "algorithmic_bytes_per_launch": byts, "avg_launch_ms": avg_ms,
-                "launches_timed": n, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})"}
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the committed ncu --set full
+        # capture (profiles/README.md says which command produced it); null when no capture of this signature exists
+        traffic, tsrc = None, None
+        tpath = os.path.join(ROOT, "profiles", "k4_dram_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                rec = json.load(f).get(f"{WORKLOAD}:tp_fwd:{key}")
+            if rec:
+                traffic, tsrc = rec["dram_bytes_per_launch"], rec["source"]
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": tsrc, "kernel": f"tp_fwd_pipe_kernel<{key}>", "algorithmic_bytes_per_launch": byts,
+                "avg_launch_ms": avg_ms, "launches_timed": n, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})"}
     kernel_share = {f"{n}[{s}]": {"launches": len(ts), "total_ms_per_step": sum(ts) / args.steps} for (n, s), ts in ktimes.items()}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
         rate, cores, sample, _ = cpu_reference_step_rate(args.ref_molecules, 2, 1)
         cpu = {"value": rate, "unit": "atoms/s", "cores": cores, "kind": "port", "sample": sample}
 
@@ -331,9 +357,8 @@ def main() -> None:
         "cpu_baseline": cpu,
         "edge_kernels": kernel_share,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown()
 
 
 if __name__ == "__main__":

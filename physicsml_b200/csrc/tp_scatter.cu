@@ -579,35 +579,48 @@ struct PipeCfg {
   int nstage, smem, grid;
 };
 
-// stage count and persistent grid for a kernel instantiation (cached per C; queries only, no allocation / sync)
+// stage count and persistent grid for a kernel instantiation (cached per (C, small); queries only, no allocation /
+// sync).  Large graphs: 4 CTAs per SM with 7-stage rings (the arithmetic of 8 consumer warps already fills the fp32
+// pipe; more CTAs only fight over it: cfg4 72% vs 86% of HBM peak).  Small graphs (a training batch of molecules: ~30
+// edges per node, ~100 edges per CTA): 5 CTAs per SM with 6-stage rings — the ramp dominates and more concurrent
+// streams shorten it (cfg2 59% vs 54%).
 template <auto kernel>  // one cache per kernel instantiation
-static bool pipe_config(int threads, int stage_bytes, int C, PipeCfg* cfg) {
-  static int cached_C = -1;
-  static PipeCfg cached;
-  static bool cached_ok = false;
-  if (C == cached_C) {
-    *cfg = cached;
-    return cached_ok;
+static bool pipe_config(int threads, int stage_bytes, int C, bool small, PipeCfg* cfg) {
+  static int cached_C[2] = {-1, -1};
+  static PipeCfg cached[2];
+  static bool cached_ok[2] = {false, false};
+  const int slot = small ? 1 : 0;
+  if (C == cached_C[slot]) {
+    *cfg = cached[slot];
+    return cached_ok[slot];
   }
   int dev = 0, sms = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int nstage = (56 * 1024) / stage_bytes;
+  int nstage = ((small ? 44 : 56) * 1024) / stage_bytes;
   if (nstage > kPipeMaxStages) nstage = kPipeMaxStages;
   if (nstage < 3) nstage = 3;
   int smem = kPipeHeaderBytes + nstage * stage_bytes;
   bool ok = smem <= max_optin;
   int per_sm = 0;
-  if (ok) ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+  if (ok) {
+    // the attribute is per kernel, not per launch: keep it at the larger of the two configurations
+    int want = kPipeHeaderBytes + ((56 * 1024) / stage_bytes < 3 ? 3 : ((56 * 1024) / stage_bytes > kPipeMaxStages ? kPipeMaxStages : (56 * 1024) / stage_bytes)) * stage_bytes;
+    if (want < smem) want = smem;
+    if (want > max_optin) want = smem;
+    ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess;
+  }
   if (ok) ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) == cudaSuccess && per_sm > 0;
   if (!ok) cudaGetLastError();
-  cached_C = C;
-  cached = PipeCfg{nstage, smem, per_sm * sms};
-  cached_ok = ok;
-  *cfg = cached;
+  cached_C[slot] = C;
+  cached[slot] = PipeCfg{nstage, smem, per_sm * sms};
+  cached_ok[slot] = ok;
+  *cfg = cached[slot];
   return ok;
 }
+
+constexpr int kSmallGraphNodes = 6000;
 
 __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -632,12 +645,12 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
     const int threads = PL::consumer_threads(C) + (dedicated ? 32 : 0);
     const int sbytes = PL::stage_floats(C) * 4;
     if (dedicated) {
-      if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, true>>(threads, sbytes, C, &cfg)) {
+      if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, true>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {
         pml::tp_fwd_pipe_kernel<PML_TP_ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage);
         PML_CHECK_LAUNCH();
         return PML_OK;
       }
-    } else if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, false>>(threads, sbytes, C, &cfg)) {
+    } else if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, false>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {
       pml::tp_fwd_pipe_kernel<PML_TP_ID, false><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage);
       PML_CHECK_LAUNCH();
       return PML_OK;
@@ -666,7 +679,7 @@ extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const floa
     pml::PipeCfg cfg;
     bool done = false;
 #define PML_TP_BWD_PIPE_D(D_, H_, Y_, R_)                                                                               \
-  if (pml::pipe_config<pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_>>(threads, sbytes, C, &cfg)) {                  \
+  if (pml::pipe_config<pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {                  \
     pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(                         \
         h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, cfg.nstage);                                                \
     done = true;                                                                                                        \
