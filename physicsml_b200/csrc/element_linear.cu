@@ -77,43 +77,98 @@ __global__ void __launch_bounds__(128) el_fwd_kernel(const float* __restrict__ x
 }
 
 // dx[n, u, m] = alpha * sum_v a_v sum_w W[u, v, w] g[n, w, m]
+// One CTA per (path, element v, chunk of 256 nodes): the chunk's nodes that carry element v are compacted
+// (deterministic ballot scan) and the [mul_in, mul_out] slab of that element is staged ONCE in shared memory (coalesced
+// along w, odd pitch) for all of them — one CTA per node, as in the forward, would re-read the 64 KB slab per node with
+// every lane on its own cache line (ncu: 7.4 ms of a 86 ms config-4 evaluation).  Thread = input channel u, EL_XNB nodes
+// at a time with their g rows broadcast from shared memory.  Nodes whose attrs row is not one-hot appear in several
+// element lists, so results are accumulated with atomics into a zero-initialised dx (exactly one addend per entry, hence
+// still deterministic, for one-hot rows).
+constexpr int EL_XCHUNK = 256;
+
 template <int D>
-__global__ void __launch_bounds__(128) el_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ attrs,
+__global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ attrs,
                                                        const float* __restrict__ W, pml_el_plan P, float* __restrict__ dx,
-                                                       int N, int Z, int accumulate) {
-  const int n = blockIdx.x, p = blockIdx.y;
+                                                       int N, int Z) {
+  constexpr int NB = D >= 5 ? 4 : 8;  // nodes per pass
+  const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
   if (P.d[p] != D) return;
-  extern __shared__ float gs[];  // [mul_out * D]
   const int MI = P.mul_in[p], MO = P.mul_out[p];
-  const float* gr = g + (size_t)n * P.o_rs + P.o_off[p];
-  for (int i = threadIdx.x; i < MO * D; i += blockDim.x) {
-    const int w = i / D, m = i - w * D;
-    gs[i] = __ldg(gr + (size_t)w * P.o_ws[p] + m);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_list[EL_XCHUNK];
+  __shared__ float s_coef[EL_XCHUNK];
+  __shared__ int s_wcnt[8];
+  extern __shared__ float dyn[];
+  const int pitch = MO | 1;                  // odd: thread u reads Ws[u][w] without bank conflicts
+  float* Ws = dyn;                           // [MI][pitch]
+  float* gs = dyn + (size_t)MI * pitch;      // [NB * nsub][MO * D]
+
+  const int n = blockIdx.y * EL_XCHUNK + tid;
+  const float a = n < N ? __ldg(attrs + (size_t)n * Z + v) : 0.f;
+  const unsigned bal = __ballot_sync(0xffffffffu, a != 0.f);
+  if (lane == 0) s_wcnt[warp] = __popc(bal);
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int w8 = 0; w8 < 8; ++w8) {
+    if (w8 < warp) off += s_wcnt[w8];
+    total += s_wcnt[w8];
+  }
+  if (total == 0) return;  // uniform
+  if (a != 0.f) {
+    const int pos = off + __popc(bal & ((1u << lane) - 1u));
+    s_list[pos] = n;
+    s_coef[pos] = a;
+  }
+  const float* Wp = W + P.w_off[p];
+  for (int i = tid; i < MI * MO; i += 256) {
+    const int u = i / MO, w = i - u * MO;
+    Ws[u * pitch + w] = __ldg(Wp + ((size_t)u * Z + v) * MO + w);
   }
   __syncthreads();
-  const float* arow = attrs + (size_t)n * Z;
-  const int z = one_hot_index(arow, Z);
-  const float* Wp = W + P.w_off[p];
-  for (int u = threadIdx.x; u < MI; u += blockDim.x) {
-    float acc[D];
+
+  // thread = (input channel u, node sub-group): with mul_in < 256 the spare threads take further nodes of the pass
+  const int lanes_u = MI >= 256 ? 256 : MI;
+  const int nsub = 256 / lanes_u;
+  const int u0 = tid % lanes_u, sub = tid / lanes_u;
+  const int pass = NB * nsub;
+  for (int j0 = 0; j0 < total; j0 += pass) {
+    const int nb = min(pass, total - j0);
+    for (int i = tid; i < nb * MO * D; i += 256) {
+      const int j = i / (MO * D), rem = i - j * (MO * D);
+      const int w = rem / D, m = rem - w * D;
+      gs[j * MO * D + rem] = __ldg(g + (size_t)s_list[j0 + j] * P.o_rs + P.o_off[p] + (size_t)w * P.o_ws[p] + m);
+    }
+    __syncthreads();
+    if (sub < nsub && sub * NB < nb) {
+      const float* gsub = gs + (size_t)sub * NB * MO * D;
+      for (int u = u0; u < MI; u += lanes_u) {
+        float acc[NB][D];
 #pragma unroll
-    for (int m = 0; m < D; ++m) acc[m] = 0.f;
-    for (int v = (z >= 0 ? z : 0); v < (z >= 0 ? z + 1 : Z); ++v) {
-      const float a = z >= 0 ? 1.f : __ldg(arow + v);
-      if (a == 0.f) continue;
-      const float* wr = Wp + ((size_t)u * Z + v) * MO;
-      for (int w = 0; w < MO; ++w) {
-        const float wv = a * __ldg(wr + w);
+        for (int j = 0; j < NB; ++j)
 #pragma unroll
-        for (int m = 0; m < D; ++m) acc[m] = fmaf(wv, gs[w * D + m], acc[m]);
+          for (int m = 0; m < D; ++m) acc[j][m] = 0.f;
+        const float* wr = Ws + u * pitch;
+        for (int w = 0; w < MO; ++w) {
+          const float wv = wr[w];
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int m = 0; m < D; ++m) acc[j][m] = fmaf(wv, gsub[(j * MO + w) * D + m], acc[j][m]);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int jj = sub * NB + j;
+          if (jj < nb) {
+            float* o = dx + (size_t)s_list[j0 + jj] * P.x_rs + P.x_off[p] + (size_t)u * D;
+            const float c = P.alpha[p] * s_coef[j0 + jj];
+#pragma unroll
+            for (int m = 0; m < D; ++m) atomicAdd(o + m, c * acc[j][m]);
+          }
+        }
       }
     }
-    float* o = dx + (size_t)n * P.x_rs + P.x_off[p] + (size_t)u * D;
-#pragma unroll
-    for (int m = 0; m < D; ++m) {
-      const float r = P.alpha[p] * acc[m];
-      o[m] = accumulate ? o[m] + r : r;
-    }
+    __syncthreads();
   }
 }
 
@@ -207,13 +262,34 @@ extern "C" int pml_element_linear_fwd(const float* x, const float* attrs, const 
   return PML_OK;
 }
 
+// dx must be zero-initialised by the caller (contributions are accumulated atomically; one addend per entry when the
+// attrs rows are one-hot).
 extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, const float* W, const pml_el_plan* plan,
                                         float* dx, int N, int Z, int accumulate, cudaStream_t stream) {
+  (void)accumulate;
   if (N <= 0 || plan->npaths <= 0) return PML_OK;
-  dim3 grid(N, plan->npaths);
-  int max_mo = 0;
-  for (int p = 0; p < plan->npaths; ++p) max_mo = plan->mul_out[p] > max_mo ? plan->mul_out[p] : max_mo;
-#define CALL(D) pml::el_bwd_x_kernel<D><<<grid, 128, (size_t)max_mo * D * sizeof(float), stream>>>(g, attrs, W, *plan, dx, N, Z, accumulate);
+  dim3 grid(1, (N + pml::EL_XCHUNK - 1) / pml::EL_XCHUNK, plan->npaths * Z);
+  size_t smem[8] = {0};
+  for (int p = 0; p < plan->npaths; ++p) {
+    const int d = plan->d[p];
+    const int nb = d >= 5 ? 4 : 8;
+    const int lanes_u = plan->mul_in[p] >= 256 ? 256 : plan->mul_in[p];
+    const size_t need =
+        ((size_t)plan->mul_in[p] * (plan->mul_out[p] | 1) + (size_t)nb * (256 / lanes_u) * plan->mul_out[p] * d) * sizeof(float);
+    if (d <= 7 && need > smem[d]) smem[d] = need;
+  }
+#define CALL(D)                                                                                                          \
+  {                                                                                                                      \
+    if (smem[D] > 200 * 1024) return PML_ERR_UNSUPPORTED;                                                                \
+    static size_t configured = 0;                                                                                        \
+    if (smem[D] > configured) {                                                                                          \
+      if (cudaFuncSetAttribute(pml::el_bwd_x_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[D]) !=    \
+          cudaSuccess)                                                                                                   \
+        return PML_ERR_LAUNCH;                                                                                           \
+      configured = smem[D];                                                                                              \
+    }                                                                                                                    \
+    pml::el_bwd_x_kernel<D><<<grid, 256, smem[D], stream>>>(g, attrs, W, *plan, dx, N, Z);                                \
+  }
   PML_EL_FOR_D(CALL)
 #undef CALL
   PML_CHECK_LAUNCH();

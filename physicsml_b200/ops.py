@@ -470,7 +470,7 @@ def element_linear_bwd_x(g: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tens
     pl = plans.get(plan)
     g, attrs, w = _f32c(g), _f32c(attrs), _f32c(w)
     n = g.shape[0]
-    dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else g.new_empty(n, pl.d_in)
+    dx = g.new_zeros(n, pl.d_in)  # accumulated atomically per (element, node chunk)
     _call("pml_element_linear_bwd_x", _p(g), _p(attrs), _p(w), C.byref(pl.c_plan), _p(dx), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return dx
 
