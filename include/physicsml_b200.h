@@ -114,13 +114,6 @@ int pml_gemm_grouped(const float* A, const float* B, float* C, const pml_gemm_pr
 int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                         int max_M, int max_N, int max_batch, int splitk, int max_k, pml_stream_t stream);
 
-/* Variant of the tensor-core GEMM for problem tables whose A operand has contiguous, 16-byte aligned K rows with
- * K % 4 == 0 in every chunk (the radial-MLP activations / cotangents): A is copied with cp.async straight into the UMMA
- * layout as raw fp32 and only the tf32 truncation remainder is computed by threads.  b_async != 0: B has contiguous K
- * rows as well (b_rs == 1, same alignment) and every problem has a single chunk; B then takes the same route. */
-int pml_gemm_rowk_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
-                     int max_M, int max_N, int max_batch, int splitk, int max_k, int b_async, pml_stream_t stream);
-
 /* ---- K5b: element-indexed linear (FullyConnectedTensorProduct with one-hot node attributes) ------------------------
  * Replaces mix_layer / residual_connection_layer (models/mace/modules/blocks.py:183-188,72-78) and NequIP's
  * self_connection_layer (models/nequip/modules/interaction_block.py:73-82). */

@@ -106,7 +106,6 @@ SIGNATURES = {
     "pml_sym_dbl": [_I, _P, _P, _P, C.POINTER(SymWeights), _P, _P, _P, _I, _I, _I, _P],
     "pml_gemm_grouped": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pml_gemm_grouped_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "pml_gemm_rowk_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "pml_element_linear_fwd": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
     "pml_element_linear_bwd_x": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
     "pml_element_linear_bwd_w": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],

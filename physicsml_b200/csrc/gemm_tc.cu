@@ -465,363 +465,6 @@ static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_pr
 }
 
 
-// =====================================================================================================================
-// Row-major-K variant for the edge-sized radial-MLP GEMMs (A = activations / cotangents with contiguous K rows).
-// ncu on the kernel above at 41 570 x 64 -> 1280: tensor pipe 10 % active, 340 warp instructions per 16-wide k-block for
-// the global -> register -> hi/lo -> shared staging, and every k-block waits on its loads.  Here
-//   * A is copied by 16-byte cp.async straight into the canonical UMMA layout as RAW fp32, RAW_STAGES k-blocks deep (no
-//     registers, no waiting).  The tensor core reads the upper 19 bits of an fp32 word as tf32, i.e. A_t = trunc(A), so
-//     only the remainder A_r = A - A_t (exact in fp32) is computed by threads, each on the units it copied itself:
-//         A B  ~=  A_t B_hi + A_t B_lo + A_r B_hi        (B through the register hi/lo path, chunk scale folded into B)
-//   * with B_ASYNC (B has contiguous K rows too: the dx GEMMs, B = W^T) B takes the same route:
-//         A B  ~=  A_t B_t + A_t B_r + A_r B_t
-// Same problem table, promotion scheme and epilogues as above.  The host selects it only for plans whose problems all
-// have a_cs == 1, K % 4 == 0 and 16-byte aligned rows (and, for B_ASYNC, b_rs == 1 and a single chunk, whose scale
-// folds into alpha).
-// =====================================================================================================================
-constexpr int RAW_STAGES = 6, RAW_AHEAD = RAW_STAGES - 2;
-
-template <int BN, bool B_ASYNC>
-struct __align__(128) RowkSmem {
-  float a_raw[RAW_STAGES][TC_BM * TC_BK];
-  float a_rem[TC_STAGES][TC_BM * TC_BK];
-  float b0[B_ASYNC ? RAW_STAGES : TC_STAGES][BN * TC_BK];  // B_ASYNC: raw ring ; else hi
-  float b1[TC_STAGES][BN * TC_BK];                         // B_ASYNC: remainder ; else lo
-  unsigned long long bar[TC_STAGES];
-  unsigned long long accbar[2];
-  uint32_t tmem_base;
-  pml_gemm_problem prob;
-};
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// copy the [ROWS x 16] k-block at (row0, k0) of a K-contiguous operand into the canonical layout (zero fill outside)
-template <int ROWS>
-__device__ __forceinline__ void async_tile(const float* __restrict__ base, long long rs, int row0, int nrows, int k0, int K,
-                                           float* __restrict__ sdst) {
-  constexpr int UNITS = ROWS * (TC_BK / 4);
-#pragma unroll
-  for (int it = 0; it < (UNITS + TC_THREADS - 1) / TC_THREADS; ++it) {
-    const int idx = threadIdx.x + it * TC_THREADS;
-    if (UNITS % TC_THREADS != 0 && idx >= UNITS) continue;
-    const int r = (idx & 7) + 8 * (idx >> 5), kc = (idx >> 3) & 3;  // see tile_coords
-    const int gr = row0 + r, gk = k0 + kc * 4;
-    const bool ok = gr < nrows && gk < K;
-    const float* src = ok ? base + (long long)gr * rs + gk : base;
-    const int unit = (r & 7) + 8 * kc + 32 * (r >> 3);
-    cp_async16_zfill(smem_u32(sdst + 4 * unit), src, ok ? 16u : 0u);
-  }
-}
-
-// remainder of the tf32 truncation for the units this thread copied itself: rem = x - (x with 13 low bits cleared)
-template <int ROWS>
-__device__ __forceinline__ void remainder_tile(const float* __restrict__ sraw, float* __restrict__ srem) {
-  constexpr int UNITS = ROWS * (TC_BK / 4);
-#pragma unroll
-  for (int it = 0; it < (UNITS + TC_THREADS - 1) / TC_THREADS; ++it) {
-    const int idx = threadIdx.x + it * TC_THREADS;
-    if (UNITS % TC_THREADS != 0 && idx >= UNITS) continue;
-    const int r = (idx & 7) + 8 * (idx >> 5), kc = (idx >> 3) & 3;
-    const int unit = (r & 7) + 8 * kc + 32 * (r >> 3);
-    const float4 x = reinterpret_cast<const float4*>(sraw)[unit];
-    float4 o;
-    o.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-    o.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-    o.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-    o.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-    reinterpret_cast<float4*>(srem)[unit] = o;
-  }
-}
-
-template <int BN, bool PROMOTE, bool B_ASYNC>
-__global__ void __launch_bounds__(TC_THREADS) gemm_rowk_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                                  float* __restrict__ C,
-                                                                  const pml_gemm_problem* __restrict__ probs,
-                                                                  int M_runtime, int splitk) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  RowkSmem<BN, B_ASYNC>& S = *reinterpret_cast<RowkSmem<BN, B_ASYNC>*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  {
-    const pml_gemm_problem& Pg = probs[blockIdx.y];
-    const int Mg = Pg.M < 0 ? M_runtime : Pg.M;
-    const int tiles_ng = (Pg.N + BN - 1) / BN;
-    const int tmg = blockIdx.x / tiles_ng;
-    if (tmg * TC_BM >= Mg || (int)(blockIdx.z / splitk) >= Pg.nbatch) return;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&Pg);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&S.prob);
-    for (int i = tid; i < (int)(sizeof(pml_gemm_problem) / 4); i += TC_THREADS) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const pml_gemm_problem& P = S.prob;
-  const int M = P.M < 0 ? M_runtime : P.M;
-  const int N = P.N;
-  const int tiles_n = (N + BN - 1) / BN;
-  const int tm = blockIdx.x / tiles_n, tn = blockIdx.x - tm * tiles_n;
-  int zb = blockIdx.z;
-  const int ks = zb % splitk;
-  zb /= splitk;
-  const long long a_rs = P.a_rs, b_rs = P.b_rs, b_cs = P.b_cs;
-  const int nchunks = P.nchunks;
-  const long long a_boff = (long long)zb * P.a_bs, b_boff = (long long)zb * P.b_bs;
-  const bool b_kfast = b_rs == 1;
-  const bool b_vec_base = b_kfast && ((b_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-
-  constexpr int NBUF = PROMOTE ? 2 : 1;
-  constexpr uint32_t TMEM_COLS = (NBUF * BN) < 32 ? 32 : (NBUF * BN);
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TC_STAGES; ++s) mbar_init(smem_u32(&S.bar[s]), 1);
-    mbar_init(smem_u32(&S.accbar[0]), 1);
-    mbar_init(smem_u32(&S.accbar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = S.tmem_base;
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-  const int row0 = tm * TC_BM, col0 = tn * BN;
-
-  struct KPos {
-    int ch, k0;
-  };
-  auto chunk_k = [&](int ch) { return P.kc[ch] < 0 ? M_runtime : P.kc[ch]; };
-  auto first_pos = [&](int ch_from) {
-    KPos q{ch_from, ks * TC_BK};
-    while (q.ch < nchunks && q.k0 >= chunk_k(q.ch)) ++q.ch;
-    return q;
-  };
-  auto next_pos = [&](KPos q) {
-    q.k0 += TC_BK * splitk;
-    if (q.k0 >= chunk_k(q.ch)) return first_pos(q.ch + 1);
-    return q;
-  };
-  // asynchronous copies of one k-block (always exactly one commit group per call, possibly empty)
-  auto issue_async = [&](const KPos& q, int raw_slot) {
-    if (q.ch < nchunks) {
-      const int K = chunk_k(q.ch);
-      async_tile<TC_BM>(A + P.a_off[q.ch] + a_boff, a_rs, row0, M, q.k0, K, S.a_raw[raw_slot]);
-      if (B_ASYNC) async_tile<BN>(B + P.b_off[q.ch] + b_boff, b_cs, col0, N, q.k0, K, S.b0[raw_slot]);
-    }
-    cp_async_commit();
-  };
-  auto fetch_b = [&](const KPos& q, TileRegs<BN>& rb) {
-    const long long boff = P.b_off[q.ch] + b_boff;
-    fetch_tile<BN>(B + boff, b_cs, b_rs, col0, N, q.k0, chunk_k(q.ch), b_vec_base && ((boff & 3) == 0), rb);
-  };
-
-  constexpr int NHALF = BN >= 64 ? 2 : 1;
-  constexpr int COLS_PER_WARP = BN / NHALF;
-  const int q = warp & 3, half = warp >> 2;
-  float acc[PROMOTE ? COLS_PER_WARP : 1];
-  if (PROMOTE) {
-#pragma unroll
-    for (int j = 0; j < COLS_PER_WARP; ++j) acc[j] = 0.f;
-  }
-  auto promote = [&](int period) {
-    const int buf = period & 1;
-    mbar_wait(smem_u32(&S.accbar[buf]), (period >> 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (half < NHALF) {
-      float v[COLS_PER_WARP];
-      tmem_ld_cols<COLS_PER_WARP / 32>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * COLS_PER_WARP), v);
-#pragma unroll
-      for (int j = 0; j < COLS_PER_WARP; ++j) acc[PROMOTE ? j : 0] += v[j];
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  };
-
-  // prologue: RAW_AHEAD k-blocks of asynchronous copies in flight
-  KPos apos = first_pos(0);  // next k-block to copy asynchronously
-  KPos cur = apos;           // k-block being multiplied
-#pragma unroll 1
-  for (int i = 0; i < RAW_AHEAD; ++i) {
-    issue_async(apos, i);
-    if (apos.ch < nchunks) apos = next_pos(apos);
-  }
-  TileRegs<BN> rb[2];
-  KPos bpos1 = cur.ch < nchunks ? next_pos(cur) : cur;
-  if (!B_ASYNC) {
-    if (cur.ch < nchunks) fetch_b(cur, rb[0]);
-    if (bpos1.ch < nchunks) fetch_b(bpos1, rb[1]);
-  }
-  int it = 0, to_promote = -1;
-#pragma unroll 1
-  while (cur.ch < nchunks) {
-    const KPos nxt = next_pos(cur);
-    const int s = it % TC_STAGES, raw = it % RAW_STAGES;
-    // stage s (remainder / B buffers) and raw slot (it + RAW_AHEAD) % RAW_STAGES were last read by the MMAs of k-block it-2
-    if (it >= TC_STAGES) mbar_wait(smem_u32(&S.bar[s]), ((it / TC_STAGES) - 1) & 1);
-    issue_async(apos, (it + RAW_AHEAD) % RAW_STAGES);
-    if (apos.ch < nchunks) apos = next_pos(apos);
-    cp_async_wait<RAW_AHEAD>();  // this thread's copies of k-block `it` have landed
-    remainder_tile<TC_BM>(S.a_raw[raw], S.a_rem[s]);
-    if (B_ASYNC) {
-      remainder_tile<BN>(S.b0[raw], S.b1[s]);
-    } else {
-      const KPos b2 = nxt.ch < nchunks ? next_pos(nxt) : nxt;
-      if ((it & 1) == 0) {
-        commit_tile<BN>(rb[0], b_kfast, P.cscale[cur.ch], S.b0[s], S.b1[s]);
-        if (b2.ch < nchunks) fetch_b(b2, rb[0]);
-      } else {
-        commit_tile<BN>(rb[1], b_kfast, P.cscale[cur.ch], S.b0[s], S.b1[s]);
-        if (b2.ch < nchunks) fetch_b(b2, rb[1]);
-      }
-    }
-    if (PROMOTE && to_promote >= 0) {
-      promote(to_promote);
-      to_promote = -1;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    const int period = PROMOTE ? it / kPromoBlocks : 0;
-    const bool opens = PROMOTE ? (it % kPromoBlocks == 0) : (it == 0);
-    const bool closes = PROMOTE ? ((it % kPromoBlocks == kPromoBlocks - 1) || nxt.ch >= nchunks) : (nxt.ch >= nchunks);
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_t = smem_u32(S.a_raw[raw]), a_r = smem_u32(S.a_rem[s]);
-      const uint32_t b_t = smem_u32(B_ASYNC ? S.b0[raw] : S.b0[s]), b_r = smem_u32(S.b1[s]);
-      const uint32_t d = tmem + (uint32_t)((period & 1) * BN);
-#pragma unroll
-      for (int kk = 0; kk < TC_BK / 8; ++kk) {
-        const uint32_t o = kk * 256;
-        umma_tf32(d, make_desc(a_r + o), make_desc(b_t + o), IDESC, (!opens || kk > 0) ? 1u : 0u);
-        umma_tf32(d, make_desc(a_t + o), make_desc(b_r + o), IDESC, 1u);
-        umma_tf32(d, make_desc(a_t + o), make_desc(b_t + o), IDESC, 1u);
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[s]))
-                   : "memory");
-      if (closes)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(&S.accbar[period & 1]))
-                     : "memory");
-    }
-    if (PROMOTE && closes) to_promote = period;
-    cur = nxt;
-    ++it;
-  }
-  cp_async_wait<0>();
-
-  if (it > 0) {
-    float* Cb = C + P.c_off + (long long)zb * P.c_bs;
-    const bool atomic = splitk > 1 || (P.c_bs == 0 && P.nbatch > 1);
-    const bool direct = !atomic && P.c_cs == 1 && ((P.c_rs & 3) == 0) && (((P.c_off + (long long)zb * P.c_bs) & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (N % 4 == 0);
-    if (PROMOTE) {
-      if (to_promote >= 0) promote(to_promote);
-    } else {
-      mbar_wait(smem_u32(&S.accbar[0]), 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    const int r = row0 + q * 32 + lane;
-    const float alpha = B_ASYNC ? P.alpha * P.cscale[0] : P.alpha;  // B_ASYNC: single chunk, its scale folds into alpha
-    const bool accumulate = P.accumulate != 0;
-    const long long c_rs = P.c_rs, c_cs = P.c_cs;
-    if (direct) {
-      if (half < NHALF) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
-          float v[32];
-          if (PROMOTE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = acc[PROMOTE ? (c0 + j) : 0];
-          } else {
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
-          }
-          const int gc0 = col0 + half * COLS_PER_WARP + c0;
-          if (r < M) {
-            float* prow = Cb + (long long)r * c_rs + gc0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (gc0 + j < N) {
-                float4 o = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
-                if (accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(prow + j);
-                  o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(prow + j) = o;
-              }
-            }
-          }
-        }
-      }
-    } else {
-      constexpr int PITCH = 32 * NHALF + 1;
-      float* stg = reinterpret_cast<float*>(S.a_raw);
-      static_assert(sizeof(float) * TC_BM * PITCH <= sizeof(S.a_raw), "staging tile does not fit");
-      __syncthreads();
-#pragma unroll 1
-      for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
-        if (half < NHALF) {
-          float v[32];
-          if (PROMOTE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = acc[PROMOTE ? (c0 + j) : 0];
-          } else {
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[(q * 32 + lane) * PITCH + half * 32 + j] = v[j];
-        }
-        __syncthreads();
-        for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
-          const int gr = row0 + rr;
-          if (gr >= M) break;
-#pragma unroll
-          for (int h = 0; h < NHALF; ++h) {
-            const int gc = col0 + h * COLS_PER_WARP + c0 + lane;
-            if (gc < N) {
-              float* p = Cb + (long long)gr * c_rs + (long long)gc * c_cs;
-              const float val = alpha * stg[rr * PITCH + h * 32 + lane];
-              if (atomic) atomicAdd(p, val);
-              else if (accumulate) *p += val;
-              else *p = val;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-template <int BN, bool PROMOTE, bool B_ASYNC>
-static int launch_rowk(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
-                       int max_M, int max_N, int max_batch, int splitk, cudaStream_t stream) {
-  const int tiles_m = (max_M + TC_BM - 1) / TC_BM, tiles_n = (max_N + BN - 1) / BN;
-  const long long gz = (long long)max_batch * splitk;
-  if (gz > 65535 || nprobs > 65535) return PML_ERR_BAD_ARG;
-  const size_t smem = sizeof(RowkSmem<BN, B_ASYNC>) + 128;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_rowk_tc_kernel<BN, PROMOTE, B_ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
-      return PML_ERR_LAUNCH;
-    configured = true;
-  }
-  dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)nprobs, (unsigned)gz);
-  gemm_rowk_tc_kernel<BN, PROMOTE, B_ASYNC><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
-  return PML_OK;
-}
-
 }  // namespace pml
 
 // Same contract as pml_gemm_grouped (gemm.cu) plus max_k: an upper bound of the reduction length one CTA sees (sum of
@@ -842,31 +485,6 @@ extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, con
     else if (max_N <= 64) rc = pml::launch_tc<64, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
     else rc = pml::launch_tc<128, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
   }
-  if (rc != PML_OK) return rc;
-  PML_CHECK_LAUNCH();
-  return PML_OK;
-}
-
-// Variant for problem tables whose A operand has contiguous, 16-byte aligned K rows with K % 4 == 0 in every chunk
-// (the caller checks; see gemm_rowk_tc_kernel).  b_async != 0 additionally requires b_rs == 1 with the same alignment
-// and a single chunk per problem.
-extern "C" int pml_gemm_rowk_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
-                                int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k, int b_async,
-                                cudaStream_t stream) {
-  if (nprobs <= 0 || max_M <= 0 || max_N <= 0 || max_batch <= 0) return PML_OK;
-  if (splitk < 1) splitk = 1;
-  if ((reinterpret_cast<uintptr_t>(A) & 15) || (b_async && (reinterpret_cast<uintptr_t>(B) & 15))) return PML_ERR_BAD_ARG;
-  const bool promote = max_k <= 0 || max_k > pml::kPromoBlocks * pml::TC_BK;
-  int rc;
-#define PML_ROWK(BN_, P_)                                                                                               \
-  (b_async ? pml::launch_rowk<BN_, P_, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream) \
-           : pml::launch_rowk<BN_, P_, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream))
-  if (promote) {
-    rc = max_N <= 32 ? PML_ROWK(32, true) : PML_ROWK(64, true);
-  } else {
-    rc = max_N <= 32 ? PML_ROWK(32, false) : (max_N <= 64 ? PML_ROWK(64, false) : PML_ROWK(128, false));
-  }
-#undef PML_ROWK
   if (rc != PML_OK) return rc;
   PML_CHECK_LAUNCH();
   return PML_OK;

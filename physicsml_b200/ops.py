@@ -308,15 +308,9 @@ def _gemm_name(n_runtime: int) -> str:
     return "pml_gemm_grouped_tc" if (GEMM_MODE[0] == "tc" and n_runtime >= TC_MIN_ROWS[0]) else "pml_gemm_grouped"
 
 
-ROWK = [os.environ.get("PML_GEMM_ROWK", "1") == "1"]  # cp.async operand path of the tensor-core GEMM when the plan allows
-
-
 def _gemm(name: str, a, b, c, table, nprob: int, m_runtime: int, max_m: int, max_n: int, max_batch: int, splitk: int,
-          max_k: int, rowk: int = 0) -> None:
-    if name.endswith("_tc") and rowk and ROWK[0]:
-        _call("pml_gemm_rowk_tc", a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, max_k,
-              1 if rowk == 2 else 0, _stream())
-    elif name.endswith("_tc"):
+          max_k: int) -> None:
+    if name.endswith("_tc"):
         _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, max_k, _stream())
     else:
         _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, _stream())
@@ -342,10 +336,9 @@ def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
             sz = C.sizeof(_lib.GemmProblem)
             for k in range(nprob):
                 _gemm(_gemm_name(n), _p(x), _p(w), _p(out), fwd.data_ptr() + k * sz, 1, n, n, pl.max_mul_out, pl.max_d, 1,
-                      pl.max_k_fwd, pl.rowk_fwd)
+                      pl.max_k_fwd)
         else:
-            _gemm(_gemm_name(n), _p(x), _p(w), _p(out), _p(fwd), nprob, n, n, pl.max_mul_out, pl.max_d, 1, pl.max_k_fwd,
-                  pl.rowk_fwd)
+            _gemm(_gemm_name(n), _p(x), _p(w), _p(out), _p(fwd), nprob, n, n, pl.max_mul_out, pl.max_d, 1, pl.max_k_fwd)
     return out
 
 
@@ -365,8 +358,7 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
     dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else g.new_empty(n, pl.d_in)
     _, bx, _ = pl.tables(g.device)
     if bx is not None and n > 0:
-        _gemm(_gemm_name(n), _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, pl.max_k_bwd_x,
-              pl.rowk_bwd_x)
+        _gemm(_gemm_name(n), _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, pl.max_k_bwd_x)
     return dx
 
 

@@ -138,19 +138,6 @@ class LinearPlan:
             p.M, p.N, p.nbatch, p.alpha, p.accumulate = -1, mi, d, 1.0, 0
             bx.append(p)
         self.has_unfed_input = len(bx) < len(self.irreps_in)
-        # eligibility for the cp.async operand path of the tensor-core GEMM (pml_gemm_rowk_tc): 0 no, 1 A only, 2 A and B
-        def rowk(problems):
-            if not problems:
-                return 0
-            a_ok = all(p.a_cs == 1 and p.a_rs % 4 == 0 and (p.nbatch == 1 or p.a_bs % 4 == 0) and
-                       all(p.kc[c] > 0 and p.kc[c] % 4 == 0 and p.a_off[c] % 4 == 0 for c in range(p.nchunks)) for p in problems)
-            if not a_ok:
-                return 0
-            b_ok = all(p.b_rs == 1 and p.b_cs % 4 == 0 and p.nchunks == 1 and p.b_off[0] % 4 == 0 and
-                       (p.nbatch == 1 or p.b_bs % 4 == 0) for p in problems)
-            return 2 if b_ok else 1
-
-        self.rowk_fwd, self.rowk_bwd_x = rowk(fwd), rowk(bx)
         # longest reduction of any problem (selects the accumulator-promoting tensor-core kernel above 128)
         self.max_k_fwd = max([sum(p.kc[c] for c in range(p.nchunks)) for p in fwd] + [1])
         self.max_k_bwd_x = max([sum(p.kc[c] for c in range(p.nchunks)) for p in bx] + [1])
