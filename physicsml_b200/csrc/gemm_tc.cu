@@ -160,6 +160,7 @@ template <int BN>
 struct __align__(128) TcSmem {
   float a[TC_STAGES][2][TC_BM * TC_BK];
   float b[TC_STAGES][2][BN * TC_BK];
+  float stage_pad[(TC_BM * (BN + 4) > 2 * 2 * (TC_BM + BN) * TC_BK) ? (TC_BM * (BN + 4) - 2 * 2 * (TC_BM + BN) * TC_BK) : 4];
   unsigned long long bar[TC_STAGES];  // ring: the MMAs that read a stage have retired
   unsigned long long accbar[2];       // an accumulation period has retired into TMEM buffer 0 / 1
   uint32_t tmem_base;
@@ -370,8 +371,15 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
     const bool accumulate = P.accumulate != 0;
     const long long c_rs = P.c_rs, c_cs = P.c_cs;
     if (direct) {
-      // row-major C: every thread owns 32-column (128-byte) runs of its row -> 16-byte vector stores, no staging, no
-      // block-wide synchronisation; the eight stores of a run complete one line in L2
+      // row-major C: the whole tile goes through shared memory once (pitch BN + 4 floats: conflict-free 128-bit accesses
+      // both by rows, as written, and along a row, as read) and leaves as full rows, one 16-byte vector per lane = up to
+      // 512 contiguous bytes per warp instruction.  (Storing straight from registers, 16 bytes per lane into 32
+      // different rows, cost 32 L1 wavefronts per instruction: the epilogue alone took 110 of the 179 us of the
+      // 41 570 x 64 -> 1280 forward.)
+      constexpr int SP = BN + 4;
+      float* stg = reinterpret_cast<float*>(S.a);  // [128][SP]: the operand ring (all MMAs retired) + stage_pad
+      static_assert(sizeof(float) * TC_BM * SP <= sizeof(S.a) + sizeof(S.b) + sizeof(S.stage_pad), "staging tile does not fit");
+      __syncthreads();  // nobody still converts into the ring
       if (half < NHALF) {
 #pragma unroll 1
         for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
@@ -382,21 +390,26 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
           } else {
             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
           }
-          const int gc0 = col0 + half * COLS_PER_WARP + c0;
-          if (r < M) {
-            float* prow = Cb + (long long)r * c_rs + gc0;
+          float* srow = stg + (q * 32 + lane) * SP + half * COLS_PER_WARP + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (gc0 + j < N) {
-                float4 o = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
-                if (accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(prow + j);
-                  o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(prow + j) = o;
-              }
-            }
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(srow + j) = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+        }
+      }
+      __syncthreads();
+      constexpr int VPR = BN / 4;              // 16-byte vectors per row
+      constexpr int RPI = 32 / VPR > 0 ? 32 / VPR : 1;  // rows per warp instruction (BN = 128: 1, 64: 2, 32: 4)
+      const int vr = lane / VPR, vc = lane % VPR;
+      for (int rr = warp * RPI + vr; rr < TC_BM; rr += (TC_THREADS / 32) * RPI) {
+        const int gr = row0 + rr, gc = col0 + vc * 4;
+        if (gr < M && gc < N) {
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * SP + vc * 4);
+          float* p = Cb + (long long)gr * c_rs + gc;
+          if (accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(p);
+            o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
           }
+          *reinterpret_cast<float4*>(p) = o;
         }
       }
     } else {
