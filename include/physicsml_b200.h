@@ -160,6 +160,10 @@ typedef struct {
 int pml_gate(const float* x, const float* dy, const float* v, const pml_gate_plan* plan, int mode, float* out0,
              float* out1, int N, pml_stream_t stream);
 
+/* Test utility: overwrite the shared memory of every SM with NaN (exposes kernels that read shared memory they never
+ * wrote). */
+int pml_debug_poison_smem(pml_stream_t stream);
+
 /* per-graph pooled readout (models/mace/modules/mace.py:252-258): out[batch[n],f] += x[n,f]; out zero-initialised */
 int pml_pool_sum(const float* x, const long long* batch, float* out, int N, int F, pml_stream_t stream);
 int pml_pool_gather(const float* g, const long long* batch, float* out, int N, int F, pml_stream_t stream);

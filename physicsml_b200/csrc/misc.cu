@@ -1,6 +1,8 @@
 // Small elementwise / segmented kernels on the path: normalised SiLU (and tanh) with first and second derivative
 // forms for the radial MLP and readout (e3nn nn.FullyConnectedNet / normalize2mom; reference blocks.py:157-160,11-28),
 // the per-graph pooled readout (mace.py:252-258) and the receiver-CSR build used by the fused edge kernels.
+#include <stdio.h>
+
 #include "pml_common.cuh"
 
 namespace pml {
@@ -120,7 +122,32 @@ __global__ void __launch_bounds__(256) irreps_to_channel_kernel(const float* __r
   else y[i] = x[j];
 }
 
+// test utility: fill the shared memory of every SM with NaN, so that a kernel reading shared memory it never wrote (the
+// residue of whatever ran before) turns a rare, tiny discrepancy into a NaN
+__global__ void poison_smem_kernel(int words) {
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = __int_as_float(0x7fc00000);
+  __syncthreads();
+  if (sm[(threadIdx.x * 31) % words] == 0.f) printf("unreachable\n");
+}
+
 }  // namespace pml
+
+extern "C" int pml_debug_poison_smem(cudaStream_t stream) {
+  int dev = 0, sms = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(pml::poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin) != cudaSuccess)
+      return PML_ERR_LAUNCH;
+    configured = true;
+  }
+  pml::poison_smem_kernel<<<sms, 256, max_optin, stream>>>(max_optin / 4);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
 
 extern "C" int pml_act(const float* x, const float* g, const float* v, float c, int kind, int order, float* y,
                        long long n, cudaStream_t stream) {
