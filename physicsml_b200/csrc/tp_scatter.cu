@@ -278,6 +278,10 @@ constexpr int kTileEdges = 512;
 
 struct TileSched {
   int TN, ntiles, G;  // nodes per tile, number of tiles, CTAs that take part (the others exit)
+  // Tiles are walked from the END of the node range: the R rows (and, in the cotangent pass, the g rows) of the last
+  // nodes are the ones their producer kernel wrote last, i.e. the part of a tensor larger than L2 that is still
+  // resident when this kernel starts.
+  __device__ __forceinline__ int first_node(int tile) const { return (ntiles - 1 - tile) * TN; }
 };
 
 __device__ __forceinline__ TileSched tile_schedule(const int* __restrict__ rowptr, int N) {
@@ -331,7 +335,7 @@ struct PipeProducer {
   __device__ __forceinline__ void tile_bounds(int tile, int& q, int& q_hi) const {
     q = 0, q_hi = 0;
     if (tile < ts.ntiles) {
-      const int n0 = tile * ts.TN, n1 = min(N, n0 + ts.TN);
+      const int n0 = ts.first_node(tile), n1 = min(N, n0 + ts.TN);
       q = __ldg(rowptr + n0), q_hi = __ldg(rowptr + n1);
     }
   }
@@ -462,7 +466,7 @@ __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __r
   using L = PipeLayout<ID>;
   PML_PIPE_PROLOGUE(true)
   for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
-    const int n0 = tile * ts.TN, n1 = min(N, n0 + ts.TN);
+    const int n0 = ts.first_node(tile), n1 = min(N, n0 + ts.TN);
     int q = __ldg(rowptr + n0);
     int end = __ldg(rowptr + n0 + 1);
     for (int n = n0; n < n1; ++n) {
@@ -507,7 +511,7 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
   const size_t rstride = (size_t)rfl, hstride = (size_t)hfl;
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
-    const int n0 = tile * ts.TN, n1 = min(N, n0 + ts.TN);
+    const int n0 = ts.first_node(tile), n1 = min(N, n0 + ts.TN);
     int q = __ldg(rowptr + n0);
     int end = __ldg(rowptr + n0 + 1);
     for (int n = n0; n < n1; ++n) {
