@@ -89,8 +89,8 @@ constexpr int EL_XCHUNK = 256;
 template <int D>
 __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ attrs,
                                                        const float* __restrict__ W, pml_el_plan P, float* __restrict__ dx,
-                                                       int N, int Z) {
-  constexpr int NB = D >= 5 ? 4 : 8;  // nodes per pass
+                                                       int N, int Z, int WC) {
+  constexpr int NB = D >= 5 ? 4 : 8;  // nodes per thread and pass
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
   if (P.d[p] != D) return;
   const int MI = P.mul_in[p], MO = P.mul_out[p];
@@ -99,9 +99,10 @@ __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__
   __shared__ float s_coef[EL_XCHUNK];
   __shared__ int s_wcnt[8];
   extern __shared__ float dyn[];
-  const int pitch = MO | 1;                  // odd: thread u reads Ws[u][w] without bank conflicts
+  const int wc = min(WC, MO);                // columns of the slab staged at a time (all of them when they fit)
+  const int pitch = wc | 1;                  // odd: thread u reads Ws[u][w] without bank conflicts
   float* Ws = dyn;                           // [MI][pitch]
-  float* gs = dyn + (size_t)MI * pitch;      // [NB * nsub][MO * D]
+  float* gs = dyn + (size_t)MI * pitch;      // [NB * nsub][wc * D]
 
   const int n = blockIdx.y * EL_XCHUNK + tid;
   const float a = n < N ? __ldg(attrs + (size_t)n * Z + v) : 0.f;
@@ -120,55 +121,59 @@ __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__
     s_list[pos] = n;
     s_coef[pos] = a;
   }
-  const float* Wp = W + P.w_off[p];
-  for (int i = tid; i < MI * MO; i += 256) {
-    const int u = i / MO, w = i - u * MO;
-    Ws[u * pitch + w] = __ldg(Wp + ((size_t)u * Z + v) * MO + w);
-  }
-  __syncthreads();
-
   // thread = (input channel u, node sub-group): with mul_in < 256 the spare threads take further nodes of the pass
   const int lanes_u = MI >= 256 ? 256 : MI;
   const int nsub = 256 / lanes_u;
   const int u0 = tid % lanes_u, sub = tid / lanes_u;
   const int pass = NB * nsub;
-  for (int j0 = 0; j0 < total; j0 += pass) {
-    const int nb = min(pass, total - j0);
-    for (int i = tid; i < nb * MO * D; i += 256) {
-      const int j = i / (MO * D), rem = i - j * (MO * D);
-      const int w = rem / D, m = rem - w * D;
-      gs[j * MO * D + rem] = __ldg(g + (size_t)s_list[j0 + j] * P.o_rs + P.o_off[p] + (size_t)w * P.o_ws[p] + m);
+  const float* Wp = W + P.w_off[p];
+  // the reduction over w is cut into slab pieces of wc columns; every piece adds its share into dx (same thread, same
+  // order every time, so the result stays deterministic for one-hot attrs)
+  for (int w0 = 0; w0 < MO; w0 += wc) {
+    const int wn = min(wc, MO - w0);
+    __syncthreads();  // the previous piece (and the node list) is no longer being read / is complete
+    for (int i = tid; i < MI * wn; i += 256) {
+      const int u = i / wn, w = i - u * wn;
+      Ws[u * pitch + w] = __ldg(Wp + ((size_t)u * Z + v) * MO + w0 + w);
     }
-    __syncthreads();
-    if (sub < nsub && sub * NB < nb) {
-      const float* gsub = gs + (size_t)sub * NB * MO * D;
-      for (int u = u0; u < MI; u += lanes_u) {
-        float acc[NB][D];
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-#pragma unroll
-          for (int m = 0; m < D; ++m) acc[j][m] = 0.f;
-        const float* wr = Ws + u * pitch;
-        for (int w = 0; w < MO; ++w) {
-          const float wv = wr[w];
+    for (int j0 = 0; j0 < total; j0 += pass) {
+      const int nb = min(pass, total - j0);
+      __syncthreads();
+      for (int i = tid; i < nb * wn * D; i += 256) {
+        const int j = i / (wn * D), rem = i - j * (wn * D);
+        const int w = rem / D, m = rem - w * D;
+        gs[j * wc * D + rem] = __ldg(g + (size_t)s_list[j0 + j] * P.o_rs + P.o_off[p] + (size_t)(w0 + w) * P.o_ws[p] + m);
+      }
+      __syncthreads();
+      if (sub < nsub && sub * NB < nb) {
+        const float* gsub = gs + (size_t)sub * NB * wc * D;
+        for (int u = u0; u < MI; u += lanes_u) {
+          float acc[NB][D];
 #pragma unroll
           for (int j = 0; j < NB; ++j)
 #pragma unroll
-            for (int m = 0; m < D; ++m) acc[j][m] = fmaf(wv, gsub[(j * MO + w) * D + m], acc[j][m]);
-        }
+            for (int m = 0; m < D; ++m) acc[j][m] = 0.f;
+          const float* wr = Ws + u * pitch;
+          for (int w = 0; w < wn; ++w) {
+            const float wv = wr[w];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const int jj = sub * NB + j;
-          if (jj < nb) {
-            float* o = dx + (size_t)s_list[j0 + jj] * P.x_rs + P.x_off[p] + (size_t)u * D;
-            const float c = P.alpha[p] * s_coef[j0 + jj];
+            for (int j = 0; j < NB; ++j)
 #pragma unroll
-            for (int m = 0; m < D; ++m) atomicAdd(o + m, c * acc[j][m]);
+              for (int m = 0; m < D; ++m) acc[j][m] = fmaf(wv, gsub[(j * wc + w) * D + m], acc[j][m]);
+          }
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const int jj = sub * NB + j;
+            if (jj < nb) {
+              float* o = dx + (size_t)s_list[j0 + jj] * P.x_rs + P.x_off[p] + (size_t)u * D;
+              const float c = P.alpha[p] * s_coef[j0 + jj];
+#pragma unroll
+              for (int m = 0; m < D; ++m) atomicAdd(o + m, c * acc[j][m]);
+            }
           }
         }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -269,18 +274,38 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
   (void)accumulate;
   if (N <= 0 || plan->npaths <= 0) return PML_OK;
   dim3 grid(1, (N + pml::EL_XCHUNK - 1) / pml::EL_XCHUNK, plan->npaths * Z);
+  // per D: the largest slab piece (multiple of 32 columns, or all columns) whose staging fits 160 KB of shared memory
   size_t smem[8] = {0};
-  for (int p = 0; p < plan->npaths; ++p) {
-    const int d = plan->d[p];
-    const int nb = d >= 5 ? 4 : 8;
-    const int lanes_u = plan->mul_in[p] >= 256 ? 256 : plan->mul_in[p];
-    const size_t need =
-        ((size_t)plan->mul_in[p] * (plan->mul_out[p] | 1) + (size_t)nb * (256 / lanes_u) * plan->mul_out[p] * d) * sizeof(float);
-    if (d <= 7 && need > smem[d]) smem[d] = need;
+  int wcs[8] = {0};
+  const size_t budget = 160 * 1024;
+  for (int d = 1; d <= 7; d += 2) {
+    int wc = 1 << 30;
+    bool any = false;
+    for (int p = 0; p < plan->npaths; ++p) {
+      if (plan->d[p] != d) continue;
+      any = true;
+      const int mi = plan->mul_in[p], mo = plan->mul_out[p];
+      const int nb = d >= 5 ? 4 : 8, lanes_u = mi >= 256 ? 256 : mi;
+      const size_t per_col = ((size_t)mi + (size_t)nb * (256 / lanes_u) * d) * sizeof(float);
+      int fit = (int)((budget - (size_t)mi * sizeof(float)) / per_col);
+      if (fit >= mo) fit = mo;
+      else fit = fit / 32 * 32;
+      if (fit < 1) return PML_ERR_UNSUPPORTED;
+      if (fit < wc) wc = fit;
+    }
+    if (!any) continue;
+    wcs[d] = wc;
+    for (int p = 0; p < plan->npaths; ++p) {
+      if (plan->d[p] != d) continue;
+      const int mi = plan->mul_in[p], mo = plan->mul_out[p];
+      const int nb = d >= 5 ? 4 : 8, lanes_u = mi >= 256 ? 256 : mi;
+      const int w = wc < mo ? wc : mo;
+      const size_t need = ((size_t)mi * (w | 1) + (size_t)nb * (256 / lanes_u) * w * d) * sizeof(float);
+      if (need > smem[d]) smem[d] = need;
+    }
   }
 #define CALL(D)                                                                                                          \
   {                                                                                                                      \
-    if (smem[D] > 200 * 1024) return PML_ERR_UNSUPPORTED;                                                                \
     static size_t configured = 0;                                                                                        \
     if (smem[D] > configured) {                                                                                          \
       if (cudaFuncSetAttribute(pml::el_bwd_x_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[D]) !=    \
@@ -288,7 +313,7 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
         return PML_ERR_LAUNCH;                                                                                           \
       configured = smem[D];                                                                                              \
     }                                                                                                                    \
-    pml::el_bwd_x_kernel<D><<<grid, 256, smem[D], stream>>>(g, attrs, W, *plan, dx, N, Z);                                \
+    pml::el_bwd_x_kernel<D><<<grid, 256, smem[D], stream>>>(g, attrs, W, *plan, dx, N, Z, wcs[D]);                        \
   }
   PML_EL_FOR_D(CALL)
 #undef CALL

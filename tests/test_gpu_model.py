@@ -15,6 +15,11 @@ CONFIGS = {
                   num_node_feats=5, num_edge_feats=0, hidden_irreps="32x0e + 32x1o", avg_num_neighbours=15.0, correlation=3)),
     "medium": dict(mlp="16x0e", Z=10, kw=dict(cut_off=5.0, num_bessel=8, num_polynomial_cutoff=5, max_ell=3, num_interactions=2,
                    num_node_feats=10, num_edge_feats=0, hidden_irreps="128x0e + 128x1o", avg_num_neighbours=20.0, correlation=3)),
+    # BASELINE configs[4] (MACE large: 256 channels, L = 2, correlation 3) at reduced graph size: exercises the 17-path
+    # tensor product (DOUT = 71: register-streaming K4), the L <= 2 symmetric contraction and 256-wide element slabs
+    "large": dict(mlp="16x0e", Z=4, kw=dict(cut_off=4.0, num_bessel=8, num_polynomial_cutoff=5, max_ell=3, num_interactions=2,
+                  num_node_feats=4, num_edge_feats=0, hidden_irreps="256x0e + 256x1o + 256x2e", avg_num_neighbours=12.0,
+                  correlation=3)),
     "l2": dict(mlp="16x0e", Z=4, kw=dict(cut_off=4.5, num_bessel=8, num_polynomial_cutoff=5, max_ell=3, num_interactions=3,
                num_node_feats=4, num_edge_feats=0, hidden_irreps="16x0e + 16x1o + 16x2e", avg_num_neighbours=12.0, correlation=3)),
 }
@@ -38,8 +43,8 @@ def test_energy_forces_parity(cuda, name):
     from physicsml_b200.mace import compute_forces_by_gradient
 
     ref, mine, cfg = _models(name, cuda)
-    n_mol = 6 if name == "medium" else 10
-    pos, z, batch = helpers.random_molecules(n_mol, 10, 22, cfg["Z"], seed=101)
+    n_mol = {"medium": 6, "large": 3}.get(name, 10)
+    pos, z, batch = helpers.random_molecules(n_mol, 10, 14 if name == "large" else 22, cfg["Z"], seed=101)
     data = helpers.make_batch(pos, z, batch, cfg["Z"], cfg["kw"]["cut_off"])
     e_ref, f_ref = energy_and_forces(ref, data)
     e64, f64 = energy_and_forces(ref.double(), helpers.to_device(data, "cpu", torch.float64))
