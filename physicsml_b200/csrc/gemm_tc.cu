@@ -38,13 +38,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
+// x = hi + lo with hi = x truncated to tf32 (13 low mantissa bits cleared) and lo = x - hi, exact in fp32.  The tensor
+// core reads the upper 19 bits of an operand word, so lo needs no conversion of its own; its truncation to tf32 costs
+// 2^-21 relative, the same order as the A_lo B_lo product 3xTF32 drops anyway.  Two full-rate integer / fp32 ops per
+// element instead of two cvt.rna.tf32 (a reduced-rate conversion pipe shared by the whole SM).
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float r = x - hi;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
 }
 
 // K-major, no swizzle: 16-byte unit (r, kc) of a [ROWS x 16] tile lives at  (r % 8) + 8 * kc + 32 * (r / 8)
