@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__
                                                        const float* __restrict__ W, pml_el_plan P, float* __restrict__ dx,
                                                        int N, int Z, int WC) {
   constexpr int NB = D >= 5 ? 4 : 8;  // nodes per thread and pass
+  constexpr int DP = D == 1 ? 1 : (D == 3 ? 4 : 8);  // staged row width: 128-bit shared-memory loads of the g rows
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
   if (P.d[p] != D) return;
   const int MI = P.mul_in[p], MO = P.mul_out[p];
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__
   const int wc = min(WC, MO);                // columns of the slab staged at a time (all of them when they fit)
   const int pitch = wc | 1;                  // odd: thread u reads Ws[u][w] without bank conflicts
   float* Ws = dyn;                           // [MI][pitch]
-  float* gs = dyn + (size_t)MI * pitch;      // [NB * nsub][wc * D]
+  float* gs = dyn + (((size_t)MI * pitch + 3) & ~(size_t)3);  // [NB * nsub][wc * DP], 16-byte aligned
 
   const int n = blockIdx.y * EL_XCHUNK + tid;
   const float a = n < N ? __ldg(attrs + (size_t)n * Z + v) : 0.f;
@@ -139,14 +140,15 @@ __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__
     for (int j0 = 0; j0 < total; j0 += pass) {
       const int nb = min(pass, total - j0);
       __syncthreads();
-      for (int i = tid; i < nb * wn * D; i += 256) {
-        const int j = i / (wn * D), rem = i - j * (wn * D);
-        const int w = rem / D, m = rem - w * D;
-        gs[j * wc * D + rem] = __ldg(g + (size_t)s_list[j0 + j] * P.o_rs + P.o_off[p] + (size_t)(w0 + w) * P.o_ws[p] + m);
+      for (int i = tid; i < nb * wn * DP; i += 256) {
+        const int j = i / (wn * DP), rem = i - j * (wn * DP);
+        const int w = rem / DP, m = rem - w * DP;
+        gs[(j * wc + w) * DP + m] =
+            m < D ? __ldg(g + (size_t)s_list[j0 + j] * P.o_rs + P.o_off[p] + (size_t)(w0 + w) * P.o_ws[p] + m) : 0.f;
       }
       __syncthreads();
       if (sub < nsub && sub * NB < nb) {
-        const float* gsub = gs + (size_t)sub * NB * wc * D;
+        const float* gsub = gs + (size_t)sub * NB * wc * DP;
         for (int u = u0; u < MI; u += lanes_u) {
           float acc[NB][D];
 #pragma unroll
@@ -157,9 +159,20 @@ __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__
           for (int w = 0; w < wn; ++w) {
             const float wv = wr[w];
 #pragma unroll
-            for (int j = 0; j < NB; ++j)
+            for (int j = 0; j < NB; ++j) {
+              float gv[DP];
+              if (DP == 1) {
+                gv[0] = gsub[j * wc + w];
+              } else {
 #pragma unroll
-              for (int m = 0; m < D; ++m) acc[j][m] = fmaf(wv, gsub[(j * wc + w) * D + m], acc[j][m]);
+                for (int c = 0; c < DP / 4; ++c) {
+                  const float4 t = reinterpret_cast<const float4*>(gsub + (size_t)(j * wc + w) * DP)[c];
+                  gv[4 * c] = t.x, gv[4 * c + 1] = t.y, gv[4 * c + 2] = t.z, gv[4 * c + 3] = t.w;
+                }
+              }
+#pragma unroll
+              for (int m = 0; m < D; ++m) acc[j][m] = fmaf(wv, gv[m], acc[j][m]);
+            }
           }
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
@@ -286,8 +299,9 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
       any = true;
       const int mi = plan->mul_in[p], mo = plan->mul_out[p];
       const int nb = d >= 5 ? 4 : 8, lanes_u = mi >= 256 ? 256 : mi;
-      const size_t per_col = ((size_t)mi + (size_t)nb * (256 / lanes_u) * d) * sizeof(float);
-      int fit = (int)((budget - (size_t)mi * sizeof(float)) / per_col);
+      const int dp = d == 1 ? 1 : (d == 3 ? 4 : 8);
+      const size_t per_col = ((size_t)mi + (size_t)nb * (256 / lanes_u) * dp) * sizeof(float);
+      int fit = (int)((budget - (size_t)(mi + 4) * sizeof(float)) / per_col);
       if (fit >= mo) fit = mo;
       else fit = fit / 32 * 32;
       if (fit < 1) return PML_ERR_UNSUPPORTED;
@@ -300,7 +314,8 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
       const int mi = plan->mul_in[p], mo = plan->mul_out[p];
       const int nb = d >= 5 ? 4 : 8, lanes_u = mi >= 256 ? 256 : mi;
       const int w = wc < mo ? wc : mo;
-      const size_t need = ((size_t)mi * (w | 1) + (size_t)nb * (256 / lanes_u) * w * d) * sizeof(float);
+      const int dp = d == 1 ? 1 : (d == 3 ? 4 : 8);
+      const size_t need = ((((size_t)mi * (w | 1) + 3) & ~(size_t)3) + (size_t)nb * (256 / lanes_u) * w * dp) * sizeof(float);
       if (need > smem[d]) smem[d] = need;
     }
   }
