@@ -160,6 +160,38 @@ def test_tp_pipelined_matches_streaming(cuda, node_irreps, lmax, C, N, deg):
     assert _rel(res[0][1][1], res[1][1][1]) < 1e-5  # dY
 
 
+@pytest.mark.parametrize("E", [0, 1, 5])
+def test_tp_scatter_degenerate_graphs(cuda, E):
+    """no edges at all / a single edge / fewer edges than persistent CTAs: every node row is still written (zeros for
+    nodes that receive nothing) and the cotangents have the right shapes and values"""
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import TPPlan
+
+    g = torch.Generator().manual_seed(5)
+    N, C, lmax = 9, 32, 2
+    tp_ref, target = _ref_tp("32x0e+32x1o", lmax, C)
+    tp_ref = tp_ref.to(cuda)
+    plan = TPPlan("32x0e+32x1o", lmax, str(target))
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)]).to(cuda)
+    h = torch.randn(N, 4 * C, generator=g).to(cuda).requires_grad_(True)
+    Y = torch.randn(E, 9, generator=g).to(cuda).requires_grad_(True)
+    R = torch.randn(E, plan.NP * C, generator=g).to(cuda).requires_grad_(True)
+    ep = ops.EdgePlan(ei, N)
+    out = ops.tp_scatter(h, Y, R, ep.gather, ep.rowptr, ep.perm, plan.handle)
+    m = tp_ref(h[ei[0]], Y, R)
+    ref = torch.zeros(N, out.shape[1], device=cuda).index_add_(0, ei[1], m)
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert (out - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    w = torch.randn(out.shape, generator=g).to(cuda)
+    gs = torch.autograd.grad([out], [h, Y, R], [w])
+    gr = torch.autograd.grad([ref], [h, Y, R], [w], allow_unused=True)
+    for a, b in zip(gs, gr):
+        b = torch.zeros_like(a) if b is None else b
+        assert a.shape == b.shape
+        if a.numel():
+            assert (a - b).abs().max() <= 1e-5 * max(1.0, b.abs().max().item())
+
+
 def test_tp_scatter_grouped_edges(cuda):
     """perm=None fast path (edges already grouped by receiver)"""
     from physicsml_b200 import ops
