@@ -26,6 +26,7 @@ CASES = [  # name, node irreps, lmax, C, N, mean degree
     ("cfg2 L1", "128x0e+128x1o", 3, 128, 1304, 32),
     ("cfg4 L0", "128x0e", 3, 128, 24000, 85),
     ("cfg4 L1", "128x0e+128x1o", 3, 128, 24000, 85),
+    ("cfg5 L1", "256x0e+256x1o+256x2e", 3, 256, 1600, 42),  # MACE large, 8 cells of ~200 atoms per GPU
 ]
 
 
