@@ -345,7 +345,7 @@ def main() -> None:
         "metric": METRIC, "value": total_atoms / (ms_dev * 1e-3), "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": "training: fwd + forces(create_graph) + MSE(E)+MSE(F) + bwd + allreduce + Adam(amsgrad)",
+        "config": {"workload": WORKLOAD, "step": "training: fwd + forces(create_graph) + MSE(E)+MSE(F) + bwd + allreduce + Adam(amsgrad, fused kernel)",
                    "molecules_per_gpu": 32, "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "parallelism": f"dp{world}",
                    "l2": "flushed between steps (256 MiB memset outside the per-step event pair)"},
         "e2e": {"value": total_atoms / (ms_e2e * 1e-3), "unit": "atoms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -160,6 +160,26 @@ typedef struct {
 int pml_gate(const float* x, const float* dy, const float* v, const pml_gate_plan* plan, int mode, float* out0,
              float* out1, int N, pml_stream_t stream);
 
+/* ---- fused Adam (amsgrad, L2 weight decay) over all parameter tensors -------------------------------
+ * Replaces torch.optim.Adam(..., amsgrad=True) as configured by the reference (models/mace/supervised/
+ * default_configs.py:25-33).  tensors / chunks are DEVICE tables (chunks of 4096 elements); step is a device scalar that
+ * the call increments before applying the update. */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* vmax;
+  long long n;
+} pml_adam_tensor;
+typedef struct {
+  int tensor;
+  int pad;
+  long long offset;
+} pml_adam_chunk;
+int pml_adam_amsgrad(const pml_adam_tensor* tensors, const pml_adam_chunk* chunks, int nchunks, float* step, float lr,
+                     float b1, float b2, float one_minus_b1, float one_minus_b2, float eps, float wd, pml_stream_t stream);
+
 /* Test utility: overwrite the shared memory of every SM with NaN (exposes kernels that read shared memory they never
  * wrote). */
 int pml_debug_poison_smem(pml_stream_t stream);

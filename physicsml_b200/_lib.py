@@ -112,6 +112,7 @@ SIGNATURES = {
     "pml_act": [_P, _P, _P, _F, _I, _I, _P, _LL, _P],
     "pml_gate": [_P, _P, _P, C.POINTER(GatePlanStruct), _I, _P, _P, _I, _P],
     "pml_debug_poison_smem": [_P],
+    "pml_adam_amsgrad": [_P, _P, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P],
     "pml_pool_sum": [_P, _P, _P, _I, _I, _P],
     "pml_pool_gather": [_P, _P, _P, _I, _I, _P],
     "pml_csr_rowptr": [_P, _P, _P, _I, _I, _P],

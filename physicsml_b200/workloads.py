@@ -110,6 +110,12 @@ def training_loss(model, data: dict, targets: dict) -> torch.Tensor:
 
 
 def make_optimizer(model, capturable: bool = False):
-    """reference default: Adam(lr=1e-2, amsgrad=True, weight_decay=5e-7) (mace/supervised/default_configs.py:25-33)"""
+    """reference default: Adam(lr=1e-2, amsgrad=True, weight_decay=5e-7) (mace/supervised/default_configs.py:25-33).
+    CUDA parameters get the fused single-kernel implementation of the same update rule (physicsml_b200.optim.FusedAdam,
+    always graph-capturable); CPU parameters (the oracle / reference arm) get torch.optim.Adam."""
     params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
+    if params and params[0].is_cuda:
+        from .optim import FusedAdam
+
+        return FusedAdam(params, lr=1e-2, weight_decay=5e-7, amsgrad=True)
     return torch.optim.Adam(params, lr=1e-2, amsgrad=True, weight_decay=5e-7, capturable=capturable)
