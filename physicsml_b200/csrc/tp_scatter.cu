@@ -346,7 +346,7 @@ struct PipeProducer {
       tile_bounds(ftile + ts.G, nq, nq_hi);
     }
     e = 0, s = 0, cnt = 0;
-    if (ftile >= ts.ntiles) return;
+    if (fq >= fq_hi) return;
     cnt = min(32, fq_hi - fq);
     if (lane < cnt) {
       const int q = fq + lane;
@@ -360,6 +360,14 @@ struct PipeProducer {
     ftile = blockIdx.x;
     tile_bounds(ftile, fq, fq_hi);
     tile_bounds(ftile + ts.G, nq, nq_hi);
+    fetch(lane, e_cur, s_cur, cnt_cur);
+    fetch(lane, e_nxt, s_nxt, cnt_nxt);
+  }
+  // one contiguous edge range instead of tiles (cotangent pass)
+  __device__ __forceinline__ void start_range(int lane, int q_lo, int q_hi) {
+    issued = 0, pos = 0, stage = 0, phase = 0;
+    ftile = ts.ntiles;
+    fq = q_lo, fq_hi = q_hi, nq = 0, nq_hi = 0;
     fetch(lane, e_cur, s_cur, cnt_cur);
     fetch(lane, e_nxt, s_nxt, cnt_nxt);
   }
@@ -426,15 +434,24 @@ __device__ __forceinline__ void load_y2_smem(const float* ys, float2 (&Yv)[NSH])
 // blockDim.x = 32*ceil(C/64) consumer threads: two channels each, packed fp32x2 arithmetic.  The copies are issued by
 // a dedicated extra warp (DEDICATED: the ring is refilled the moment a slot is released, independent of anybody's
 // arithmetic) or by warp 0 between its own edges (no extra warp: a third more CTAs fit when registers bound occupancy).
-#define PML_PIPE_PROLOGUE(LOAD_R_)                                                                                     \
+#define PML_PIPE_PROLOGUE(LOAD_R_, RANGED_)                                                                                     \
   extern __shared__ __align__(128) unsigned char smem_raw[];                                                           \
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                                                              \
   uint64_t* empty = full + kPipeMaxStages;                                                                             \
   float* stages = reinterpret_cast<float*>(smem_raw + kPipeHeaderBytes);                                               \
   const int nthr_c = blockDim.x - (DEDICATED ? 32 : 0);                                                                \
   const int consumer_warps = nthr_c >> 5;                                                                              \
-  const TileSched ts = tile_schedule(rowptr, N);                                                                       \
-  if ((int)blockIdx.x >= ts.G) return;                                                                                 \
+  TileSched ts;                                                                                                        \
+  int q_lo = 0, q_hi = 0;                                                                                              \
+  if (RANGED_) { /* even split of the edge list, walked from the end like the tiles */                                 \
+    const long long E_ = __ldg(rowptr + N), b_ = (long long)gridDim.x - 1 - blockIdx.x;                                \
+    q_lo = (int)(E_ * b_ / gridDim.x), q_hi = (int)(E_ * (b_ + 1) / gridDim.x);                                        \
+    ts.TN = 1, ts.ntiles = 0, ts.G = (int)gridDim.x;                                                                   \
+    if (q_lo >= q_hi) return;                                                                                          \
+  } else {                                                                                                             \
+    ts = tile_schedule(rowptr, N);                                                                                     \
+    if ((int)blockIdx.x >= ts.G) return;                                                                               \
+  }                                                                                                                    \
   pipe_init(full, empty, nstage, consumer_warps);                                                                      \
   __syncthreads();                                                                                                     \
   const int lane = threadIdx.x & 31;                                                                                   \
@@ -443,12 +460,12 @@ __device__ __forceinline__ void load_y2_smem(const float* ys, float2 (&Yv)[NSH])
   prod.h = h, prod.Y = Y, prod.R = R, prod.gather = gather, prod.perm = perm, prod.rowptr = rowptr;                    \
   prod.stages = stages, prod.full = full, prod.empty = empty, prod.N = N, prod.C = C, prod.nstage = nstage, prod.ts = ts; \
   if (DEDICATED && (int)threadIdx.x >= nthr_c) {                                                                       \
-    prod.start(lane);                                                                                                  \
+    if (RANGED_) prod.start_range(lane, q_lo, q_hi); else prod.start(lane);                                                                                               \
     while (!prod.done()) prod.issue(1 << 30, 0, 1 << 30, true, lane);                                                  \
     return;                                                                                                            \
   }                                                                                                                    \
   if (is_producer) {                                                                                                   \
-    prod.start(lane);                                                                                                  \
+    if (RANGED_) prod.start_range(lane, q_lo, q_hi); else prod.start(lane);                                                                                               \
     prod.issue(nstage, 0, nstage, true, lane);                                                                         \
   }                                                                                                                    \
   const int u = 2 * threadIdx.x; /* channels (u, u+1) */                                                               \
@@ -464,7 +481,7 @@ __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __r
                                    const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage) {
   using T = TPCode<ID>;
   using L = PipeLayout<ID>;
-  PML_PIPE_PROLOGUE(true)
+  PML_PIPE_PROLOGUE(true, false)
   for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
     const int n0 = ts.first_node(tile), n1 = min(N, n0 + ts.TN);
     int q = __ldg(rowptr + n0);
@@ -507,15 +524,25 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
   using T = TPCode<ID>;
   using L = PipeLayout<ID>;
   constexpr int NV = next_pow2(T::NSH);
-  PML_PIPE_PROLOGUE((WANT_H || WANT_Y))
+  PML_PIPE_PROLOGUE((WANT_H || WANT_Y), true)
   const size_t rstride = (size_t)rfl, hstride = (size_t)hfl;
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-  for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
-    const int n0 = ts.first_node(tile), n1 = min(N, n0 + ts.TN);
-    int q = __ldg(rowptr + n0);
-    int end = __ldg(rowptr + n0 + 1);
-    for (int n = n0; n < n1; ++n) {
-      const int end_next = (n + 2 <= N) ? __ldg(rowptr + n + 2) : end;
+  // The cotangent pass has no per-node output (dR, dY are per edge, dh is accumulated atomically), so a node's edges
+  // may be split between CTAs: every CTA gets the same number of edges whatever the node degrees are.
+  int n;  // node holding edge q_lo: rowptr[n] <= q_lo < rowptr[n + 1]
+  {
+    int lo = 0, hi = N;  // smallest m in (lo, hi] with rowptr[m] > q_lo
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(rowptr + mid) > q_lo) hi = mid; else lo = mid;
+    }
+    n = hi - 1;
+  }
+  {
+    int q = q_lo;
+    int end = min(__ldg(rowptr + n + 1), q_hi);
+    for (;; ++n) {
+      const int end_next = (n + 2 <= N) ? min(__ldg(rowptr + n + 2), q_hi) : q_hi;
       float2 gv[T::DOUT];
       if (q < end) {
         T::load_out2(g + (size_t)n * T::DOUT * C, C, uc, gv);
@@ -573,6 +600,7 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
           }
         }
       }
+      if (q >= q_hi) break;
       end = end_next;
     }
   }
