@@ -320,8 +320,10 @@ class SymSpec:
         self.outs = tuple((int(l), int(p)) for l, p in outs)
         self.corr = int(corr)
         self.S = (lmax + 1) ** 2
-        # number of weight rows k per (out, nu)
-        self.K = [[so3.u_matrix(self.coupling, o, nu).shape[-1] for nu in range(1, corr + 1)] for o in self.outs]
+        # weight rows per (out, nu): K_full as in the reference's parameters, K after the basis reduction of the
+        # symmetrised polynomials (so3.reduced_contraction) - the kernels see W' = B^T W with K rows
+        self.K_full = [[so3.u_matrix(self.coupling, o, nu).shape[-1] for nu in range(1, corr + 1)] for o in self.outs]
+        self.K = [[so3.reduced_contraction(self.coupling, o, nu)[1].shape[1] for nu in range(1, corr + 1)] for o in self.outs]
         self.d_out = sum(2 * l + 1 for l, _ in self.outs)
 
     @property
@@ -383,7 +385,8 @@ def _emit_sym(spec: SymSpec, ident: int) -> str:
         L.append("  }")
 
     # gather all monomials: per out index a, per nu: dict (k, M, idx) -> coef
-    monos = [[so3.contraction_monomials(spec.coupling, o, nu) for nu in range(1, corr + 1)] for o in spec.outs]
+    # (k indexes the reduced weight rows W' = B^T W, see so3.reduced_contraction)
+    monos = [[so3.reduced_contraction(spec.coupling, o, nu)[0] for nu in range(1, corr + 1)] for o in spec.outs]
 
     # ---------------- forward
     L.append("  // out[M] per output irrep, concatenated: out[off_a + M]")
@@ -401,6 +404,7 @@ def _emit_sym(spec: SymSpec, ident: int) -> str:
                     expr = " + ".join(f"{_f(c)} * ({_mono_expr(idx)})" for idx, c in byk[k][M])
                     L.append(f"      out[{off + M}] = fmaf(w, {expr}, out[{off + M}]);")
                 L.append("    }")
+                L.append("    PML_SYM_SYNC")
         off += 2 * lo + 1
     L.append("  }")
 
@@ -437,6 +441,7 @@ def _emit_sym(spec: SymSpec, ident: int) -> str:
                     )
                     L.append(f"      dx[{j}] += {expr};")
                 L.append("    }")
+                L.append("    PML_SYM_SYNC")
         off += 2 * lo + 1
     L.append("  }")
 
@@ -485,6 +490,7 @@ def _emit_sym(spec: SymSpec, ident: int) -> str:
                         )
                         L.append(f"      ddx[{j}] += {expr};")
                 L.append("    }")
+                L.append("    PML_SYM_SYNC")
         off += 2 * lo + 1
     L.append("  }")
     L.append("};")
@@ -509,7 +515,7 @@ def generate(out_dir: str = GEN_DIR) -> dict:
     parts = ["// GENERATED by physicsml_b200/codegen.py — do not edit.", "#pragma once", "template <int ID> struct SymCode;"]
     for ident, spec in enumerate(sym_specs):
         parts.append(_emit_sym(spec, ident))
-        registry["sym"][spec.key] = {"id": ident, "S": spec.S, "dout": spec.d_out, "K": spec.K, "outs": list(spec.outs)}
+        registry["sym"][spec.key] = {"id": ident, "S": spec.S, "dout": spec.d_out, "K": spec.K, "K_full": spec.K_full, "outs": list(spec.outs)}
     _write_if_changed(os.path.join(out_dir, "sym_gen.cuh"), "\n".join(parts) + "\n")
 
     ids = [

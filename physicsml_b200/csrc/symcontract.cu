@@ -8,6 +8,17 @@
 //
 // Compiled once per contraction signature: -DPML_SYM_ID=<id>.
 #include "pml_common.cuh"
+
+// The generated bodies are straight-line code of 4 k (fwd) to 30 k (dbl) instructions, far beyond the instruction
+// caches (ncu: stall_no_instruction 8.5 cycles per issue, issue slots 15-33 % busy).  One CTA per SM whose warps
+// re-converge at a barrier after every weight keeps all warps of the SM inside the same few cache lines, so the
+// instruction stream is fetched once per SM instead of once per warp.
+#ifndef PML_SYM_BLOCK
+#define PML_SYM_BLOCK 256
+#endif
+#ifndef PML_SYM_SYNC
+#define PML_SYM_SYNC __syncthreads();
+#endif
 #include "gen/sym_gen.cuh"
 
 #ifndef PML_SYM_ID
@@ -88,11 +99,13 @@ struct WGrad {
 };
 
 template <int ID>
-__global__ void __launch_bounds__(128) sym_fwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
+__global__ void __launch_bounds__(PML_SYM_BLOCK) sym_fwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
                                                       pml_sym_weights W, float* __restrict__ out, int N, int C, int Z) {
   using T = SymCode<ID>;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * C) return;
+  // no early exit: every thread of the CTA takes part in the barriers of the generated body
+  const long long tot = (long long)N * C, idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx_raw < tot;
+  const long long idx = active ? idx_raw : tot - 1;
   const int b = (int)(idx / C), c = (int)(idx - (long long)b * C);
   float xv[T::S], o[T::DOUT];
 #pragma unroll
@@ -102,16 +115,18 @@ __global__ void __launch_bounds__(128) sym_fwd_kernel(const float* __restrict__ 
   const NodeElem el(attrs, b, Z);
   const WLoad wl{W, el, C, c};
   T::fwd(xv, wl, o);
-  T::store_out(out + (size_t)b * T::DOUT * C, C, c, o);
+  if (active) T::store_out(out + (size_t)b * T::DOUT * C, C, c, o);
 }
 
 template <int ID, bool WANT_W>
-__global__ void __launch_bounds__(128) sym_bwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
+__global__ void __launch_bounds__(PML_SYM_BLOCK) sym_bwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
                                                       pml_sym_weights W, const float* __restrict__ g,
                                                       float* __restrict__ dx, int N, int C, int Z) {
   using T = SymCode<ID>;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * C) return;
+  // no early exit: every thread of the CTA takes part in the barriers of the generated body
+  const long long tot = (long long)N * C, idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx_raw < tot;
+  const long long idx = active ? idx_raw : tot - 1;
   const int b = (int)(idx / C), c = (int)(idx - (long long)b * C);
   float xv[T::S], gv[T::DOUT], d[T::S];
 #pragma unroll
@@ -122,9 +137,9 @@ __global__ void __launch_bounds__(128) sym_bwd_kernel(const float* __restrict__ 
   T::load_out(g + (size_t)b * T::DOUT * C, C, c, gv);
   const NodeElem el(attrs, b, Z);
   const WLoad wl{W, el, C, c};
-  const WGrad wg{W, el, C, c, true};
+  const WGrad wg{W, el, C, c, active};
   T::template bwd<WANT_W>(xv, wl, gv, d, wg);
-  if (dx != nullptr) {
+  if (dx != nullptr && active) {
 #pragma unroll
     for (int i = 0; i < T::S; ++i) dx[(size_t)idx * T::S + i] = d[i];
   }
@@ -134,13 +149,15 @@ __global__ void __launch_bounds__(128) sym_bwd_kernel(const float* __restrict__ 
 // weight cotangent that the double-backward pass of force-matching training needs (reference computes it through
 // generic autograd over the einsum graph; lightning/module.py:39-40 sets create_graph=True).
 template <int ID, bool WANT_W>
-__global__ void __launch_bounds__(128) sym_dbl_kernel(const float* __restrict__ x, const float* __restrict__ v,
+__global__ void __launch_bounds__(PML_SYM_BLOCK) sym_dbl_kernel(const float* __restrict__ x, const float* __restrict__ v,
                                                       const float* __restrict__ attrs, pml_sym_weights W,
                                                       const float* __restrict__ g, float* __restrict__ dg,
                                                       float* __restrict__ ddx, int N, int C, int Z) {
   using T = SymCode<ID>;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * C) return;
+  // no early exit: every thread of the CTA takes part in the barriers of the generated body
+  const long long tot = (long long)N * C, idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx_raw < tot;
+  const long long idx = active ? idx_raw : tot - 1;
   const int b = (int)(idx / C), c = (int)(idx - (long long)b * C);
   float xv[T::S], vv[T::S], gv[T::DOUT], o[T::DOUT], d[T::S];
 #pragma unroll
@@ -154,10 +171,10 @@ __global__ void __launch_bounds__(128) sym_dbl_kernel(const float* __restrict__ 
   T::load_out(g + (size_t)b * T::DOUT * C, C, c, gv);
   const NodeElem el(attrs, b, Z);
   const WLoad wl{W, el, C, c};
-  const WGrad wg{W, el, C, c, true};
+  const WGrad wg{W, el, C, c, active};
   T::template dbl<WANT_W>(xv, vv, wl, gv, o, d, wg);
-  if (dg != nullptr) T::store_out(dg + (size_t)b * T::DOUT * C, C, c, o);
-  if (ddx != nullptr) {
+  if (dg != nullptr && active) T::store_out(dg + (size_t)b * T::DOUT * C, C, c, o);
+  if (ddx != nullptr && active) {
 #pragma unroll
     for (int i = 0; i < T::S; ++i) ddx[(size_t)idx * T::S + i] = d[i];
   }
@@ -179,7 +196,7 @@ extern "C" int PML_CAT(pml_sym_fwd_launch_, PML_SYM_ID)(const float* x, const fl
                                                          float* out, int N, int C, int Z, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
   const long long tot = (long long)N * C;
-  pml::sym_fwd_kernel<PML_SYM_ID><<<pml::ceil_div(tot, 128), 128, 0, stream>>>(x, attrs, *W, out, N, C, Z);
+  pml::sym_fwd_kernel<PML_SYM_ID><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, attrs, *W, out, N, C, Z);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -191,9 +208,9 @@ extern "C" int PML_CAT(pml_sym_bwd_launch_, PML_SYM_ID)(const float* x, const fl
   if (N <= 0) return PML_OK;
   const long long tot = (long long)N * C;
   if (pml_sym_has_gw(*W))
-    pml::sym_bwd_kernel<PML_SYM_ID, true><<<pml::ceil_div(tot, 128), 128, 0, stream>>>(x, attrs, *W, g, dx, N, C, Z);
+    pml::sym_bwd_kernel<PML_SYM_ID, true><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, attrs, *W, g, dx, N, C, Z);
   else
-    pml::sym_bwd_kernel<PML_SYM_ID, false><<<pml::ceil_div(tot, 128), 128, 0, stream>>>(x, attrs, *W, g, dx, N, C, Z);
+    pml::sym_bwd_kernel<PML_SYM_ID, false><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, attrs, *W, g, dx, N, C, Z);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -204,9 +221,9 @@ extern "C" int PML_CAT(pml_sym_dbl_launch_, PML_SYM_ID)(const float* x, const fl
   if (N <= 0) return PML_OK;
   const long long tot = (long long)N * C;
   if (pml_sym_has_gw(*W))
-    pml::sym_dbl_kernel<PML_SYM_ID, true><<<pml::ceil_div(tot, 128), 128, 0, stream>>>(x, v, attrs, *W, g, dg, ddx, N, C, Z);
+    pml::sym_dbl_kernel<PML_SYM_ID, true><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, v, attrs, *W, g, dg, ddx, N, C, Z);
   else
-    pml::sym_dbl_kernel<PML_SYM_ID, false><<<pml::ceil_div(tot, 128), 128, 0, stream>>>(x, v, attrs, *W, g, dg, ddx, N, C, Z);
+    pml::sym_dbl_kernel<PML_SYM_ID, false><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, v, attrs, *W, g, dg, ddx, N, C, Z);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

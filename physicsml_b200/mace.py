@@ -205,7 +205,7 @@ class SymmetricContraction(torch.nn.Module):
         )
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        ws = [w for c in self.contractions for w in c.by_nu()]
+        ws = self.plan.reduce_weights([w for c in self.contractions for w in c.by_nu()])
         return ops.sym_contract(x, y, ws, self.plan.handle)
 
 

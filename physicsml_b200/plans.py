@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 
+import numpy as np
 import torch
 
 from . import _lib, so3
@@ -254,10 +255,27 @@ class SymPlan:
                 "physicsml_b200.codegen.default_sym_specs() and rebuild"
             )
         self.spec_id = reg[self.spec.key]["id"]
-        self.K = self.spec.K  # [out][nu-1]
+        self.K = self.spec.K  # [out][nu-1], rows of the reduced weights the kernels read
+        self.K_full = self.spec.K_full  # rows of the reference's parameters
+        self._B = {}  # device -> list of [K_full, K] matrices (None where the reduction is the identity)
         self.S, self.DOUT, self.C, self.Z, self.corr = self.spec.S, self.spec.d_out, channels, num_elements, corr
         self.n_out = len(self.spec.outs)
         self.handle = register(self)
+
+    def reduce_weights(self, weights):
+        """reference parameters [Z, K_full, C] (flat list ordered (out a, nu)) -> W' = B^T W [Z, K, C]: the polynomials
+        the K_full rows multiply are linearly dependent (so3.reduced_contraction); plain differentiable torch ops, so
+        gradients reach the parameters through autograd."""
+        dev = weights[0].device
+        if dev not in self._B:
+            mats = []
+            for a, o in enumerate(self.spec.outs):
+                for nu in range(1, self.corr + 1):
+                    B = so3.reduced_contraction(self.spec.coupling, o, nu)[1]
+                    ident = B.shape[0] == B.shape[1] and np.array_equal(B, np.eye(B.shape[0]))
+                    mats.append(None if ident else torch.tensor(B.T.copy(), dtype=torch.float32, device=dev))
+            self._B[dev] = mats
+        return [w if Bt is None else torch.matmul(Bt, w) for w, Bt in zip(weights, self._B[dev])]
 
     def weight_struct(self, weights, grads=None):
         """weights: flat list ordered (out a, nu = 1..corr)."""

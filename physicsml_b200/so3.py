@@ -305,3 +305,48 @@ def contraction_monomials(coupling: tuple, out: tuple, nu: int, tol: float = 1e-
                 if abs(c) > tol:
                     res[(k, M, idx)] = float(c)
     return res
+
+
+@functools.lru_cache(maxsize=None)
+def reduced_contraction(coupling: tuple, out: tuple, nu: int, tol: float = 1e-9):
+    """The K weight rows of one (output irrep, degree nu) of the symmetric contraction multiply K polynomials
+    P_k[M](x) that are far from independent once the generalised-CG tensor is symmetrised over its nu feature axes
+    (lmax 3, 1o, nu 3: 51 rows, rank 12).  Pick J = rank independent rows (sparsest first) and write every row in
+    that basis, P_k = sum_j B[k, j] P_sel[j]; then
+
+        out_M = sum_k W_k P_k[M](x) = sum_j W'_j P_sel[j][M](x),     W' = B^T W   (a tiny matrix product on the weights)
+
+    so the kernels evaluate J instead of K polynomials (about a quarter of the monomial terms).
+    Returns (monomials {(j, M, idx): coef} of the basis rows, B as a [K, J] float64 array, sel)."""
+    monos = contraction_monomials(coupling, out, nu)
+    K = u_matrix(coupling, out, nu).shape[-1]
+    cols = sorted({(M, idx) for (_, M, idx) in monos})
+    col_of = {c: i for i, c in enumerate(cols)}
+    A = np.zeros((K, len(cols)))
+    for (k, M, idx), c in monos.items():
+        A[k, col_of[(M, idx)]] = c
+    nnz = (np.abs(A) > 0).sum(axis=1)
+    order = sorted(range(K), key=lambda k: (nnz[k], k))
+    sel, basis = [], []  # chosen rows and their orthonormalised copies (modified Gram-Schmidt rank test)
+    for k in order:
+        if nnz[k] == 0:
+            continue
+        r = A[k].copy()
+        for q in basis:
+            r -= (r @ q) * q
+        if np.linalg.norm(r) > tol * max(1.0, np.linalg.norm(A[k])):
+            sel.append(k)
+            basis.append(r / np.linalg.norm(r))
+    sel.sort()  # a full-rank set reduces to the identity
+    J = len(sel)
+    if J == 0:
+        return {}, np.zeros((K, 0)), ()
+    B = np.linalg.lstsq(A[sel].T, A.T, rcond=None)[0].T  # A = B @ A[sel]
+    if np.abs(B @ A[sel] - A).max() > 1e-10:
+        raise AssertionError("basis reduction of the contraction polynomials is not exact")
+    B[np.abs(B) < 1e-12] = 0.0
+    for j, k in enumerate(sel):
+        B[k] = 0.0
+        B[k, j] = 1.0
+    red = {(j, M, idx): c for j, k in enumerate(sel) for (kk, M, idx), c in monos.items() if kk == k}
+    return red, B, tuple(sel)
