@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(PML_SYM_BLOCK) sym_fwd_kernel(const float* __r
 }
 
 template <int ID, bool WANT_W>
-__global__ void __launch_bounds__(PML_SYM_BLOCK) sym_bwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
+__global__ void __launch_bounds__(PML_SYM_BLOCK, 3) sym_bwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
                                                       pml_sym_weights W, const float* __restrict__ g,
                                                       float* __restrict__ dx, int N, int C, int Z) {
   using T = SymCode<ID>;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(PML_SYM_BLOCK) sym_bwd_kernel(const float* __r
 // weight cotangent that the double-backward pass of force-matching training needs (reference computes it through
 // generic autograd over the einsum graph; lightning/module.py:39-40 sets create_graph=True).
 template <int ID, bool WANT_W>
-__global__ void __launch_bounds__(PML_SYM_BLOCK) sym_dbl_kernel(const float* __restrict__ x, const float* __restrict__ v,
+__global__ void __launch_bounds__(PML_SYM_BLOCK, 3) sym_dbl_kernel(const float* __restrict__ x, const float* __restrict__ v,
                                                       const float* __restrict__ attrs, pml_sym_weights W,
                                                       const float* __restrict__ g, float* __restrict__ dg,
                                                       float* __restrict__ ddx, int N, int C, int Z) {

@@ -331,10 +331,35 @@ def _gemm(name: str, a, b, c, table, nprob: int, m_runtime: int, max_m: int, max
         _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, _stream())
 
 
-def _splitk_for(k_extent: int, ctas_without_split: int) -> int:
-    """split the reduction so that ~4 CTAs per SM are in flight, keeping >= 4 k-tiles (of 16) per CTA"""
-    want = (4 * 148 + ctas_without_split - 1) // max(1, ctas_without_split)
+_SMS = 148
+
+
+def _tc_slots(bn: int, promote: bool) -> int:
+    """CTAs of gemm_grouped_tc_kernel<bn, promote> resident on the GPU (registers bound it: 96-126 registers x 256
+    threads -> 2 per SM; the 80-register non-promoting BN <= 64 variants -> 3 per SM)"""
+    return _SMS * (2 if (promote or bn >= 128) else 3)
+
+
+def _splitk_for(k_extent: int, ctas_without_split: int, slots: int = 4 * _SMS) -> int:
+    """split the reduction so that the grid fills `slots` CTAs without spilling into a nearly empty extra wave
+    (floor, not ceil: 10 tiles x 60 splits = 600 CTAs on 592 slots ran three rounds instead of two), keeping >= 4
+    k-tiles (of 16) per CTA"""
+    want = slots // max(1, ctas_without_split)
     return max(1, min(want, max(1, k_extent // 64), 4096))
+
+
+def _splitk_rows(tiles: int, k_extent: int, slots: int) -> int:
+    """split-K for a row-tiled GEMM with a long reduction (dx of the wide radial layer: 325 row tiles on 296 slots
+    = two rounds, the second one 10 % full).  Cost model: rounds x (k-blocks x 1.1 us + epilogue)."""
+    best, best_cost = 1, None
+    for sk in range(1, 9):
+        if sk > 1 and k_extent // sk < 128:
+            break
+        rounds = (tiles * sk + slots - 1) // slots
+        cost = rounds * (k_extent / (16.0 * sk) * 1.1 + (5.0 if sk > 1 else 3.0))
+        if best_cost is None or cost < 0.95 * best_cost:
+            best, best_cost = sk, cost
+    return best
 
 
 @torch.library.custom_op(f"{NS}::irrep_linear", mutates_args=(), device_types="cuda")
@@ -370,10 +395,17 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
     pl = plans.get(plan)
     g, w = _f32c(g), _f32c(w)
     n = g.shape[0]
-    dx = g.new_zeros(n, pl.d_in) if pl.has_unfed_input else _new_empty(g, n, pl.d_in)
+    name = _gemm_name(n)
+    sk = 1
+    if name.endswith("_tc") and pl.max_k_bwd_x >= 256:
+        bn = 32 if pl.max_mul_in <= 32 else 64
+        tiles = ((n + 127) // 128) * ((pl.max_mul_in + bn - 1) // bn) * len(pl._bwd_x) * pl.max_d
+        sk = _splitk_rows(tiles, pl.max_k_bwd_x, _tc_slots(bn, True))
+    dx = g.new_zeros(n, pl.d_in) if (pl.has_unfed_input or sk > 1) else _new_empty(g, n, pl.d_in)
     _, bx, _ = pl.tables(g.device)
     if bx is not None and n > 0:
-        _gemm(_gemm_name(n), _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, 1, pl.max_k_bwd_x)
+        _gemm(name, _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, sk,
+              (pl.max_k_bwd_x + sk - 1) // sk + 16 if sk > 1 else pl.max_k_bwd_x)
     return dx
 
 
@@ -396,7 +428,8 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
             ctas = ((pl.max_mul_in + 127) // 128) * ((pl.max_mul_out + bn - 1) // bn) * len(pl._bwd_w) * pl.max_d
         else:
             ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
-        sk = _splitk_for(n, ctas)
+        sk = _splitk_for(n, ctas, 2 * _tc_slots(bn, False) if name.endswith("_tc") and bn >= 128 else
+                         (_tc_slots(bn, False) if name.endswith("_tc") else 4 * _SMS))
         k_cta = (n + sk - 1) // sk + 16
         # Weight gradients are sums over nodes / edges whose fp32 evaluation order already carries ~sqrt(n) eps; up to
         # 1024 terms per CTA they run on the plain TMEM accumulator (worst-case truncation bias 2e-5 relative, measured
