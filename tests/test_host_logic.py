@@ -84,6 +84,39 @@ def test_contraction_monomials_equal_dense_oracle():
     assert np.abs(got - want).max() < 1e-6 * max(1.0, np.abs(want).max())  # U is built in fp32 by the reference
 
 
+def test_reduced_contraction_basis_is_exact():
+    """K6 evaluates W' = B^T W on a basis of the (linearly dependent) per-weight polynomials: the reduced form must
+    reproduce the full sum  sum_k W_k P_k[M](x)  for arbitrary weights, and the registry must carry the reduced sizes."""
+    from physicsml_b200 import _lib, so3
+    from physicsml_b200.codegen import SymSpec
+
+    rng = np.random.default_rng(5)
+    lmax = 3
+    coup = tuple((l, (-1) ** l) for l in range(lmax + 1))
+    x = rng.standard_normal((lmax + 1) ** 2)
+    total_full = total_red = 0
+    for out in [(0, 1), (1, -1), (2, 1)]:
+        for nu in (1, 2, 3):
+            full = so3.contraction_monomials(coup, out, nu)
+            red, B, sel = so3.reduced_contraction(coup, out, nu)
+            K = so3.u_matrix(coup, out, nu).shape[-1]
+            assert B.shape == (K, len(sel)) and len(sel) <= K
+            W = rng.standard_normal(K)
+            Wr = B.T @ W
+            want, got = np.zeros(2 * out[0] + 1), np.zeros(2 * out[0] + 1)
+            for (k, M, idx), c in full.items():
+                want[M] += W[k] * c * np.prod(x[list(idx)])
+            for (j, M, idx), c in red.items():
+                got[M] += Wr[j] * c * np.prod(x[list(idx)])
+            assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+            total_full += len(full)
+            total_red += len(red)
+    assert total_red * 3 < total_full  # 5911 -> 1211 monomial terms at lmax 3, L <= 2
+    spec = SymSpec(3, [(0, 1), (1, -1)], 3)
+    assert spec.K_full == [[1, 4, 23], [1, 6, 51]] and spec.K == [[1, 4, 8], [1, 3, 12]]
+    assert _lib.registry()["sym"][spec.key]["K"] == spec.K
+
+
 def test_generated_registry_covers_baseline_configs():
     from physicsml_b200 import _lib, so3
 
