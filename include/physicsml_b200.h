@@ -114,6 +114,18 @@ int pml_gemm_grouped(const float* A, const float* B, float* C, const pml_gemm_pr
 int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                         int max_M, int max_N, int max_batch, int splitk, int max_k, pml_stream_t stream);
 
+/* ---- K3w: streaming kernels for the wide output layer of the radial MLP (reference blocks.py:157-160,211,
+ * interaction_block.py:61-64,85: the last nn.FullyConnectedNet layer, hidden 64 -> paths x channels).
+ * pml_wide_pack_w splits W [K <= 64, N] (element (k, n) at W[k*w_rs + n*w_cs]) into tf32 hi/lo parts laid out, per
+ * 64-column tile, as the shared-memory image the tensor core reads (pml_wide_image_floats(N) floats);
+ * pml_wide_fwd computes C[M, N] = alpha * A[M, K] @ W from that image with persistent A-stationary CTAs
+ * (TMA-fed B ring, tcgen05 3xTF32, double-buffered TMEM accumulators).  Returns PML_ERR_UNSUPPORTED (-2) for shapes
+ * outside K % 4 == 0, K <= 64, N % 64 == 0, 16-byte aligned rows: callers fall back to pml_gemm_grouped_tc. */
+long long pml_wide_image_floats(int N);
+int pml_wide_pack_w(const float* W, long long w_rs, long long w_cs, int K, int N, float* image, pml_stream_t stream);
+int pml_wide_fwd(const float* A, long long lda, int K, const float* image, float* C, long long ldc, int M, int N,
+                 float alpha, pml_stream_t stream);
+
 /* ---- K5b: element-indexed linear (FullyConnectedTensorProduct with one-hot node attributes) ------------------------
  * Replaces mix_layer / residual_connection_layer (models/mace/modules/blocks.py:183-188,72-78) and NequIP's
  * self_connection_layer (models/nequip/modules/interaction_block.py:73-82). */

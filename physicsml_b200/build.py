@@ -57,7 +57,7 @@ def build(verbose: bool = True, jobs: int | None = None) -> str:
     sym_gen = os.path.join(CSRC, "gen", "sym_gen.cuh")
     ids = os.path.join(CSRC, "gen", "pml_ids.h")
     work = []
-    for name in ("gemm", "gemm_tc", "featurise", "element_linear", "misc", "neighbour_list", "gate", "adam"):
+    for name in ("gemm", "gemm_tc", "gemm_wide", "featurise", "element_linear", "misc", "neighbour_list", "gate", "adam"):
         src = os.path.join(CSRC, name + ".cu")
         if os.path.exists(src):
             work.append((src, os.path.join(OBJ, name + ".o"), [], [common, os.path.join(CSRC, "gemm_problem.h")]))

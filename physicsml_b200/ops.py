@@ -362,12 +362,33 @@ def _splitk_rows(tiles: int, k_extent: int, slots: int) -> int:
     return best
 
 
+WIDE_MIN_ROWS = [int(os.environ.get("PML_WIDE_MIN_ROWS", "4096"))]
+
+
+def _wide_ok(pl, n: int) -> bool:
+    """the streaming kernels of csrc/gemm_wide.cu take the wide scalar layers (radial-MLP output) on edge-sized inputs"""
+    return pl.wide is not None and GEMM_MODE[0] == "tc" and n >= WIDE_MIN_ROWS[0]
+
+
+def _wide_image(w: Tensor, k: int, n: int, w_rs: int, w_cs: int) -> Tensor:
+    """tf32 hi/lo shared-memory images of W [k, n] (element (i, j) at w[i*w_rs + j*w_cs]), one per 64-column tile"""
+    image = torch.empty(((n + 63) // 64) * 2 * 64 * 64, device=w.device, dtype=torch.float32)
+    _call("pml_wide_pack_w", _p(w), w_rs, w_cs, k, n, _p(image), _stream())
+    return image
+
+
 @torch.library.custom_op(f"{NS}::irrep_linear", mutates_args=(), device_types="cuda")
 def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
     pl = plans.get(plan)
     x, w = _f32c(x), _f32c(w)
     n = x.shape[0]
     shape = (n, pl.channels, pl.S) if pl.out_layout == "channel" else (n, pl.d_out)
+    if _wide_ok(pl, n):
+        k, nn, alpha = pl.wide
+        out = _new_empty(x, shape)
+        image = _wide_image(w, k, nn, nn, 1)
+        _call("pml_wide_fwd", _p(x), k, k, _p(image), _p(out), nn, n, nn, alpha, _stream())
+        return out
     out = x.new_zeros(shape) if pl.has_unfed_output else _new_empty(x, shape)
     fwd, _, _ = pl.tables(x.device)
     if fwd is not None and n > 0:
