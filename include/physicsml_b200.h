@@ -125,6 +125,12 @@ long long pml_wide_image_floats(int N);
 int pml_wide_pack_w(const float* W, long long w_rs, long long w_cs, int K, int N, float* image, pml_stream_t stream);
 int pml_wide_fwd(const float* A, long long lda, int K, const float* image, float* C, long long ldc, int M, int N,
                  float alpha, pml_stream_t stream);
+/* dx of the same layer: dA[M, K] = alpha * G[M, N] @ W^T.  pml_wide_pack_wt writes one [64 x 32] hi/lo tile of W^T per
+ * 32-wide chunk of N (same total size as the forward image); pml_wide_bwd_x streams G through a register-prefetched
+ * shared-memory ring, promotes the TMEM accumulator into fp32 registers every 128 k.  N % 32 == 0. */
+int pml_wide_pack_wt(const float* W, long long w_rs, long long w_cs, int K, int N, float* image, pml_stream_t stream);
+int pml_wide_bwd_x(const float* G, long long ldg, int N, const float* image, float* dA, long long lda, int K, int M,
+                   float alpha, pml_stream_t stream);
 
 /* ---- K5b: element-indexed linear (FullyConnectedTensorProduct with one-hot node attributes) ------------------------
  * Replaces mix_layer / residual_connection_layer (models/mace/modules/blocks.py:183-188,72-78) and NequIP's

@@ -108,6 +108,8 @@ SIGNATURES = {
     "pml_gemm_grouped_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pml_wide_pack_w": [_P, _LL, _LL, _I, _I, _P, _P],
     "pml_wide_fwd": [_P, _LL, _I, _P, _P, _LL, _I, _I, _F, _P],
+    "pml_wide_pack_wt": [_P, _LL, _LL, _I, _I, _P, _P],
+    "pml_wide_bwd_x": [_P, _LL, _I, _P, _P, _LL, _I, _I, _F, _P],
     "pml_element_linear_fwd": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
     "pml_element_linear_bwd_x": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],
     "pml_element_linear_bwd_w": [_P, _P, _P, C.POINTER(ElPlan), _P, _I, _I, _I, _P],

@@ -71,13 +71,32 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 46;
   return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
+// One elected thread issues every MMA of the CTA, so its instruction stream is the critical path (measured: the
+// per-k-step descriptor arithmetic and predicate set-up of separate asm statements cost more than the MMAs themselves
+// take to execute).  A whole k-block of the 3xTF32 product goes out as one asm statement: the four descriptors advance
+// by 256 bytes (16 in descriptor units) per 8-wide k-step inside it.
+#define PML_MMA3(P)                                                    \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %5, " P ";\n\t"   \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %5, pt;\n\t"      \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %5, pt;\n\t"
+#define PML_ADV "add.s64 ah, ah, 16;\n\tadd.s64 al, al, 16;\n\tadd.s64 bh, bh, 16;\n\tadd.s64 bl, bl, 16;\n\t"
+#define PML_MMA_HEAD                                                                                               \
+  "{\n\t.reg .pred p, pt;\n\t.reg .b64 ah, al, bh, bl;\n\t"                                                        \
+  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"                                                           \
+  "mov.b64 ah, %1;\n\tmov.b64 al, %2;\n\tmov.b64 bh, %3;\n\tmov.b64 bl, %4;\n\t"
+// D (+)= A B over 4 / 8 k-steps; `accumulate` = 0 clears D with the very first MMA
+__device__ __forceinline__ void umma_3x_k32(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(PML_MMA_HEAD PML_MMA3("p") PML_ADV PML_MMA3("pt") PML_ADV PML_MMA3("pt") PML_ADV PML_MMA3("pt") "}"
+               ::"r"(d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void umma_3x_k64(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(PML_MMA_HEAD PML_MMA3("p") PML_ADV PML_MMA3("pt") PML_ADV PML_MMA3("pt") PML_ADV PML_MMA3("pt") PML_ADV
+               PML_MMA3("pt") PML_ADV PML_MMA3("pt") PML_ADV PML_MMA3("pt") PML_ADV PML_MMA3("pt") "}"
+               ::"r"(d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+               : "memory");
 }
 #define PML_TMEM_LD32(r, taddr)                                                                                        \
   asm volatile(                                                                                                        \
@@ -196,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) wide_fwd_kernel(const float* __res
     // ---------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t a_hi = smem_u32(S.a[0]), a_lo = smem_u32(S.a[1]);
+      const uint64_t da_hi = make_desc(smem_u32(S.a[0])), da_lo = make_desc(smem_u32(S.a[1]));
       int t = 0, it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const int ns = item % nsplit;
@@ -209,13 +228,7 @@ __global__ void __launch_bounds__(THREADS, 1) wide_fwd_kernel(const float* __res
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t b_hi = smem_u32(S.b[s]), b_lo = b_hi + TILE_FLOATS * 4;
           const uint32_t d = tmem + (uint32_t)(buf * BN);
-#pragma unroll
-          for (int kk = 0; kk < KP / 8; ++kk) {
-            const uint32_t o = kk * 256;
-            umma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, kk > 0 ? 1u : 0u);
-            umma_tf32(d, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
-            umma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
-          }
+          umma_3x_k64(d, da_hi, da_lo, make_desc(b_hi), make_desc(b_lo), IDESC, 0u);
           umma_commit(smem_u32(&S.b_empty[s]));
           umma_commit(smem_u32(&S.acc_full[buf]));
         }
@@ -307,6 +320,223 @@ __global__ void __launch_bounds__(THREADS, 1) wide_fwd_kernel(const float* __res
   }
 }
 
+
+// =====================================================================================================================
+// dx of the same layer:  dA[M, K] = alpha * G[M, N] @ W^T   (K <= 64 outputs, reduction over the wide dimension N).
+// The big operand G is now the streamed one: 8 loader warps pull 128 x 32 chunks through a register ring four chunks
+// deep (the loads of chunk c+4 are issued when chunk c is converted), split them into tf32 hi/lo and store them in the
+// UMMA layout of a 3-stage ring; W^T arrives pre-split, 16 KB per chunk, by TMA; warp 12 issues the MMAs; warps 0-3
+// own the accumulators: every 128 k the tensor core switches TMEM buffer and they add the retired one into fp32
+// registers (the tensor core truncates its running sum: see gemm_tc.cu), then write the 128 x K block.  The loaders run
+// across row-block boundaries, so the stream never drains between items.
+// =====================================================================================================================
+constexpr int XC = 32;                      // reduction chunk
+constexpr int X_A_STAGES = 3, X_B_STAGES = 4, X_PERIOD = 4;  // promotion every X_PERIOD chunks = 128 k
+constexpr int X_A_FLOATS = BM * XC, X_B_FLOATS = KP * XC;    // one hi (or lo) image: 16 KB / 8 KB
+constexpr int X_THREADS = 448;              // warps 0-3 accumulate, 4-11 load G, 12 MMA, 13 B producer
+constexpr int X_DEPTH = 4;                  // chunks of register prefetch
+
+__device__ __forceinline__ int unit32_of(int r, int kc) { return (r & 7) + 8 * kc + 64 * (r >> 3); }
+__device__ __forceinline__ uint64_t make_desc32(uint32_t saddr) {  // [rows x 32] K-major tile: LBO 128 B, SBO 1024 B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// image[c][0 = hi, 1 = lo][unit32_of(k_out, kc)] = W[k_out, 32 c + 4 kc .. + 3] split; k_out >= K zero-filled
+__global__ void pack_wt_kernel(const float* __restrict__ W, long long w_rs, long long w_cs, int K, int N,
+                               float* __restrict__ image) {
+  const int c = blockIdx.x;
+  for (int idx = threadIdx.x; idx < KP * (XC / 4); idx += blockDim.x) {
+    const int kc = idx & 7, r = idx >> 3;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = c * XC + kc * 4 + j;
+      v[j] = (r < K && n < N) ? __ldg(W + (long long)r * w_rs + (long long)n * w_cs) : 0.f;
+    }
+    float4 hi, lo;
+    split_tf32(v[0], hi.x, lo.x);
+    split_tf32(v[1], hi.y, lo.y);
+    split_tf32(v[2], hi.z, lo.z);
+    split_tf32(v[3], hi.w, lo.w);
+    float* base = image + (size_t)c * 2 * X_B_FLOATS;
+    reinterpret_cast<float4*>(base)[unit32_of(r, kc)] = hi;
+    reinterpret_cast<float4*>(base + X_B_FLOATS)[unit32_of(r, kc)] = lo;
+  }
+}
+
+struct __align__(128) BwdXSmem {
+  float a[X_A_STAGES][2 * X_A_FLOATS];  // hi, lo per stage     96 KB
+  float b[X_B_STAGES][2 * X_B_FLOATS];  // hi, lo per stage     64 KB
+  unsigned long long a_full[X_A_STAGES], a_empty[X_A_STAGES], b_full[X_B_STAGES], b_empty[X_B_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(X_THREADS, 1) wide_bwd_x_kernel(const float* __restrict__ G, long long ldg, int N,
+                                                                  const float* __restrict__ image, float* __restrict__ dA,
+                                                                  long long lda, int K, int M, float alpha) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdXSmem& S = *reinterpret_cast<BwdXSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nitems = (M + BM - 1) / BM;
+  const int nch = N / XC;
+  const int my_items = ((int)blockIdx.x < nitems) ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_items * nch;  // chunks this CTA streams
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < X_A_STAGES; ++s) {
+      mbar_init(smem_u32(&S.a_full[s]), 8);
+      mbar_init(smem_u32(&S.a_empty[s]), 1);
+    }
+    for (int s = 0; s < X_B_STAGES; ++s) {
+      mbar_init(smem_u32(&S.b_full[s]), 1);
+      mbar_init(smem_u32(&S.b_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&S.acc_full[s]), 1);
+      mbar_init(smem_u32(&S.acc_empty[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 13) {
+    // ---------------- B producer: chunk images repeat for every item
+    if (lane == 0) {
+      for (int g = 0; g < total; ++g) {
+        const int c = g % nch, s = g % X_B_STAGES;
+        mbar_wait(smem_u32(&S.b_empty[s]), ((g / X_B_STAGES) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&S.b_full[s]);
+        mbar_expect_tx(fb, 2u * X_B_FLOATS * 4u);
+        bulk_g2s(smem_u32(S.b[s]), image + (size_t)c * 2 * X_B_FLOATS, 2u * X_B_FLOATS * 4u, fb);
+      }
+    }
+  } else if (warp == 12) {
+    // ---------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int P = 0;  // accumulation periods issued so far
+      for (int g = 0; g < total; ++g) {
+        const int c = g % nch, sa = g % X_A_STAGES, sb = g % X_B_STAGES;
+        const bool opens = (c % X_PERIOD) == 0, closes = (c % X_PERIOD) == X_PERIOD - 1 || c == nch - 1;
+        const int buf = P & 1;
+        if (opens) mbar_wait(smem_u32(&S.acc_empty[buf]), ((P >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(&S.a_full[sa]), (g / X_A_STAGES) & 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // loaders' generic-proxy stores -> tensor core
+        mbar_wait(smem_u32(&S.b_full[sb]), (g / X_B_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(S.a[sa]), a_lo = a_hi + X_A_FLOATS * 4;
+        const uint32_t b_hi = smem_u32(S.b[sb]), b_lo = b_hi + X_B_FLOATS * 4;
+        const uint32_t d = tmem + (uint32_t)(buf * BN);
+        umma_3x_k32(d, make_desc32(a_hi), make_desc32(a_lo), make_desc32(b_hi), make_desc32(b_lo), IDESC, opens ? 0u : 1u);
+        umma_commit(smem_u32(&S.a_empty[sa]));
+        umma_commit(smem_u32(&S.b_empty[sb]));
+        if (closes) {
+          umma_commit(smem_u32(&S.acc_full[buf]));
+          ++P;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- G loaders: 256 threads, 4 float4 per thread and chunk
+    const int lt = tid - 128;
+    float4 q[X_DEPTH][4];
+    auto load = [&](float4 (&dst)[4], int g) {
+      if (g >= total) return;
+      const int ik = g / nch, c = g - ik * nch;
+      const int row0 = ((int)blockIdx.x + ik * (int)gridDim.x) * BM;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = lt + 256 * i;
+        const int r = (idx & 7) + 8 * (idx >> 6), kc = (idx >> 3) & 7;
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < M) dst[i] = __ldcs(reinterpret_cast<const float4*>(G + (long long)(row0 + r) * ldg + c * XC + kc * 4));
+      }
+    };
+    auto store = [&](const float4 (&src)[4], int g) {
+      const int s = g % X_A_STAGES;
+      mbar_wait(smem_u32(&S.a_empty[s]), ((g / X_A_STAGES) & 1) ^ 1);
+      float* hi_base = S.a[s];
+      float* lo_base = hi_base + X_A_FLOATS;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = lt + 256 * i;
+        const int r = (idx & 7) + 8 * (idx >> 6), kc = (idx >> 3) & 7;
+        float4 hi, lo;
+        split_tf32(src[i].x, hi.x, lo.x);
+        split_tf32(src[i].y, hi.y, lo.y);
+        split_tf32(src[i].z, hi.z, lo.z);
+        split_tf32(src[i].w, hi.w, lo.w);
+        const int u = unit32_of(r, kc);
+        reinterpret_cast<float4*>(hi_base)[u] = hi;
+        reinterpret_cast<float4*>(lo_base)[u] = lo;
+      }
+      // no proxy fence here: it would wait for the prefetch loads this thread has in flight (fence.proxy.async is a
+      // MEMBAR + FENCE.VIEW.ASYNC).  The MMA thread, which has none, fences after it has acquired a_full.
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&S.a_full[s]));
+    };
+#pragma unroll
+    for (int u = 0; u < X_DEPTH; ++u) load(q[u], u);
+    for (int g = 0; g < total; g += X_DEPTH) {
+#pragma unroll
+      for (int u = 0; u < X_DEPTH; ++u) {
+        if (g + u < total) {
+          store(q[u], g + u);
+          load(q[u], g + u + X_DEPTH);
+        }
+      }
+    }
+  } else {
+    // ---------------- warps 0-3: accumulator promotion (TMEM lane quadrant `warp`) and the output block
+    int P = 0;
+    for (int ik = 0; ik < my_items; ++ik) {
+      const int row0 = ((int)blockIdx.x + ik * (int)gridDim.x) * BM;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      const int nper = (nch + X_PERIOD - 1) / X_PERIOD;
+      for (int p = 0; p < nper; ++p, ++P) {
+        const int buf = P & 1;
+        mbar_wait(smem_u32(&S.acc_full[buf]), (P >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float v[BN];
+        tmem_ld64(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN), v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty[buf]));
+#pragma unroll
+        for (int j = 0; j < BN; ++j) acc[j] += v[j];
+      }
+      const int gr = row0 + warp * 32 + lane;
+      if (gr < M) {
+        float* orow = dA + (long long)gr * lda;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4)
+          if (j < K) *reinterpret_cast<float4*>(orow + j) = make_float4(alpha * acc[j], alpha * acc[j + 1], alpha * acc[j + 2], alpha * acc[j + 3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN) : "memory");
+  }
+}
+
 }  // namespace wide
 }  // namespace pml
 
@@ -354,6 +584,42 @@ extern "C" int pml_wide_fwd(const float* A, long long lda, int K, const float* i
   }
   const int grid = min(sms, tiles_m * nsplit);
   wide_fwd_kernel<<<grid, THREADS, smem, stream>>>(A, lda, K, image, C, ldc, M, ntiles_n, nsplit, alpha);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+// image <- packed tf32 hi/lo tiles of W^T for the dx kernel: one [64 k_out x 32 n] tile per 32-wide chunk of N
+// (2 * 64 * 32 floats per chunk: pml_wide_image_floats(N) floats in total, the same size as the forward image)
+extern "C" int pml_wide_pack_wt(const float* W, long long w_rs, long long w_cs, int K, int N, float* image,
+                                cudaStream_t stream) {
+  if (K <= 0 || K > pml::wide::KP || N <= 0 || (N % pml::wide::XC)) return PML_ERR_BAD_ARG;
+  pml::wide::pack_wt_kernel<<<N / pml::wide::XC, 256, 0, stream>>>(W, w_rs, w_cs, K, N, image);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+// dA[M, K] = alpha * G[M, N] @ W^T  (G rows ldg apart, dA rows lda apart, 16-byte aligned; K % 4 == 0, K <= 64,
+// N % 32 == 0); image from pml_wide_pack_wt
+extern "C" int pml_wide_bwd_x(const float* G, long long ldg, int N, const float* image, float* dA, long long lda, int K,
+                              int M, float alpha, cudaStream_t stream) {
+  using namespace pml::wide;
+  if (M <= 0) return PML_OK;
+  if (K <= 0 || K > KP || (K & 3) || (N % XC) || (ldg & 3) || (lda & 3) || (reinterpret_cast<uintptr_t>(G) & 15) ||
+      (reinterpret_cast<uintptr_t>(dA) & 15) || (reinterpret_cast<uintptr_t>(image) & 15))
+    return PML_ERR_UNSUPPORTED;
+  static int sms = 0;
+  static bool configured = false;
+  const int smem = (int)sizeof(BwdXSmem) + 128;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(wide_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return PML_ERR_LAUNCH;
+    configured = true;
+  }
+  const int nitems = (M + BM - 1) / BM;
+  wide_bwd_x_kernel<<<min(sms, nitems), X_THREADS, smem, stream>>>(G, ldg, N, image, dA, lda, K, M, alpha);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

@@ -255,6 +255,46 @@ def test_irrep_linear(cuda, irr_in, irr_out, layout, N):
         assert _rel(a, b) < 2e-5
 
 
+@pytest.mark.parametrize("K,N,rows", [(64, 1280, 5000), (64, 512, 4097), (64, 1280, 20033), (32, 256, 4500), (8, 320, 4100)])
+def test_wide_radial_layer_matches_fp64_and_general_kernel(cuda, K, N, rows):
+    """K3w (csrc/gemm_wide.cu): the streaming kernels that take the wide radial-MLP output layer on edge-sized inputs
+    (ragged last row block, K < 64 zero-padded, N not a multiple of 128) against fp64 and against the general grouped
+    tensor-core kernel; first and second derivatives through the op's autograd formulas."""
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import LinearPlan
+
+    g = torch.Generator().manual_seed(3)
+    plan = LinearPlan(f"{K}x0e", f"{N}x0e", scale=1.7)
+    assert plan.wide == (K, N, plan.alpha[0])
+    x = torch.randn(rows, K, generator=g).to(cuda).requires_grad_(True)
+    w = torch.randn(K * N, generator=g).to(cuda).requires_grad_(True)
+    gy = torch.randn(rows, N, generator=g).to(cuda).requires_grad_(True)
+    vx = torch.randn(rows, K, generator=g).to(cuda)
+
+    def run():
+        y = ops.irrep_linear(x, w, plan.handle)
+        dx, dw = torch.autograd.grad([y], [x, w], [gy], create_graph=True)
+        d2 = torch.autograd.grad((dx * vx).sum(), [w, gy])
+        return [y, dx, dw, *d2]
+
+    old = ops.WIDE_MIN_ROWS[0]
+    try:
+        ops.WIDE_MIN_ROWS[0] = 4096
+        assert ops._wide_ok(plan, rows)
+        wide = [t.detach().clone() for t in run()]
+        ops.WIDE_MIN_ROWS[0] = 1 << 30
+        general = [t.detach().clone() for t in run()]
+    finally:
+        ops.WIDE_MIN_ROWS[0] = old
+    a = 1.7 / K ** 0.5
+    W = w.detach().double().view(K, N)
+    ref = [a * x.detach().double() @ W, a * gy.detach().double() @ W.t(), a * (x.detach().double().t() @ gy.detach().double()).reshape(-1),
+           a * (vx.double().t() @ gy.detach().double()).reshape(-1), a * vx.double() @ W]
+    for got_w, got_g, want in zip(wide, general, ref):
+        assert _rel(got_w.double(), want) < 5e-6
+        assert _rel(got_g.double(), want) < 5e-6
+
+
 @pytest.mark.parametrize("irr_in,irr_out,layout", [
     ("8x0e+8x1o+8x2e", "8x0e+8x1o+8x2e", "irreps"), ("8x0e+8x1o+8x2e", "8x0e+8x1o+8x2e", "channel"),
     ("32x0e+32x1o", "32x0e", "irreps"), ("128x0e+128x1o+128x2e+128x3o", "128x0e+128x1o+128x2e+128x3o", "channel"),
