@@ -89,7 +89,7 @@ constexpr int EL_XCHUNK = 256;
 template <int D>
 __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ attrs,
                                                        const float* __restrict__ W, pml_el_plan P, float* __restrict__ dx,
-                                                       int N, int Z, int WC) {
+                                                       int N, int Z, int WC, int chunk) {
   constexpr int NB = D >= 5 ? 4 : 8;  // nodes per thread and pass
   constexpr int DP = D == 1 ? 1 : (D == 3 ? 4 : 8);  // staged row width: 128-bit shared-memory loads of the g rows
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
@@ -105,8 +105,10 @@ __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__
   float* Ws = dyn;                           // [MI][pitch]
   float* gs = dyn + (((size_t)MI * pitch + 3) & ~(size_t)3);  // [NB * nsub][wc * DP], 16-byte aligned
 
-  const int n = blockIdx.y * EL_XCHUNK + tid;
-  const float a = n < N ? __ldg(attrs + (size_t)n * Z + v) : 0.f;
+  // `chunk` <= EL_XCHUNK nodes per CTA: a batch of molecules (N ~ 1e3) is cut finer than a large structure so that
+  // its (path, element, chunk) groups cover all SMs (config 2: 96 busy CTAs of 54 nodes at 256 -> 336 of 14 at 64)
+  const int n = blockIdx.y * chunk + tid;
+  const float a = (tid < chunk && n < N) ? __ldg(attrs + (size_t)n * Z + v) : 0.f;
   const unsigned bal = __ballot_sync(0xffffffffu, a != 0.f);
   if (lane == 0) s_wcnt[warp] = __popc(bal);
   __syncthreads();
@@ -286,7 +288,8 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
                                         float* dx, int N, int Z, int accumulate, cudaStream_t stream) {
   (void)accumulate;
   if (N <= 0 || plan->npaths <= 0) return PML_OK;
-  dim3 grid(1, (N + pml::EL_XCHUNK - 1) / pml::EL_XCHUNK, plan->npaths * Z);
+  const int chunk = N <= 8192 ? 64 : pml::EL_XCHUNK;
+  dim3 grid(1, (N + chunk - 1) / chunk, plan->npaths * Z);
   // per D: the largest slab piece (multiple of 32 columns, or all columns) whose staging fits 160 KB of shared memory
   size_t smem[8] = {0};
   int wcs[8] = {0};
@@ -328,7 +331,7 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
         return PML_ERR_LAUNCH;                                                                                           \
       configured = smem[D];                                                                                              \
     }                                                                                                                    \
-    pml::el_bwd_x_kernel<D><<<grid, 256, smem[D], stream>>>(g, attrs, W, *plan, dx, N, Z, wcs[D]);                        \
+    pml::el_bwd_x_kernel<D><<<grid, 256, smem[D], stream>>>(g, attrs, W, *plan, dx, N, Z, wcs[D], chunk);                        \
   }
   PML_EL_FOR_D(CALL)
 #undef CALL
