@@ -205,14 +205,15 @@ __global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
   if (P.d[p] != D) return;
   const int MI = P.mul_in[p], MO = P.mul_out[p];
-  const int tiles_w = (MO + 15) / 16;
+  constexpr int T = 32;  // output tile T x T per CTA, 2 x 2 entries per thread: every staged x / g value feeds two FMAs
+  const int tiles_w = (MO + T - 1) / T;
   const int tu = blockIdx.x / tiles_w, tw = blockIdx.x - tu * tiles_w;
-  if (tu * 16 >= MI) return;
+  if (tu * T >= MI) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int s_list[EL_CHUNK];
   __shared__ float s_coef[EL_CHUNK];
   __shared__ int s_wcnt[8];
-  __shared__ float xs[EL_NB][16 * D], gs[EL_NB][16 * D];
+  __shared__ float xs[EL_NB][T * D], gs[EL_NB][T * D];
 
   const int n = blockIdx.y * EL_CHUNK + tid;
   const float a = n < N ? __ldg(attrs + (size_t)n * Z + v) : 0.f;
@@ -234,28 +235,45 @@ __global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__
   __syncthreads();
 
   const int ul = tid >> 4, wl = tid & 15;
-  float acc = 0.f;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   for (int j0 = 0; j0 < total; j0 += EL_NB) {
     const int nb = min(EL_NB, total - j0);
-    for (int i = tid; i < nb * 16 * D; i += 256) {
-      const int j = i / (16 * D), rem = i - j * (16 * D);
+    for (int i = tid; i < nb * T * D; i += 256) {
+      const int j = i / (T * D), rem = i - j * (T * D);
       const int uu = rem / D, m = rem - uu * D;
       const int node = s_list[j0 + j];
-      const int gu = tu * 16 + uu, gw = tw * 16 + uu;
+      const int gu = tu * T + uu, gw = tw * T + uu;
       xs[j][rem] = gu < MI ? __ldg(x + (size_t)node * P.x_rs + P.x_off[p] + (size_t)gu * D + m) : 0.f;
       gs[j][rem] = gw < MO ? __ldg(g + (size_t)node * P.o_rs + P.o_off[p] + (size_t)gw * P.o_ws[p] + m) : 0.f;
     }
     __syncthreads();
     for (int j = 0; j < nb; ++j) {
-      float s = 0.f;
+      float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-      for (int m = 0; m < D; ++m) s = fmaf(xs[j][ul * D + m], gs[j][wl * D + m], s);
-      acc = fmaf(s_coef[j0 + j], s, acc);
+      for (int m = 0; m < D; ++m) {
+        const float x0 = xs[j][ul * D + m], x1 = xs[j][(ul + 16) * D + m];
+        const float g0 = gs[j][wl * D + m], g1 = gs[j][(wl + 16) * D + m];
+        s[0][0] = fmaf(x0, g0, s[0][0]);
+        s[0][1] = fmaf(x0, g1, s[0][1]);
+        s[1][0] = fmaf(x1, g0, s[1][0]);
+        s[1][1] = fmaf(x1, g1, s[1][1]);
+      }
+      const float c = s_coef[j0 + j];
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) acc[a2][b2] = fmaf(c, s[a2][b2], acc[a2][b2]);
     }
     __syncthreads();
   }
-  const int u = tu * 16 + ul, w = tw * 16 + wl;
-  if (u < MI && w < MO && acc != 0.f) atomicAdd(dW + P.w_off[p] + ((size_t)u * Z + v) * MO + w, P.alpha[p] * acc);
+#pragma unroll
+  for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+    for (int b2 = 0; b2 < 2; ++b2) {
+      const int u = tu * T + ul + 16 * a2, w = tw * T + wl + 16 * b2;
+      if (u < MI && w < MO && acc[a2][b2] != 0.f)
+        atomicAdd(dW + P.w_off[p] + ((size_t)u * Z + v) * MO + w, P.alpha[p] * acc[a2][b2]);
+    }
 }
 
 }  // namespace pml
@@ -346,7 +364,7 @@ extern "C" int pml_element_linear_bwd_w(const float* x, const float* g, const fl
   if (plan->npaths <= 0 || N <= 0) return PML_OK;
   int max_t = 0;
   for (int p = 0; p < plan->npaths; ++p) {
-    const int t = ((plan->mul_in[p] + 15) / 16) * ((plan->mul_out[p] + 15) / 16);
+    const int t = ((plan->mul_in[p] + 31) / 32) * ((plan->mul_out[p] + 31) / 32);
     max_t = t > max_t ? t : max_t;
   }
   dim3 grid(max_t, (N + pml::EL_CHUNK - 1) / pml::EL_CHUNK, plan->npaths * Z);
