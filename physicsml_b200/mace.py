@@ -371,8 +371,9 @@ class PooledMACEModule(torch.nn.Module):
 
 def compute_forces_by_gradient(energy: torch.Tensor, coordinates: torch.Tensor, training: bool = False) -> torch.Tensor:
     """reference lightning/module.py:28-48"""
-    (grad,) = torch.autograd.grad([energy], [coordinates], grad_outputs=[torch.ones_like(energy)],
-                                  retain_graph=training, create_graph=training, allow_unused=True)
+    with ops.input_grads_only():  # only d/d coordinates is asked for: no weight gradients in the force pass
+        (grad,) = torch.autograd.grad([energy], [coordinates], grad_outputs=[torch.ones_like(energy)],
+                                      retain_graph=training, create_graph=training, allow_unused=True)
     if grad is None:
         raise RuntimeWarning("Gradient is None")
     return -1 * grad

@@ -9,6 +9,7 @@ tensors raises ``NotImplementedError`` from the dispatcher, and a missing shared
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import List, Optional, Tuple
@@ -478,9 +479,31 @@ def _lin_setup(ctx, inputs, output):
     ctx.plan = plan
 
 
+# ``ctx.needs_input_grad`` is fixed when the forward runs (weights require grad), so the cotangent formulas below would
+# compute every weight gradient even when the caller differentiates w.r.t. the coordinates only - the force pass of
+# every evaluation and of every training step.  PyTorch prunes those branches for its own ops (one node per gradient);
+# a fused op cannot be pruned from outside, so ``compute_forces_by_gradient`` says so explicitly.  (Config 4: 19.5 of
+# 62.8 ms of an energy+forces evaluation were weight gradients nobody asked for.)
+_PARAM_GRADS = [True]
+
+
+@contextlib.contextmanager
+def input_grads_only():
+    """inside: first-order cotangent formulas skip the parameter gradients (the caller asks for input gradients only,
+    e.g. forces = -dE/dx); the recorded graph (create_graph=True) still reaches the parameters through the input
+    gradients, which is all force-matching training differentiates"""
+    old = _PARAM_GRADS[0]
+    _PARAM_GRADS[0] = False
+    try:
+        yield
+    finally:
+        _PARAM_GRADS[0] = old
+
+
 def _lin_bwd(ctx, g):
     x, w = ctx.saved_tensors
     nx, nw = ctx.needs_input_grad[:2]
+    nw = nw and _PARAM_GRADS[0]
     return (irrep_linear_bwd_x(g, w, ctx.plan) if nx else None, irrep_linear_bwd_w(x, g, ctx.plan) if nw else None, None)
 
 
@@ -584,6 +607,7 @@ def _el_setup(ctx, inputs, output):
 def _el_bwd(ctx, g):
     x, attrs, w = ctx.saved_tensors
     nx, _, nw = ctx.needs_input_grad[:3]
+    nw = nw and _PARAM_GRADS[0]
     return (element_linear_bwd_x(g, attrs, w, ctx.plan) if nx else None, None,
             element_linear_bwd_w(x, g, attrs, ctx.plan) if nw else None, None)
 
@@ -703,9 +727,9 @@ def _sym_bwd(ctx, g):
     x, attrs, *ws = ctx.saved_tensors
     nx = ctx.needs_input_grad[0]
     nw = ctx.needs_input_grad[2]
-    nw_any = any(nw) if isinstance(nw, (list, tuple)) else bool(nw)
+    nw_any = (any(nw) if isinstance(nw, (list, tuple)) else bool(nw)) and _PARAM_GRADS[0]
     res = sym_contract_bwd(x, attrs, list(ws), g, ctx.plan, nx, nw_any)
-    return (res[0] if nx else None, None, list(res[1:]) if nw_any else None, None)
+    return (res[0] if nx else None, None, list(res[1:]) if nw_any else [None] * len(ws), None)
 
 
 sym_contract.register_autograd(_sym_bwd, setup_context=_sym_setup)
@@ -741,7 +765,7 @@ def _sym_bwd_bwd(ctx, grads):
             gg = _acc(gg, sym_contract(x, attrs, vw, ctx.plan))
         if nx:
             gx = _acc(gx, sym_contract_bwd(x, attrs, vw, g, ctx.plan, True, False)[0])
-    return (gx, None, gw if nw_any else None, gg, None, None, None)
+    return (gx, None, gw if nw_any else [None] * len(ws), gg, None, None, None)
 
 
 sym_contract_bwd.register_autograd(_sym_bwd_bwd, setup_context=_sym_bwd_setup)

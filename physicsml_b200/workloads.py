@@ -105,7 +105,10 @@ def training_loss(model, data: dict, targets: dict) -> torch.Tensor:
     pos = d["coordinates"].detach().requires_grad_(True)
     d["coordinates"] = pos
     e = model(d)["y_graph_scalars"]
-    (g,) = torch.autograd.grad([e], [pos], grad_outputs=[torch.ones_like(e)], retain_graph=True, create_graph=True)
+    from . import ops
+
+    with ops.input_grads_only():  # the force pass: gradients w.r.t. the coordinates only
+        (g,) = torch.autograd.grad([e], [pos], grad_outputs=[torch.ones_like(e)], retain_graph=True, create_graph=True)
     return torch.nn.functional.mse_loss(e, targets["energy"]) + torch.nn.functional.mse_loss(-g, targets["forces"])
 
 

@@ -64,7 +64,8 @@ for _ in range(2):
 torch.cuda.synchronize()
 print(f"peak memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
 ops.enable_kernel_timing(["pml_tp_fwd", "pml_tp_bwd", "pml_sym_fwd", "pml_sym_bwd", "pml_gemm_grouped", "pml_gemm_grouped_tc",
-                          "pml_edge_featurise_fwd", "pml_edge_featurise_bwd", "pml_element_linear_fwd", "pml_element_linear_bwd_x"])
+                          "pml_edge_featurise_fwd", "pml_edge_featurise_bwd", "pml_element_linear_fwd", "pml_element_linear_bwd_x",
+                          "pml_wide_fwd", "pml_wide_bwd_x", "pml_act"])
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
@@ -92,3 +93,28 @@ for name, recs in ops.KERNEL_TIMING.items():
         rows.append((tot, line))
 for _, line in sorted(rows, reverse=True):
     print(line)
+
+if len(sys.argv) > 3 and sys.argv[3] == "shapes":  # per-shape time of the general grouped GEMM (event-bracketed)
+    import collections
+
+    ops.KERNEL_TIMING.clear()
+    records, orig = [], ops._gemm
+
+    def wrapped(gname, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, max_k):
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        orig(gname, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, max_k)
+        x1.record()
+        records.append(((sys._getframe(1).f_code.co_name, nprob, m_runtime, max_m, max_n, max_batch, splitk, max_k), x0, x1))
+
+    ops._gemm = wrapped
+    evaluate()
+    torch.cuda.synchronize()
+    agg = collections.OrderedDict()
+    for key, x0, x1 in records:
+        v = agg.setdefault(key, [0, 0.0])
+        v[0] += 1
+        v[1] += x0.elapsed_time(x1)
+    print("general GEMM by (caller, nprob, M_runtime, max_M, max_N, batch, splitk, max_k): launches, ms each, ms total")
+    for key, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{str(key):90s} {n:3d} {t / n:8.3f} {t:8.3f}")

@@ -29,7 +29,7 @@ def timeit(fn):
     return a.elapsed_time(b) / reps * 1e3
 
 
-for K, N in ((64, 1280), (64, 512)):
+for K, N in ((64, 1280), (64, 512), (64, 64), (8, 64)):
     pl = plans.LinearPlan(f"{K}x0e", f"{N}x0e")
     x = torch.randn(E, K, device=dev)
     w = torch.randn(K * N, device=dev)
