@@ -59,6 +59,14 @@ int pml_tp_fwd(int spec, const float* h, const float* Y, const float* R, const i
  * (zero-initialised when C > 32), dR [E,NP*C] may be NULL to skip it. g [N, C*DOUT]. */
 int pml_tp_bwd(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
                const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, pml_stream_t stream);
+/* Same kernels with a choice of layout inside every block of the output row `out` / its cotangent `g`:
+ * out_layout 0 = e3nn order u*(2l+1) + m (what pml_tp_fwd / pml_tp_bwd use), 1 = component-major m*C + u (packed
+ * 8-byte stores; the per-irrep linear that consumes the row then reads its reduction index with unit stride). */
+int pml_tp_fwd_ex(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
+                  const int* perm, float* out, int N, int C, int out_layout, pml_stream_t stream);
+int pml_tp_bwd_ex(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                  const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, int out_layout,
+                  pml_stream_t stream);
 /* Kernel selection for K4 (diagnostics): by default the TMA-pipelined persistent kernels run whenever NP*C and DIN*C
  * are multiples of 4 floats (16-byte rows), h / R are 16-byte aligned and DOUT <= 48.  Bit 0 of v forces the
  * register-streaming kernels that also serve every other shape; bits 1 / 2 flip the producer placement of the

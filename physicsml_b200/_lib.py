@@ -100,6 +100,8 @@ SIGNATURES = {
     "pml_edge_featurise_jvp": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P],
     "pml_tp_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "pml_tp_bwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "pml_tp_fwd_ex": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "pml_tp_bwd_ex": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "pml_tp_set_simple": [_I],
     "pml_sym_fwd": [_I, _P, _P, C.POINTER(SymWeights), _P, _I, _I, _I, _P],
     "pml_sym_bwd": [_I, _P, _P, C.POINTER(SymWeights), _P, _P, _I, _I, _I, _P],

@@ -106,11 +106,14 @@ def _emit_tp(spec: so3.TPSpec, ident: int) -> str:
             L.append(f"    atomicAdd(hrow + (size_t)C * {off} + (size_t)u * {d} + {i}, h[{off + i}]);")
         off += d
     L.append("  }")
-    for name, op in (("load_out", "a[{k}] = __ldg(row + (size_t)C * {off} + (size_t)u * {d} + {m});"),
-                     ("store_out", "row[(size_t)C * {off} + (size_t)u * {d} + {m}] = a[{k}];")):
+    # output row: block b of irrep l at C*off_b; inside a block either the e3nn order u*(2l+1) + m (MM = false) or
+    # component-major m*C + u (MM = true: unit stride along the channels, which is what both the packed stores of this
+    # kernel and the k-loop of the GEMM that consumes the row want)
+    for name, op in (("load_out", "a[{k}] = __ldg(row + (size_t)C * {off} + (MM ? (size_t){m} * C + u : (size_t)u * {d} + {m}));"),
+                     ("store_out", "row[(size_t)C * {off} + (MM ? (size_t){m} * C + u : (size_t)u * {d} + {m})] = a[{k}];")):
         const = "const " if name == "load_out" else ""
         aconst = "" if name == "load_out" else "const "
-        L.append(f"  __device__ __forceinline__ static void {name}({const}float* __restrict__ row, int C, int u, {aconst}float (&a)[DOUT]) {{")
+        L.append(f"  template <bool MM> __device__ __forceinline__ static void {name}({const}float* __restrict__ row, int C, int u, {aconst}float (&a)[DOUT]) {{")
         off = 0
         for l, _ in spec.out_ls:
             d = 2 * l + 1
@@ -278,21 +281,25 @@ def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
             L.append(f"    h[{off + i}] = make_float2(hrow[C * {off} + u * {d} + {i}], hrow[C * {off} + (u + 1) * {d} + {i}]);")
         off += d
     L.append("  }")
-    L.append("  __device__ __forceinline__ static void load_out2(const float* __restrict__ row, int C, int u, float2 (&a)[DOUT]) {")
+    L.append("  template <bool MM> __device__ __forceinline__ static void load_out2(const float* __restrict__ row, int C, int u, float2 (&a)[DOUT]) {")
     off = 0
     for l, _ in spec.out_ls:
         d = 2 * l + 1
         for m in range(d):
-            L.append(f"    a[{off + m}] = make_float2(__ldg(row + (size_t)C * {off} + (size_t)u * {d} + {m}), __ldg(row + (size_t)C * {off} + (size_t)(u + 1) * {d} + {m}));")
+            L.append(f"    if (MM) a[{off + m}] = __ldg(reinterpret_cast<const float2*>(row + (size_t)C * {off} + (size_t){m} * C + u));")
+            L.append(f"    else a[{off + m}] = make_float2(__ldg(row + (size_t)C * {off} + (size_t)u * {d} + {m}), __ldg(row + (size_t)C * {off} + (size_t)(u + 1) * {d} + {m}));")
         off += d
     L.append("  }")
-    L.append("  __device__ __forceinline__ static void store_out2(float* __restrict__ row, int C, int u, const float2 (&a)[DOUT]) {")
+    L.append("  template <bool MM> __device__ __forceinline__ static void store_out2(float* __restrict__ row, int C, int u, const float2 (&a)[DOUT]) {")
     off = 0
     for l, _ in spec.out_ls:
         d = 2 * l + 1
         for m in range(d):
-            L.append(f"    row[(size_t)C * {off} + (size_t)u * {d} + {m}] = a[{off + m}].x;")
-            L.append(f"    row[(size_t)C * {off} + (size_t)(u + 1) * {d} + {m}] = a[{off + m}].y;")
+            L.append(f"    if (MM) *reinterpret_cast<float2*>(row + (size_t)C * {off} + (size_t){m} * C + u) = a[{off + m}];")
+            L.append("    else {")
+            L.append(f"      row[(size_t)C * {off} + (size_t)u * {d} + {m}] = a[{off + m}].x;")
+            L.append(f"      row[(size_t)C * {off} + (size_t)(u + 1) * {d} + {m}] = a[{off + m}].y;")
+            L.append("    }")
         off += d
     L.append("  }")
     # fp32 reductions into dh[s]: the 2(2l+1) floats of channels (u, u+1) of one block are contiguous and 8-byte

@@ -8,9 +8,9 @@ struct pml_sym_weights;
 
 #define DECL_TP(ID)                                                                                                      \
   extern "C" int pml_tp_fwd_launch_##ID(const float*, const float*, const float*, const int*, const int*, const int*,    \
-                                        float*, int, int, cudaStream_t);                                                 \
+                                        float*, int, int, int, cudaStream_t);                                            \
   extern "C" int pml_tp_bwd_launch_##ID(const float*, const float*, const float*, const float*, const int*, const int*,  \
-                                        const int*, float*, float*, float*, int, int, cudaStream_t);
+                                        const int*, float*, float*, float*, int, int, int, cudaStream_t);
 PML_TP_FOREACH(DECL_TP)
 #undef DECL_TP
 
@@ -47,12 +47,13 @@ extern "C" int pml_tp_set_simple(int v) {
 extern "C" int pml_num_tp_specs(void) { return PML_TP_NUM_SPECS; }
 extern "C" int pml_num_sym_specs(void) { return PML_SYM_NUM_SPECS; }
 
-extern "C" int pml_tp_fwd(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
-                          const int* perm, float* out, int N, int C, cudaStream_t stream) {
+// out_layout: 0 = e3nn order inside every output block (u*(2l+1) + m), 1 = component-major (m*C + u)
+extern "C" int pml_tp_fwd_ex(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
+                             const int* perm, float* out, int N, int C, int out_layout, cudaStream_t stream) {
   switch (spec) {
 #define CASE(ID) \
   case ID:       \
-    return pml_tp_fwd_launch_##ID(h, Y, R, gather, rowptr, perm, out, N, C, stream);
+    return pml_tp_fwd_launch_##ID(h, Y, R, gather, rowptr, perm, out, N, C, out_layout, stream);
     PML_TP_FOREACH(CASE)
 #undef CASE
     default:
@@ -60,18 +61,29 @@ extern "C" int pml_tp_fwd(int spec, const float* h, const float* Y, const float*
   }
 }
 
-extern "C" int pml_tp_bwd(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
-                          const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C,
-                          cudaStream_t stream) {
+extern "C" int pml_tp_bwd_ex(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                             const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C,
+                             int out_layout, cudaStream_t stream) {
   switch (spec) {
 #define CASE(ID) \
   case ID:       \
-    return pml_tp_bwd_launch_##ID(h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, stream);
+    return pml_tp_bwd_launch_##ID(h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, out_layout, stream);
     PML_TP_FOREACH(CASE)
 #undef CASE
     default:
       return PML_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int pml_tp_fwd(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
+                          const int* perm, float* out, int N, int C, cudaStream_t stream) {
+  return pml_tp_fwd_ex(spec, h, Y, R, gather, rowptr, perm, out, N, C, 0, stream);
+}
+
+extern "C" int pml_tp_bwd(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                          const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C,
+                          cudaStream_t stream) {
+  return pml_tp_bwd_ex(spec, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, 0, stream);
 }
 
 extern "C" int pml_sym_fwd(int spec, const float* x, const float* attrs, const pml_sym_weights* W, float* out, int N,

@@ -62,7 +62,7 @@ template <int ID>
 __global__ void __launch_bounds__(128) tp_fwd_kernel(const float* __restrict__ h, const float* __restrict__ Y,
                                                      const float* __restrict__ R, const int* __restrict__ gather,
                                                      const int* __restrict__ rowptr, const int* __restrict__ perm,
-                                                     float* __restrict__ out, int N, int C, int nslab) {
+                                                     float* __restrict__ out, int N, int C, int nslab, int mm) {
   using T = TPCode<ID>;
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(128) tp_fwd_kernel(const float* __restrict__ h
     T::load_h(h + (size_t)s0 * hstride, C, uc, h0);
     T::fwd(h0, Y0, R0, acc);
   }
-  if (active) T::store_out(out + (size_t)n * T::DOUT * C, C, u, acc);
+  if (active) {  // mm: component-major blocks (m*C + u) instead of the e3nn order (u*(2l+1) + m)
+    if (mm) T::template store_out<true>(out + (size_t)n * T::DOUT * C, C, u, acc);
+    else T::template store_out<false>(out + (size_t)n * T::DOUT * C, C, u, acc);
+  }
 }
 
 // Cotangents of the trilinear form, grouped by the SAME scatter segments as the forward so that the large row
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(128) tp_bwd_kernel(const float* __restrict__ h
                                                      const int* __restrict__ gather, const int* __restrict__ rowptr,
                                                      const int* __restrict__ perm, float* __restrict__ dh,
                                                      float* __restrict__ dY, float* __restrict__ dR, int N, int C,
-                                                     int nslab) {
+                                                     int nslab, int mm) {
   using T = TPCode<ID>;
   constexpr int NV = next_pow2(T::NSH);
   const int lane = threadIdx.x & 31;
@@ -139,7 +142,8 @@ __global__ void __launch_bounds__(128) tp_bwd_kernel(const float* __restrict__ h
   const int uc = active ? u : C - 1;
 
   float gv[T::DOUT];
-  T::load_out(g + (size_t)n * T::DOUT * C, C, uc, gv);
+  if (mm) T::template load_out<true>(g + (size_t)n * T::DOUT * C, C, uc, gv);
+  else T::template load_out<false>(g + (size_t)n * T::DOUT * C, C, uc, gv);
   if (!active) {
 #pragma unroll
     for (int k = 0; k < T::DOUT; ++k) gv[k] = 0.f;
@@ -478,7 +482,7 @@ __device__ __forceinline__ void load_y2_smem(const float* ys, float2 (&Yv)[NSH])
 template <int ID, bool DEDICATED>
 __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                    const int* __restrict__ gather, const int* __restrict__ rowptr,
-                                   const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage) {
+                                   const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage, int mm) {
   using T = TPCode<ID>;
   using L = PipeLayout<ID>;
   PML_PIPE_PROLOGUE(true, false)
@@ -510,7 +514,10 @@ __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __r
         if (is_producer) prod.issue(2, consumed, nstage, false, lane);
         T::fwd2(hv, Yv, Rv, acc);
       }
-      if (active) T::store_out2(out + (size_t)n * T::DOUT * C, C, u, acc);
+      if (active) {
+        if (mm) T::template store_out2<true>(out + (size_t)n * T::DOUT * C, C, u, acc);
+        else T::template store_out2<false>(out + (size_t)n * T::DOUT * C, C, u, acc);
+      }
       end = end_next;
     }
   }
@@ -520,7 +527,7 @@ template <int ID, bool DEDICATED, bool WANT_H, bool WANT_Y, bool WANT_R>
 __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                    const float* __restrict__ g, const int* __restrict__ gather,
                                    const int* __restrict__ rowptr, const int* __restrict__ perm, float* __restrict__ dh,
-                                   float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage) {
+                                   float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage, int mm) {
   using T = TPCode<ID>;
   using L = PipeLayout<ID>;
   constexpr int NV = next_pow2(T::NSH);
@@ -545,7 +552,8 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
       const int end_next = (n + 2 <= N) ? min(__ldg(rowptr + n + 2), q_hi) : q_hi;
       float2 gv[T::DOUT];
       if (q < end) {
-        T::load_out2(g + (size_t)n * T::DOUT * C, C, uc, gv);
+        if (mm) T::template load_out2<true>(g + (size_t)n * T::DOUT * C, C, uc, gv);
+        else T::template load_out2<false>(g + (size_t)n * T::DOUT * C, C, uc, gv);
         if (!active) {
 #pragma unroll
           for (int k = 0; k < T::DOUT; ++k) gv[k] = make_float2(0.f, 0.f);
@@ -667,7 +675,7 @@ extern "C" int pml_tp_force_simple(void);
 // Launchers (one pair per compiled signature; dispatched by id in capi.cu).  Streams are the caller's.
 extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const float* Y, const float* R, const int* gather,
                                                        const int* rowptr, const int* perm, float* out, int N, int C,
-                                                       cudaStream_t stream) {
+                                                       int mm, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
   using PL = pml::PipeLayout<PML_TP_ID>;
   const int mode = pml_tp_force_simple();  // bit0: streaming kernels; bit1 / bit2: flip the fwd / bwd producer placement
@@ -678,12 +686,12 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
     const int sbytes = PL::stage_floats(C) * 4;
     if (dedicated) {
       if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, true>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {
-        pml::tp_fwd_pipe_kernel<PML_TP_ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage);
+        pml::tp_fwd_pipe_kernel<PML_TP_ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
         PML_CHECK_LAUNCH();
         return PML_OK;
       }
     } else if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, false>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {
-      pml::tp_fwd_pipe_kernel<PML_TP_ID, false><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage);
+      pml::tp_fwd_pipe_kernel<PML_TP_ID, false><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
       PML_CHECK_LAUNCH();
       return PML_OK;
     }
@@ -691,7 +699,7 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
   const int nslab = (C + 31) / 32;
   const int wpb = 4;
   const long long items = (long long)N * nslab;
-  pml::tp_fwd_kernel<PML_TP_ID><<<pml::ceil_div(items, wpb), wpb * 32, 0, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, nslab);
+  pml::tp_fwd_kernel<PML_TP_ID><<<pml::ceil_div(items, wpb), wpb * 32, 0, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, nslab, mm);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -699,7 +707,7 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
 // dh and (when C > 32) dY must be zero-initialised by the caller; dR is fully overwritten.
 extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const float* Y, const float* R, const float* g,
                                                        const int* gather, const int* rowptr, const int* perm, float* dh,
-                                                       float* dY, float* dR, int N, int C, cudaStream_t stream) {
+                                                       float* dY, float* dR, int N, int C, int mm, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
   const int mask = (dh ? 1 : 0) | (dY ? 2 : 0) | (dR ? 4 : 0);
   using PL = pml::PipeLayout<PML_TP_ID>;
@@ -713,7 +721,7 @@ extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const floa
 #define PML_TP_BWD_PIPE_D(D_, H_, Y_, R_)                                                                               \
   if (pml::pipe_config<pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {                  \
     pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(                         \
-        h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, cfg.nstage);                                                \
+        h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, cfg.nstage, mm);                                             \
     done = true;                                                                                                        \
   }
 #define PML_TP_BWD_PIPE(M, H_, Y_, R_)           \
@@ -747,7 +755,7 @@ extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const floa
 #define PML_TP_BWD_CASE(M, H_, Y_, R_)                                                                              \
   case M:                                                                                                           \
     pml::tp_bwd_kernel<PML_TP_ID, H_, Y_, R_><<<grid, wpb * 32, 0, stream>>>(h, Y, R, g, gather, rowptr, perm, dh, dY, \
-                                                                            dR, N, C, nslab);                       \
+                                                                            dR, N, C, nslab, mm);                   \
     break;
   switch (mask) {
     PML_TP_BWD_CASE(1, true, false, false)

@@ -29,9 +29,10 @@ def _irreps(x) -> list:
 class IrrepLinear(torch.nn.Module):
     """o3.Linear with internal shared weights (flat ``weight``; ``bias``/``output_mask`` kept for state-dict parity)."""
 
-    def __init__(self, irreps_in, irreps_out, scale: float = 1.0, out_layout: str = "irreps") -> None:
+    def __init__(self, irreps_in, irreps_out, scale: float = 1.0, out_layout: str = "irreps",
+                 in_layout: str = "irreps") -> None:
         super().__init__()
-        self.plan = LinearPlan(irreps_in, irreps_out, scale=scale, out_layout=out_layout)
+        self.plan = LinearPlan(irreps_in, irreps_out, scale=scale, out_layout=out_layout, in_layout=in_layout)
         self.weight = torch.nn.Parameter(torch.randn(self.plan.weight_numel))
         self.bias = torch.nn.Parameter(torch.zeros(0))
         mask = torch.zeros(self.plan.d_out)
@@ -127,7 +128,9 @@ class InteractionBlock(torch.nn.Module):
         lmax = max(l for _, l, _ in sh)
         self.lmax = lmax
         self.linear_node_feats = IrrepLinear(node, node)
-        self.tp = TPPlan(node, lmax, inter, sh_parity=-1 if any(p == -1 for _, _, p in sh) else 1)
+        # the aggregated message only ever feeds `linear`: it is kept component-major (m*C + u inside every path
+        # block), which gives the tensor-product kernels packed stores and the GEMM a unit-stride reduction index
+        self.tp = TPPlan(node, lmax, inter, sh_parity=-1 if any(p == -1 for _, _, p in sh) else 1, out_layout="component")
         n_edge_feats = so3.irreps_dim(_irreps(edge_feats_irreps))
         self.net_R_channels = RadialMLP([n_edge_feats, 64, 64, 64, self.tp.NP * self.tp.C])
         self.conv_tp = _TPBuffers(self.tp)
@@ -136,8 +139,11 @@ class InteractionBlock(torch.nn.Module):
         self.channels = inter[0][0]
         # '/ avg_num_neighbours' (blocks.py:229) is folded into the GEMM's alpha; the final reshape (blocks.py:235)
         # into its output strides (of `linear` for layers >= 1, of `mix_layer` for layer 0)
-        self.linear = IrrepLinear(tp_simplified, inter, scale=1.0 / avg_num_neighbours,
-                                  out_layout="irreps" if (mix_with_node_attrs or not channel) else "channel")
+        # one input block per path (same flat weight layout as the simplified irreps: blocks of one irrep are adjacent)
+        assert so3.simplify_irreps(self.tp.out_irreps) == tp_simplified
+        self.linear = IrrepLinear(self.tp.out_irreps, inter, scale=1.0 / avg_num_neighbours,
+                                  out_layout="irreps" if (mix_with_node_attrs or not channel) else "channel",
+                                  in_layout="component")
         self.mix_layer = (
             ElementLinear(inter, so3.irreps_dim(attrs), inter, out_layout="channel" if channel else "irreps")
             if mix_with_node_attrs else None

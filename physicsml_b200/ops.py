@@ -209,7 +209,8 @@ def tp_scatter(h: Tensor, Y: Tensor, R: Tensor, gather: Tensor, rowptr: Tensor, 
     h, Y, R = _f32c(h), _f32c(Y), _f32c(R)
     N = rowptr.numel() - 1
     out = _new_empty(h, N, pl.C * pl.DOUT)
-    _call("pml_tp_fwd", pl.spec_id, _p(h), _p(Y), _p(R), _p(gather), _p(rowptr), _p(perm), _p(out), N, pl.C, _stream())
+    _call("pml_tp_fwd_ex", pl.spec_id, _p(h), _p(Y), _p(R), _p(gather), _p(rowptr), _p(perm), _p(out), N, pl.C,
+          pl.out_layout_id, _stream())
     return out
 
 
@@ -229,8 +230,9 @@ def tp_scatter_bwd(h: Tensor, Y: Tensor, R: Tensor, g: Tensor, gather: Tensor, r
     dY = (torch.zeros_like(Y) if pl.C > 32 else _empty_like(Y)) if need_y else _new_empty(Y, 0)
     dR = _empty_like(R) if need_r else _new_empty(R, 0)
     if need_h or need_y or need_r:
-        _call("pml_tp_bwd", pl.spec_id, _p(h), _p(Y), _p(R), _p(g), _p(gather), _p(rowptr), _p(perm),
-              _p(dh) if need_h else None, _p(dY) if need_y else None, _p(dR) if need_r else None, N, pl.C, _stream())
+        _call("pml_tp_bwd_ex", pl.spec_id, _p(h), _p(Y), _p(R), _p(g), _p(gather), _p(rowptr), _p(perm),
+              _p(dh) if need_h else None, _p(dY) if need_y else None, _p(dR) if need_r else None, N, pl.C,
+              pl.out_layout_id, _stream())
     return dh, dY, dR
 
 

@@ -40,7 +40,14 @@ class LinearPlan:
     (the reference's ``reshape_irreps``, irreps_tools.py:47-67, fused into the GEMM's output strides).
     """
 
-    def __init__(self, irreps_in, irreps_out, scale: float = 1.0, out_layout: str = "irreps") -> None:
+    def __init__(self, irreps_in, irreps_out, scale: float = 1.0, out_layout: str = "irreps",
+                 in_layout: str = "irreps") -> None:
+        # in_layout "component": every input block is stored component-major, x[n, off_b + m*mul + u] (what
+        # tp_scatter writes with TPPlan(out_layout="component")): unit stride along the reduction index u
+        if in_layout not in ("irreps", "component"):
+            raise ValueError(in_layout)
+        self.in_layout = in_layout
+        mmaj = in_layout == "component"
         self.irreps_in = so3.parse_irreps(irreps_in)
         self.irreps_out = so3.parse_irreps(irreps_out)
         self.scale = float(scale)
@@ -114,6 +121,11 @@ class LinearPlan:
                     p.a_off[c], p.b_off[c], p.kc[c] = in_off[i], w, self.irreps_in[i][0]
                 p.c_off = o_off[o]
                 p.a_rs, p.a_cs, p.a_bs = self.d_in, d, 1
+                if mmaj:
+                    muls_in = {self.irreps_in[i][0] for i, _ in sub}
+                    if len(muls_in) != 1:
+                        raise NotImplementedError("component-major input blocks of one irrep with different multiplicities")
+                    p.a_cs, p.a_bs = 1, muls_in.pop()
                 p.b_rs, p.b_cs, p.b_bs = mo, 1, 0
                 p.c_rs, p.c_cs, p.c_bs = self.out_row, o_cs[o], 1
                 p.M, p.N, p.nbatch, p.alpha = -1, mo, d, self.alpha[o]
@@ -143,7 +155,7 @@ class LinearPlan:
             if any(self.irreps_out[o][0] != mo for o, _ in ch):
                 raise NotImplementedError("output blocks of one irrep with different multiplicities")
             p.b_rs, p.b_cs, p.b_bs = 1, mo, 0  # B[k = w, col = u] = W[u, w]
-            p.c_rs, p.c_cs, p.c_bs = self.d_in, d, 1
+            p.c_rs, p.c_cs, p.c_bs = (self.d_in, 1, mi) if mmaj else (self.d_in, d, 1)
             p.M, p.N, p.nbatch, p.alpha, p.accumulate = -1, mi, d, 1.0, 0
             bx.append(p)
         self.has_unfed_input = len(bx) < len(self.irreps_in)
@@ -162,6 +174,8 @@ class LinearPlan:
             p.a_off[0], p.b_off[0], p.kc[0] = in_off[i], o_off[o], -1
             p.c_off = w
             p.a_rs, p.a_cs, p.a_bs = d, self.d_in, 1  # A[u, k = n] = x[n, in_off + u d + m]
+            if mmaj:
+                p.a_rs, p.a_bs = 1, mi  # x[n, in_off + m mul + u]
             p.b_rs, p.b_cs, p.b_bs = self.out_row, o_cs[o], 1  # B[k = n, w] = g[n, o_off + w cs + m]
             p.c_rs, p.c_cs, p.c_bs = mo, 1, 0
             p.M, p.N, p.nbatch, p.alpha, p.accumulate = mi, mo, d, self.alpha[o], 0
@@ -234,7 +248,13 @@ class ElementLinearPlan:
 
 
 class TPPlan:
-    def __init__(self, node_irreps, sh_lmax: int, target_irreps, sh_parity: int = -1) -> None:
+    def __init__(self, node_irreps, sh_lmax: int, target_irreps, sh_parity: int = -1, out_layout: str = "irreps") -> None:
+        # out_layout "component": every output block is written component-major, out[n, C*off_b + m*C + u], instead of
+        # the e3nn order u*(2l+1) + m: packed 8-byte stores from the kernel and a unit-stride reduction index for the
+        # linear that follows (LinearPlan(in_layout="component")).  Internal to a module: never leaves it.
+        if out_layout not in ("irreps", "component"):
+            raise ValueError(out_layout)
+        self.out_layout_id = 1 if out_layout == "component" else 0
         self.spec = so3.build_tp_spec(node_irreps, sh_lmax, target_irreps, sh_parity)
         muls = {m for m, _, _ in so3.parse_irreps(node_irreps)}
         self.C = muls.pop()

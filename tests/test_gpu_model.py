@@ -62,9 +62,16 @@ def test_energy_forces_parity(cuda, name):
     assert (f - f_ref).abs().max().item() <= 1e-4
 
 
-def test_training_step_gradients(cuda):
-    """force-matching loss: d(loss)/d(params) through the double-backward formulas vs the oracle's autograd"""
+@pytest.mark.parametrize("prune", [False, True])
+def test_training_step_gradients(cuda, prune):
+    """force-matching loss: d(loss)/d(params) through the double-backward formulas vs the oracle's autograd.
+    prune=True runs the force pass under ops.input_grads_only() (what compute_forces_by_gradient and the benchmark's
+    training step do): no weight gradients are computed in that pass, the parameter gradients of the loss must not
+    change."""
+    import contextlib
+
     from oracle.ref_model import RefPooledMACE  # noqa: F401
+    from physicsml_b200 import ops
     from physicsml_b200.mace import compute_forces_by_gradient
 
     ref, mine, cfg = _models("small", cuda)
@@ -78,7 +85,8 @@ def test_training_step_gradients(cuda):
         d = dict(d)
         d["coordinates"] = d["coordinates"].clone().requires_grad_(True)
         e = model(d)["y_graph_scalars"]
-        (gr,) = torch.autograd.grad([e], [d["coordinates"]], [torch.ones_like(e)], create_graph=True, retain_graph=True)
+        with (ops.input_grads_only() if (prune and dev != "cpu") else contextlib.nullcontext()):
+            (gr,) = torch.autograd.grad([e], [d["coordinates"]], [torch.ones_like(e)], create_graph=True, retain_graph=True)
         return ((e - e_t.to(dev)) ** 2).mean() + ((-gr - f_t.to(dev)) ** 2).mean()
 
     l_ref = loss_of(ref, data, "cpu")
