@@ -160,6 +160,58 @@ def test_tp_pipelined_matches_streaming(cuda, node_irreps, lmax, C, N, deg):
     assert _rel(res[0][1][1], res[1][1][1]) < 1e-5  # dY
 
 
+@pytest.mark.parametrize("node_irreps,lmax,C,N,deg", [("128x0e+128x1o", 3, 128, 150, 21), ("32x0e+32x1o", 2, 32, 70, 9),
+                                                      ("6x0e+6x1o", 2, 6, 40, 5)])
+def test_tp_component_major_message_and_linear(cuda, node_irreps, lmax, C, N, deg):
+    """The layout MACE uses between K4 and its per-irrep linear: tp_scatter with out_layout="component" is the
+    e3nn-layout result with every path block transposed ([C, 2l+1] -> [2l+1, C]; pipelined and register-streaming
+    kernels), and IrrepLinear(in_layout="component") on it equals the irreps-layout linear on the e3nn row - values,
+    first derivatives and the second-order terms force-matching training takes."""
+    from e3nn import o3
+    from physicsml_b200 import ops
+    from physicsml_b200.mace import IrrepLinear
+    from physicsml_b200.plans import TPPlan
+
+    g = torch.Generator().manual_seed(21)
+    ei = _edges(N, deg, g, cuda)
+    E = ei.shape[1]
+    _, target = _ref_tp(node_irreps, lmax, C)
+    pe = TPPlan(node_irreps, lmax, str(target))
+    pc = TPPlan(node_irreps, lmax, str(target), out_layout="component")
+    d_in = sum(m * (2 * l + 1) for m, l, _ in pe.out_irreps)
+    h = torch.randn(N, o3.Irreps(node_irreps).dim, generator=g).to(cuda).requires_grad_(True)
+    Y = torch.randn(E, (lmax + 1) ** 2, generator=g).to(cuda).requires_grad_(True)
+    R = torch.randn(E, pe.NP * C, generator=g).to(cuda).requires_grad_(True)
+    ep = ops.EdgePlan(ei, N)
+
+    def to_component(row):  # e3nn row -> component-major row
+        out, off = [], 0
+        for m, l, _ in pe.out_irreps:
+            d = 2 * l + 1
+            out.append(row[:, off:off + m * d].reshape(-1, m, d).transpose(1, 2).reshape(-1, m * d))
+            off += m * d
+        return torch.cat(out, dim=1)
+
+    torch.manual_seed(0)
+    lin_e = IrrepLinear(pe.out_irreps, str(target), scale=0.3).to(cuda)
+    lin_c = IrrepLinear(pc.out_irreps, str(target), scale=0.3, in_layout="component").to(cuda)
+    lin_c.load_state_dict(lin_e.state_dict())
+    gy = torch.randn(N, lin_e.plan.d_out, generator=g).to(cuda).requires_grad_(True)
+    v = [torch.randn(t.shape, generator=g).to(cuda) for t in (h, Y, R)]
+    res = []
+    for plan, lin in ((pe, lin_e), (pc, lin_c)):
+        a = ops.tp_scatter(h, Y, R, ep.gather, ep.rowptr, ep.perm, plan.handle)
+        assert a.shape == (N, d_in)
+        y = lin(a)
+        gs = torch.autograd.grad([y], [h, Y, R, lin.weight], [gy], create_graph=True)
+        g2 = torch.autograd.grad(sum((t * w).sum() for t, w in zip(gs[:3], v)), [h, R, lin.weight, gy])
+        res.append((a.detach(), y.detach(), [t.detach() for t in gs], [t.detach() for t in g2]))
+    assert _rel(res[1][0], to_component(res[0][0])) < 1e-6  # same arithmetic, different addresses
+    assert _rel(res[1][1], res[0][1]) < 1e-5
+    for a, b in zip(res[1][2] + res[1][3], res[0][2] + res[0][3]):
+        assert _rel(a, b) < 2e-5
+
+
 @pytest.mark.parametrize("E", [0, 1, 5])
 def test_tp_scatter_degenerate_graphs(cuda, E):
     """no edges at all / a single edge / fewer edges than persistent CTAs: every node row is still written (zeros for
