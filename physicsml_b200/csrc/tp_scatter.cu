@@ -686,6 +686,10 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
     const int sbytes = PL::stage_floats(C) * 4;
     if (dedicated) {
       if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, true>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {
+        // small graphs: one CTA per node (tile), more CTAs than slots: the hardware hands a free slot the next node, so
+        // nodes of different degree balance themselves instead of being paired statically
+        // (config 2, 1304 nodes on 740 slots: 65.6 -> 57.3 us, 57.5 -> 65.8 % of HBM peak)
+        if (N < pml::kSmallGraphNodes) cfg.grid = N < 4 * cfg.grid ? N : 4 * cfg.grid;
         pml::tp_fwd_pipe_kernel<PML_TP_ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
         PML_CHECK_LAUNCH();
         return PML_OK;

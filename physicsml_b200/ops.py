@@ -66,7 +66,7 @@ def enable_kernel_timing(names) -> None:
 
 def _call(name: str, *args, launches: int = 1) -> None:
     LAUNCHES[0] += launches
-    rec = KERNEL_TIMING.get(name)
+    rec = KERNEL_TIMING.get(name[:-3] if name.endswith("_ex") else name)  # pml_tp_fwd_ex is timed as pml_tp_fwd
     if rec is None:
         _lib.check(getattr(_lib.lib(), name)(*args), name)
         return

@@ -212,6 +212,32 @@ def test_tp_component_major_message_and_linear(cuda, node_irreps, lmax, C, N, de
         assert _rel(a, b) < 2e-5
 
 
+def test_kernel_timing_hook_sees_the_edge_kernels(cuda):
+    """bench.py's roofline comes from ops.KERNEL_TIMING["pml_tp_fwd"]: the hook must keep seeing the fused edge kernels
+    whichever entry point (pml_tp_fwd / pml_tp_fwd_ex) the op calls"""
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import TPPlan
+
+    g = torch.Generator().manual_seed(2)
+    N, C, lmax = 12, 8, 2
+    ei = _edges(N, 4, g, cuda)
+    _, target = _ref_tp("8x0e+8x1o", lmax, C)
+    ep = ops.EdgePlan(ei, N)
+    try:
+        ops.enable_kernel_timing(["pml_tp_fwd", "pml_tp_bwd"])
+        for layout in ("irreps", "component"):
+            plan = TPPlan("8x0e+8x1o", lmax, str(target), out_layout=layout)
+            h = torch.randn(N, 32, generator=g).to(cuda).requires_grad_(True)
+            Y = torch.randn(ei.shape[1], 9, generator=g).to(cuda)
+            R = torch.randn(ei.shape[1], plan.NP * C, generator=g).to(cuda)
+            ops.tp_scatter(h, Y, R, ep.gather, ep.rowptr, ep.perm, plan.handle).sum().backward()
+        torch.cuda.synchronize()
+        assert len(ops.KERNEL_TIMING["pml_tp_fwd"]) == 2 and len(ops.KERNEL_TIMING["pml_tp_bwd"]) == 2
+        assert all(a.elapsed_time(b) > 0 for _, a, b in ops.KERNEL_TIMING["pml_tp_fwd"])
+    finally:
+        ops.enable_kernel_timing([])
+
+
 @pytest.mark.parametrize("E", [0, 1, 5])
 def test_tp_scatter_degenerate_graphs(cuda, E):
     """no edges at all / a single edge / fewer edges than persistent CTAs: every node row is still written (zeros for
