@@ -15,6 +15,8 @@
 //     overlap the MMAs of tile j+1 and the copy of tile j+2.
 // fp32 accuracy: K <= 64 means at most 24 MMAs per accumulator, far below the length where the tensor core's
 // truncating accumulation shows (see gemm_tc.cu, kPromoBlocks).
+#include <cstdlib>
+
 #include "pml_common.cuh"
 
 namespace pml {
@@ -537,6 +539,225 @@ __global__ void __launch_bounds__(X_THREADS, 1) wide_bwd_x_kernel(const float* _
   }
 }
 
+
+// =====================================================================================================================
+// dx, second version: the streamed operand lives in TENSOR MEMORY.  With both operands in shared memory every
+// tcgen05.mma M128 N64 K8 re-reads its 4 KB A tile, three times per k-step under 3xTF32, and the kernel above is bound
+// by shared-memory bandwidth (104 KB of traffic per 16 KB chunk of G).  Here a chunk of G goes: coalesced global loads
+// -> registers -> raw [128 x 32] staging tile (shared memory) -> the thread that owns a row reads it back, splits it
+// into tf32 hi/lo and writes both halves into TMEM (tcgen05.st 32x32b, lane = row, column = k); the MMAs take A from
+// TMEM ([a_tmem] operand form) and only the W^T images come from shared memory: 56 KB of shared-memory traffic per chunk.
+// Two loader sets of four warps (one per TMEM lane quadrant) alternate chunks; 4 TMEM stages of 64 columns (hi | lo).
+// =====================================================================================================================
+constexpr int XT_A_STAGES = 4, XT_RAW_PITCH = 36, XT_RAW_STAGES = 4, XT_AHEAD = 3;
+
+#define PML_MMA3_TS(P)                                                     \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], bh, %5, " P ";\n\t"     \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bl, %5, pt;\n\t"        \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bh, %5, pt;\n\t"
+#define PML_ADV_TS "add.u32 ah, ah, 8;\n\tadd.u32 al, al, 8;\n\tadd.s64 bh, bh, 16;\n\tadd.s64 bl, bl, 16;\n\t"
+__device__ __forceinline__ void umma_3x_k32_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pt;\n\t.reg .b64 bh, bl;\n\t.reg .b32 ah, al;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+      "mov.b32 ah, %1;\n\tmov.b32 al, %2;\n\tmov.b64 bh, %3;\n\tmov.b64 bl, %4;\n\t"
+      PML_MMA3_TS("p") PML_ADV_TS PML_MMA3_TS("pt") PML_ADV_TS PML_MMA3_TS("pt") PML_ADV_TS PML_MMA3_TS("pt") "}"
+      ::"r"(d), "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
+        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
+        "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+
+struct __align__(128) BwdXTSmem {
+  float raw[2][XT_RAW_STAGES][BM * XT_RAW_PITCH];  // [loader set][stage]: raw fp32 chunks, row pitch 36 floats  144 KB
+  unsigned long long raw_full[2][XT_RAW_STAGES];
+  float b[X_B_STAGES][2 * X_B_FLOATS];  // W^T chunk images (hi, lo)                                       64 KB
+  unsigned long long a_full[XT_A_STAGES], a_empty[XT_A_STAGES], b_full[X_B_STAGES], b_empty[X_B_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(X_THREADS, 1) wide_bwd_x_tmem_kernel(const float* __restrict__ G, long long ldg, int N,
+                                                                       const float* __restrict__ image,
+                                                                       float* __restrict__ dA, long long lda, int K, int M,
+                                                                       float alpha) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdXTSmem& S = *reinterpret_cast<BwdXTSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nitems = (M + BM - 1) / BM;
+  const int nch = N / XC;
+  const int my_items = ((int)blockIdx.x < nitems) ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_items * nch;
+  constexpr uint32_t TCOLS = 512;            // 2 accumulators x 64 + 4 A stages x 64 = 384 -> next power of two
+  constexpr uint32_t A_COL0 = 2 * BN;        // first A-stage column
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < XT_A_STAGES; ++s) {
+      mbar_init(smem_u32(&S.a_full[s]), 4);
+      mbar_init(smem_u32(&S.a_empty[s]), 1);
+    }
+    for (int s = 0; s < 2 * XT_RAW_STAGES; ++s) mbar_init(smem_u32(&S.raw_full[0][0] + s), 128);
+    for (int s = 0; s < X_B_STAGES; ++s) {
+      mbar_init(smem_u32(&S.b_full[s]), 1);
+      mbar_init(smem_u32(&S.b_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&S.acc_full[s]), 1);
+      mbar_init(smem_u32(&S.acc_empty[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 13) {
+    if (lane == 0) {
+      for (int g = 0; g < total; ++g) {
+        const int c = g % nch, s = g % X_B_STAGES;
+        mbar_wait(smem_u32(&S.b_empty[s]), ((g / X_B_STAGES) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&S.b_full[s]);
+        mbar_expect_tx(fb, 2u * X_B_FLOATS * 4u);
+        bulk_g2s(smem_u32(S.b[s]), image + (size_t)c * 2 * X_B_FLOATS, 2u * X_B_FLOATS * 4u, fb);
+      }
+    }
+  } else if (warp == 12) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int P = 0;
+      for (int g = 0; g < total; ++g) {
+        const int c = g % nch, sa = g % XT_A_STAGES, sb = g % X_B_STAGES;
+        const bool opens = (c % X_PERIOD) == 0, closes = (c % X_PERIOD) == X_PERIOD - 1 || c == nch - 1;
+        const int buf = P & 1;
+        if (opens) mbar_wait(smem_u32(&S.acc_empty[buf]), ((P >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(&S.a_full[sa]), (g / XT_A_STAGES) & 1);
+        mbar_wait(smem_u32(&S.b_full[sb]), (g / X_B_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = tmem + A_COL0 + (uint32_t)(sa * 2 * XC), a_lo = a_hi + XC;
+        const uint32_t b_hi = smem_u32(S.b[sb]), b_lo = b_hi + X_B_FLOATS * 4;
+        umma_3x_k32_ts(tmem + (uint32_t)(buf * BN), a_hi, a_lo, make_desc32(b_hi), make_desc32(b_lo), IDESC, opens ? 0u : 1u);
+        umma_commit(smem_u32(&S.a_empty[sa]));
+        umma_commit(smem_u32(&S.b_empty[sb]));
+        if (closes) {
+          umma_commit(smem_u32(&S.acc_full[buf]));
+          ++P;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- loader sets: set = chunk parity, quad = TMEM lane quadrant of this warp
+    const int set = (warp - 4) >> 2, quad = (warp - 4) & 3;
+    const int lt = tid - 128 - set * 128;  // 0..127 inside the set
+    // The set's chunks (global chunk g = set + 2 n) go global -> shared by 16-byte cp.async, XT_AHEAD chunks ahead of
+    // their conversion: ~100 KB in flight per SM without holding a single register (a register prefetch ring deep
+    // enough for DRAM latency at this rate would need 128 registers per thread).
+    auto issue = [&](int n) {
+      const int g = set + 2 * n;
+      if (g >= total) return;
+      const int ik = g / nch, c = g - ik * nch;
+      const int row0 = ((int)blockIdx.x + ik * (int)gridDim.x) * BM;
+      float* rawb = S.raw[set][n % XT_RAW_STAGES];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = lt + 128 * i;
+        const int r = (idx & 7) + 8 * (idx >> 6), kc = (idx >> 3) & 7;
+        const bool ok = row0 + r < M;
+        const float* src = G + (long long)(ok ? row0 + r : row0) * ldg + c * XC + kc * 4;
+        const uint32_t dst = smem_u32(rawb + r * XT_RAW_PITCH + kc * 4);
+        const uint32_t bytes = ok ? 16u : 0u;  // rows past M are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.raw_full[set][n % XT_RAW_STAGES]))
+                   : "memory");
+    };
+    const int my_chunks = (total - set + 1) / 2;  // chunks g = set, set + 2, ... < total
+#pragma unroll
+    for (int n = 0; n < XT_AHEAD; ++n) issue(n);
+    for (int n = 0; n < my_chunks; ++n) {
+      const int g = set + 2 * n;
+      const float* rawb = S.raw[set][n % XT_RAW_STAGES];
+      mbar_wait(smem_u32(&S.raw_full[set][n % XT_RAW_STAGES]), (n / XT_RAW_STAGES) & 1);
+      float hi[XC], lo[XC];
+      const float* myrow = rawb + (quad * 32 + lane) * XT_RAW_PITCH;
+#pragma unroll
+      for (int j = 0; j < XC / 4; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(myrow + 4 * j);
+        split_tf32(t.x, hi[4 * j], lo[4 * j]);
+        split_tf32(t.y, hi[4 * j + 1], lo[4 * j + 1]);
+        split_tf32(t.z, hi[4 * j + 2], lo[4 * j + 2]);
+        split_tf32(t.w, hi[4 * j + 3], lo[4 * j + 3]);
+      }
+      // every thread of the set has read chunk n (hence n - 1): the stage of chunk n - 1 may be refilled
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+      issue(n + XT_AHEAD);
+      const int s = g % XT_A_STAGES;
+      mbar_wait(smem_u32(&S.a_empty[s]), ((g / XT_A_STAGES) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + A_COL0 + (uint32_t)(s * 2 * XC);
+      tmem_st32(ta, hi);
+      tmem_st32(ta + XC, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&S.a_full[s]));
+    }
+  } else {
+    // ---------------- warps 0-3: accumulator promotion and the output block (as in wide_bwd_x_kernel)
+    int P = 0;
+    for (int ik = 0; ik < my_items; ++ik) {
+      const int row0 = ((int)blockIdx.x + ik * (int)gridDim.x) * BM;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      const int nper = (nch + X_PERIOD - 1) / X_PERIOD;
+      for (int p = 0; p < nper; ++p, ++P) {
+        const int buf = P & 1;
+        mbar_wait(smem_u32(&S.acc_full[buf]), (P >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float v[BN];
+        tmem_ld64(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN), v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&S.acc_empty[buf]));
+#pragma unroll
+        for (int j = 0; j < BN; ++j) acc[j] += v[j];
+      }
+      const int gr = row0 + warp * 32 + lane;
+      if (gr < M) {
+        float* orow = dA + (long long)gr * lda;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4)
+          if (j < K) *reinterpret_cast<float4*>(orow + j) = make_float4(alpha * acc[j], alpha * acc[j + 1], alpha * acc[j + 2], alpha * acc[j + 3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
+  }
+}
+
 }  // namespace wide
 }  // namespace pml
 
@@ -619,6 +840,20 @@ extern "C" int pml_wide_bwd_x(const float* G, long long ldg, int N, const float*
     configured = true;
   }
   const int nitems = (M + BM - 1) / BM;
+  static int use_tmem = -1;  // PML_WIDE_X_TMEM=0 selects the first version (operands in shared memory) for A/B runs
+  if (use_tmem < 0) use_tmem = getenv("PML_WIDE_X_TMEM") ? atoi(getenv("PML_WIDE_X_TMEM")) : 1;
+  if (use_tmem) {
+    static bool configured_t = false;
+    const int smem_t = (int)sizeof(BwdXTSmem) + 128;
+    if (!configured_t) {
+      if (cudaFuncSetAttribute(wide_bwd_x_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t) != cudaSuccess)
+        return PML_ERR_LAUNCH;
+      configured_t = true;
+    }
+    wide_bwd_x_tmem_kernel<<<min(sms, nitems), X_THREADS, smem_t, stream>>>(G, ldg, N, image, dA, lda, K, M, alpha);
+    PML_CHECK_LAUNCH();
+    return PML_OK;
+  }
   wide_bwd_x_kernel<<<min(sms, nitems), X_THREADS, smem, stream>>>(G, ldg, N, image, dA, lda, K, M, alpha);
   PML_CHECK_LAUNCH();
   return PML_OK;
