@@ -373,6 +373,24 @@ def _wide_ok(pl, n: int) -> bool:
     return pl.wide is not None and GEMM_MODE[0] == "tc" and n >= WIDE_MIN_ROWS[0]
 
 
+NARROW_MIN_ROWS = [int(os.environ.get("PML_NARROW_MIN_ROWS", "262144"))]
+
+
+def _narrow_ok(pl, n: int) -> bool:
+    """64 -> 64 scalar layers on very large edge sets (a periodic box: 2 M edges) also go through the streaming dx
+    kernel; on a batch of molecules the extra pack launch costs more than the kernel saves"""
+    return pl.narrow is not None and GEMM_MODE[0] == "tc" and n >= NARROW_MIN_ROWS[0]
+
+
+def _stream_reduce(a: Tensor, w: Tensor, rows: int, n_red: int, n_out: int, w_rs: int, w_cs: int, alpha: float) -> Tensor:
+    """out[rows, n_out] = alpha * a[rows, n_red] @ Wt^T with Wt[o, r] = w[o*w_rs + r*w_cs] (streaming dx kernel)"""
+    out = _new_empty(a, rows, n_out)
+    image = torch.empty(((n_red + 63) // 64) * 2 * 64 * 64, device=w.device, dtype=torch.float32)
+    _call("pml_wide_pack_wt", _p(w), w_rs, w_cs, n_out, n_red, _p(image), _stream())
+    _call("pml_wide_bwd_x", _p(a), n_red, n_red, _p(image), _p(out), n_out, n_out, rows, alpha, _stream())
+    return out
+
+
 def _wide_image(w: Tensor, k: int, n: int, w_rs: int, w_cs: int) -> Tensor:
     """tf32 hi/lo shared-memory images of W [k, n] (element (i, j) at w[i*w_rs + j*w_cs]), one per 64-column tile"""
     image = torch.empty(((n + 63) // 64) * 2 * 64 * 64, device=w.device, dtype=torch.float32)
@@ -386,6 +404,9 @@ def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
     x, w = _f32c(x), _f32c(w)
     n = x.shape[0]
     shape = (n, pl.channels, pl.S) if pl.out_layout == "channel" else (n, pl.d_out)
+    if _narrow_ok(pl, n):
+        k, nn, alpha = pl.narrow  # y = x W: reduce over k, W[r = k index, o = nn index] at w[r*nn + o]
+        return _stream_reduce(x, w, n, k, nn, 1, nn, alpha)
     if _wide_ok(pl, n):
         k, nn, alpha = pl.wide
         out = _new_empty(x, shape)
@@ -419,6 +440,9 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
     pl = plans.get(plan)
     g, w = _f32c(g), _f32c(w)
     n = g.shape[0]
+    if _narrow_ok(pl, n):
+        k, nn, alpha = pl.narrow  # dx = g W^T: reduce over nn, W[o = k index, r = nn index] at w[o*nn + r]
+        return _stream_reduce(g, w, n, nn, k, nn, 1, alpha)
     if _wide_ok(pl, n):
         k, nn, alpha = pl.wide
         dx = _new_empty(g, n, pl.d_in)

@@ -91,11 +91,17 @@ class LinearPlan:
         # scalar layer with a short reduction and a wide output (the output layer of the radial MLP): (K, N, alpha) for
         # the streaming kernels of csrc/gemm_wide.cu, else None
         self.wide = None
+        self.narrow = None
         if (len(self.irreps_in) == 1 and len(self.irreps_out) == 1 and self.irreps_in[0][1] == 0
                 and self.irreps_out[0][1] == 0 and len(paths) == 1 and out_layout == "irreps"):
             k_, n_ = self.irreps_in[0][0], self.irreps_out[0][0]
             if k_ <= 64 and k_ % 4 == 0 and n_ % 64 == 0 and n_ >= 256:
                 self.wide = (k_, n_, self.alpha[0])
+            # narrow scalar layers (the hidden layers of the radial MLP, 64 -> 64): both y = x W and dx = g W^T are
+            # "reduce over <= a few 32-chunks into <= 64 outputs", which is what the streaming dx kernel computes
+            self.narrow = None
+            if k_ % 32 == 0 and n_ % 32 == 0 and k_ <= 64 and n_ <= 64:
+                self.narrow = (k_, n_, self.alpha[0])
         self.max_mul_in = max(m for m, _, _ in self.irreps_in)
         self.max_mul_out = max(m for m, _, _ in self.irreps_out)
         self.max_d = max(2 * l + 1 for _, l, _ in self.irreps_out)

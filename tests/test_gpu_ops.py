@@ -373,6 +373,34 @@ def test_wide_radial_layer_matches_fp64_and_general_kernel(cuda, K, N, rows):
         assert _rel(got_g.double(), want) < 5e-6
 
 
+@pytest.mark.parametrize("K,N,rows", [(64, 64, 5000), (32, 64, 4133), (64, 32, 9001)])
+def test_narrow_radial_layers_through_the_streaming_kernel(cuda, K, N, rows):
+    """the hidden layers of the radial MLP on very large edge sets: y = x W and dx = g W^T both run the streaming
+    (TMEM-operand) dx kernel with the weight image packed in the matching orientation"""
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import LinearPlan
+
+    g = torch.Generator().manual_seed(5)
+    plan = LinearPlan(f"{K}x0e", f"{N}x0e", scale=0.9)
+    assert plan.narrow == (K, N, plan.alpha[0])
+    x = torch.randn(rows, K, generator=g).to(cuda)
+    w = torch.randn(K * N, generator=g).to(cuda)
+    gy = torch.randn(rows, N, generator=g).to(cuda)
+    old = ops.NARROW_MIN_ROWS[0]
+    try:
+        ops.NARROW_MIN_ROWS[0] = 1024
+        assert ops._narrow_ok(plan, rows)
+        y, dx = ops.irrep_linear(x, w, plan.handle), ops.irrep_linear_bwd_x(gy, w, plan.handle)
+        ops.NARROW_MIN_ROWS[0] = 1 << 30
+        y0, dx0 = ops.irrep_linear(x, w, plan.handle), ops.irrep_linear_bwd_x(gy, w, plan.handle)
+    finally:
+        ops.NARROW_MIN_ROWS[0] = old
+    a = 0.9 / K ** 0.5
+    W = w.double().view(K, N)
+    for got, got0, want in ((y, y0, a * x.double() @ W), (dx, dx0, a * gy.double() @ W.t())):
+        assert _rel(got.double(), want) < 5e-6 and _rel(got0.double(), want) < 5e-6
+
+
 @pytest.mark.parametrize("irr_in,irr_out,layout", [
     ("8x0e+8x1o+8x2e", "8x0e+8x1o+8x2e", "irreps"), ("8x0e+8x1o+8x2e", "8x0e+8x1o+8x2e", "channel"),
     ("32x0e+32x1o", "32x0e", "irreps"), ("128x0e+128x1o+128x2e+128x3o", "128x0e+128x1o+128x2e+128x3o", "channel"),
