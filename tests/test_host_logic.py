@@ -154,6 +154,63 @@ def test_linear_plan_matches_oracle_layout():
     assert ElementLinearPlan("4x0e+4x1o+4x2e", 4, "4x0e+4x1o+4x2e").weight_numel == ref.weight_numel == 192
 
 
+def _run_gemm_table(probs, A, B, C, M_runtime):
+    """plain-numpy executor of a pml_gemm_problem table (the semantics both GEMM kernels implement)"""
+    for p in probs:
+        M = M_runtime if p.M < 0 else p.M
+        for z in range(p.nbatch):
+            acc = np.zeros((M, p.N))
+            for c in range(p.nchunks):
+                K = M_runtime if p.kc[c] < 0 else p.kc[c]
+                a_idx = p.a_off[c] + z * p.a_bs + np.arange(M)[:, None] * p.a_rs + np.arange(K)[None, :] * p.a_cs
+                b_idx = p.b_off[c] + z * p.b_bs + np.arange(K)[:, None] * p.b_rs + np.arange(p.N)[None, :] * p.b_cs
+                acc += p.cscale[c] * (A[a_idx] @ B[b_idx])
+            c_idx = p.c_off + z * p.c_bs + np.arange(M)[:, None] * p.c_rs + np.arange(p.N)[None, :] * p.c_cs
+            if p.accumulate or (p.c_bs == 0 and p.nbatch > 1):
+                np.add.at(C, c_idx, p.alpha * acc)
+            else:
+                C[c_idx] = p.alpha * acc
+
+
+def test_linear_plan_component_major_tables_address_the_same_elements():
+    """LinearPlan(in_layout="component") (the layout K4 writes for MACE's per-irrep linear): forward, dx and dW tables
+    executed in numpy on a component-major input equal the irreps-layout tables on the e3nn-ordered input"""
+    from physicsml_b200 import so3
+    from physicsml_b200.plans import LinearPlan
+
+    rng = np.random.default_rng(9)
+    irr_in, irr_out, n = "6x0e+6x0e+6x1o+6x1o+6x1o+6x2e", "6x0e+6x1o+6x2e", 5
+    pe = LinearPlan(irr_in, irr_out, scale=0.7)
+    pc = LinearPlan(irr_in, irr_out, scale=0.7, in_layout="component")
+    assert pe.weight_numel == pc.weight_numel
+    x = rng.standard_normal((n, pe.d_in))
+    xc, off = np.empty_like(x), 0
+    for m, l, _ in so3.parse_irreps(irr_in):  # [mul, 2l+1] -> [2l+1, mul] inside every block
+        d = 2 * l + 1
+        xc[:, off:off + m * d] = x[:, off:off + m * d].reshape(n, m, d).transpose(0, 2, 1).reshape(n, m * d)
+        off += m * d
+    w = rng.standard_normal(pe.weight_numel)
+    g = rng.standard_normal((n, pe.d_out))
+    ye, yc = np.zeros(n * pe.d_out), np.zeros(n * pe.d_out)
+    _run_gemm_table(pe._fwd, x.ravel(), w, ye, n)
+    _run_gemm_table(pc._fwd, xc.ravel(), w, yc, n)
+    assert np.abs(ye).max() > 0 and np.allclose(ye, yc, rtol=0, atol=1e-12)
+    dxe, dxc = np.zeros(n * pe.d_in), np.zeros(n * pe.d_in)
+    _run_gemm_table(pe._bwd_x, g.ravel(), w, dxe, n)
+    _run_gemm_table(pc._bwd_x, g.ravel(), w, dxc, n)
+    back, off = np.empty((n, pe.d_in)), 0
+    dxc = dxc.reshape(n, -1)
+    for m, l, _ in so3.parse_irreps(irr_in):  # component-major cotangent -> e3nn order
+        d = 2 * l + 1
+        back[:, off:off + m * d] = dxc[:, off:off + m * d].reshape(n, d, m).transpose(0, 2, 1).reshape(n, m * d)
+        off += m * d
+    assert np.allclose(dxe.reshape(n, -1), back, rtol=0, atol=1e-12)
+    dwe, dwc = np.zeros(pe.weight_numel), np.zeros(pe.weight_numel)
+    _run_gemm_table(pe._bwd_w, x.ravel(), g.ravel(), dwe, n)
+    _run_gemm_table(pc._bwd_w, xc.ravel(), g.ravel(), dwc, n)
+    assert np.abs(dwe).max() > 0 and np.allclose(dwe, dwc, rtol=0, atol=1e-12)
+
+
 def test_no_cpu_fallback():
     from physicsml_b200 import neighbour_list, ops
 
