@@ -211,6 +211,30 @@ def test_linear_plan_component_major_tables_address_the_same_elements():
     assert np.abs(dwe).max() > 0 and np.allclose(dwe, dwc, rtol=0, atol=1e-12)
 
 
+def test_gemm_scheduling_helpers_and_grad_pruning_flag():
+    """host-side scheduling of the grouped GEMM (whole waves, no nearly empty extra wave) and the context manager that
+    switches weight gradients off for the force pass"""
+    from physicsml_b200 import ops
+
+    assert ops._tc_slots(128, False) == 296 and ops._tc_slots(64, False) == 444 and ops._tc_slots(64, True) == 296
+    # dW of the wide radial layer: 10 column tiles on two waves of 296 slots -> 59 splits (590 CTAs), not 60 (600)
+    assert ops._splitk_for(41570, 10, 2 * ops._tc_slots(128, False)) == 59
+    assert ops._splitk_for(41570, 4, ops._tc_slots(64, False)) == 111
+    assert ops._splitk_for(100, 10, 592) == 1  # never fewer than 64 k per CTA
+    sk = ops._splitk_rows(325, 1280, 296)  # 325 row tiles on 296 slots: split the long reduction
+    assert 2 <= sk <= 8 and 1280 // sk >= 128
+    assert ops._splitk_rows(3000, 1280, 296) == 1 and ops._splitk_rows(325, 128, 296) == 1
+    assert ops._PARAM_GRADS[0] is True
+    with pytest.raises(RuntimeError):
+        with ops.input_grads_only():
+            assert ops._PARAM_GRADS[0] is False
+            with ops.input_grads_only():
+                assert ops._PARAM_GRADS[0] is False
+            assert ops._PARAM_GRADS[0] is False
+            raise RuntimeError("boom")
+    assert ops._PARAM_GRADS[0] is True
+
+
 def test_no_cpu_fallback():
     from physicsml_b200 import neighbour_list, ops
 
