@@ -444,12 +444,8 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
         k, nn, alpha = pl.narrow  # dx = g W^T: reduce over nn, W[o = k index, r = nn index] at w[o*nn + r]
         return _stream_reduce(g, w, n, nn, k, nn, 1, alpha)
     if _wide_ok(pl, n):
-        k, nn, alpha = pl.wide
-        dx = _new_empty(g, n, pl.d_in)
-        image = torch.empty(((nn + 63) // 64) * 2 * 64 * 64, device=w.device, dtype=torch.float32)
-        _call("pml_wide_pack_wt", _p(w), nn, 1, k, nn, _p(image), _stream())
-        _call("pml_wide_bwd_x", _p(g), nn, nn, _p(image), _p(dx), k, k, n, alpha, _stream())
-        return dx
+        k, nn, alpha = pl.wide  # same reduction as the narrow case, over the wide dimension
+        return _stream_reduce(g, w, n, nn, k, nn, 1, alpha)
     name = _gemm_name(n)
     sk = 1
     if name.endswith("_tc") and pl.max_k_bwd_x >= 256:
