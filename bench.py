@@ -1,12 +1,15 @@
 #!/usr/bin/env python
-"""Benchmark of the MACE hot path (BASELINE.json metric: MACE energy+forces atoms/s; fused-edge-kernel % HBM roofline).
+"""Benchmark of the MACE / NequIP message-passing hot path (BASELINE.json metric: MACE energy+forces atoms/s at
+1/2/4/8 B200; fused-edge-kernel % HBM roofline).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own code on the host CPU cores
 
-Workload at every N: configs[1] of BASELINE.json — MACE medium (128x0e+128x1o, lmax 3, correlation 3) TRAINING step on
-32 synthetic SPICE-like molecules (30-50 atoms) per GPU: forward, forces with create_graph, MSE(E)+MSE(F), backward,
-gradient all-reduce (NCCL, N > 1), Adam-amsgrad.  Weak scaling: per-GPU work is fixed.  Prints ONE JSON line on rank 0.
+Headline workload at every N: configs[1] of BASELINE.json — MACE medium (128x0e+128x1o, lmax 3, correlation 3) TRAINING
+step on 32 synthetic SPICE-like molecules (30-50 atoms) per GPU: forward, forces with create_graph, MSE(E)+MSE(F),
+backward, gradient all-reduce (NCCL, N > 1), Adam-amsgrad.  Weak scaling: per-GPU work is fixed.  The other four
+BASELINE configs are measured in the same run and printed under ``other_configs`` (training configs at every N,
+inference configs at N = 1).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -22,7 +25,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "mace_medium_spice_train"
+OTHERS = ["mace_small_qm9", "nequip_organic", "water_box_infer", "mace_large_bulk_train"]
 METRIC = "mace_energy_forces_atoms_per_sec"
+PARITY_MOLECULES = 4  # sub-batch the GPU arm is checked on against the CPU oracle inside the benchmark run
 
 
 def _peaks():
@@ -31,6 +36,17 @@ def _peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def shared_config(world: int = 1) -> dict:
+    """the `config` object both arms print (same workload, same step; the driver compares them)"""
+    from physicsml_b200 import workloads as wl
+
+    data, _, _, _ = wl.make_batch(WORKLOAD, 0)
+    return {"workload": WORKLOAD,
+            "step": "training: fwd + forces(create_graph) + MSE(E)+MSE(F) + bwd + allreduce + Adam(amsgrad)",
+            "molecules_per_gpu": wl.CONFIGS[WORKLOAD]["n_mol"], "atoms_per_gpu": int(data["coordinates"].shape[0]),
+            "edges_per_gpu": int(data["edge_index"].shape[1])}
 
 
 class ClockSampler:
@@ -70,28 +86,51 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
+        # median over the samples taken while the GPU was clocked up (idle samples between legs are not "under load")
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(n_mol: int, steps: int, warmup: int):
-    """Reference algorithm (oracle restatement of the reference's PyTorch/e3nn path) on the host cores: same model,
-    same training step, on a bounded sample of the workload (n_mol molecules).  Returns (atoms/s, cores, sample str)."""
+# CPU legs: the reference's own code (oracle/_ref, unmodified sources over the e3nn shims) or, if that was not staged,
+# the oracle port
+# ----------------------------------------------------------------------------------------------------------------------
+def _cpu_model(name: str):
+    """-> (model, kind): the reference's own modules when oracle/_ref (or /root/reference) is present, else the port"""
     import torch
 
-    from oracle.ref_model import RefPooledMACE
+    from physicsml_b200 import workloads as wl
+
+    cfg = wl.CONFIGS[name]
+    try:
+        from oracle import reference_models as rm
+
+        if rm.available():
+            kw = dict(cfg["model"])
+            kw["avg_num_neighbours"] = wl.mean_degree(name)
+            torch.manual_seed(0)
+            cls = rm.ReferencePooledMACE if cfg["family"] == "mace" else rm.ReferencePooledNequip
+            return cls(cfg["mlp"], **kw), "reference"
+    except Exception as exc:  # fall back to the port, loudly
+        print(f"[bench] reference sources unavailable ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+    return wl.build_model(name, oracle=True), "port"
+
+
+def cpu_reference_step_rate(n_mol, steps: int, warmup: int, budget_s: float | None = None):
+    """The reference's training step on the host cores, same model, same step, on `n_mol` molecules of the workload
+    (None = the full batch).  -> (atoms/s, cores, sample str, ms per step, kind)"""
+    import torch
+
     from physicsml_b200 import workloads as wl
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    data, targets, kw, mlp = wl.make_batch(WORKLOAD, 0, n_mol=n_mol)
-    kw["avg_num_neighbours"] = wl.mean_degree(WORKLOAD)
-    torch.manual_seed(0)
-    model = RefPooledMACE(mlp_irreps=mlp, **kw)
+    data, targets, _, _ = wl.make_batch(WORKLOAD, 0, n_mol=n_mol)
+    model, kind = _cpu_model(WORKLOAD)
     opt = wl.make_optimizer(model)
     n_atoms = data["coordinates"].shape[0]
     times = []
+    t_start = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
@@ -101,36 +140,65 @@ def cpu_reference_step_rate(n_mol: int, steps: int, warmup: int):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        if budget_s is not None and times and time.perf_counter() - t_start > budget_s:
+            break
     per = sum(times) / len(times)
-    sample = f"{n_mol} of 32 molecules ({n_atoms} atoms, {data['edge_index'].shape[1]} edges), {steps} timed training steps, fp32, {cores} threads"
-    return n_atoms / per, cores, sample, per * 1e3
+    total = wl.CONFIGS[WORKLOAD]["n_mol"]
+    sample = (f"{n_mol or total} of {total} molecules ({n_atoms} atoms, {data['edge_index'].shape[1]} edges), {len(times)} timed "
+              f"training steps, fp32, {cores} threads")
+    return n_atoms / per, cores, sample, per * 1e3, kind
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_mol = args.ref_molecules
-    rate, cores, sample, ms = cpu_reference_step_rate(n_mol, max(1, args.steps), max(1, args.warmup))
+    n_mol = args.ref_molecules if args.ref_molecules > 0 else None
+    rate, cores, sample, ms, kind = cpu_reference_step_rate(n_mol, max(1, args.steps), max(1, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "atoms/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": rate, "unit": "atoms/s", "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": shared_config(),
+        "cpu_baseline": {"value": rate, "unit": "atoms/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def edge_kernel_bytes(pl, n_nodes: int, n_edges: int, mask=None) -> int:
+    """ALGORITHMIC bytes of one fused edge-kernel launch: every tensor once.
+    forward: E*(4*P*C + 4*S + 16) + N*4*C*(DIN + DOUT).  cotangent with outputs mask = (dh, dY, dR): reads Y, the
+    indices, h and g rows, R unless only dR is wanted; writes the requested cotangents."""
+    PC, S = pl.NP * pl.C, pl.NSH
+    if mask is None:
+        return n_edges * (4 * PC + 4 * S + 16) + n_nodes * 4 * pl.C * (pl.DIN + pl.DOUT)
+    need_h, need_y, need_r = mask
+    b = n_edges * (4 * S + 16) + n_nodes * 4 * pl.C * (pl.DIN + pl.DOUT)
+    if need_h or need_y:
+        b += n_edges * 4 * PC
+    if need_r:
+        b += n_edges * 4 * PC
+    if need_y:
+        b += n_edges * 4 * S
+    if need_h:
+        b += n_nodes * 4 * pl.C * pl.DIN
+    return b
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-molecules", type=int, default=4, help="bounded sample size of the CPU reference legs")
+    ap.add_argument("--ref-molecules", type=int, default=0,
+                    help="molecules of the batch the --impl reference arm runs (0 = the full 32-molecule batch)")
+    ap.add_argument("--cpu-baseline-molecules", type=int, default=PARITY_MOLECULES,
+                    help="bounded sample of the cpu_baseline leg inside the GPU arm's run")
+    ap.add_argument("--configs", default="all", help="'all', 'headline' or a comma-separated list of other_configs to run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph")
@@ -144,9 +212,9 @@ def main() -> None:
     import torch
     import torch.distributed as dist
 
-    from physicsml_b200 import ops, plans
+    from physicsml_b200 import ops, parallel, plans
     from physicsml_b200 import workloads as wl
-    from physicsml_b200.mace import PooledMACEModule
+    from physicsml_b200.graphs import GraphedEval, GraphedStep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -159,86 +227,20 @@ def main() -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False
-
-    data, targets, kw, mlp = wl.make_batch(WORKLOAD, rank)
-    kw["avg_num_neighbours"] = wl.mean_degree(WORKLOAD)
-    torch.manual_seed(0)
-    model = PooledMACEModule(mlp_irreps=mlp, **kw).to(dev)
-    use_graph = not args.eager
-    opt = wl.make_optimizer(model, capturable=use_graph)
-    params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
-    n_atoms = data["coordinates"].shape[0]
-    n_edges = data["edge_index"].shape[1]
-
-    # host (pinned) copies for the end-to-end leg, device-resident copies for the kernel-path leg
-    host = {k: (v.pin_memory() if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in data.items()}
-    host_t = {k: v.pin_memory() for k, v in targets.items()}
-    d_dev = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in data.items()}
-    t_dev = {k: v.to(dev) for k, v in targets.items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v) and v.dim() > 0)
-    h2d += sum(v.numel() * v.element_size() for v in host_t.values())
-    loss_host = torch.zeros(1).pin_memory()
-
-    def allreduce_grads():
-        if world == 1:
-            return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(world)
-        off = 0
-        for p in params:
-            n = p.numel()
-            p.grad.copy_(flat[off : off + n].view_as(p))
-            off += n
-
-    def step(d, t):
-        opt.zero_grad(set_to_none=True)
-        loss = wl.training_loss(model, d, t)
-        loss.backward()
-        allreduce_grads()
-        opt.step()
-        return loss
-
-    graphed = None
-    if use_graph:
-        from physicsml_b200.graphs import GraphedStep
-
-        try:
-            graphed = GraphedStep(model, opt, d_dev, t_dev, wl.training_loss, after_backward=allreduce_grads, warmup=3)
-        except Exception as exc:  # capture is an optimisation: report and continue eagerly
-            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
-            graphed = None
-            opt = wl.make_optimizer(model, capturable=False)
-
-    def step_resident():
-        if graphed is not None:
-            return graphed()
-        return step(d_dev, t_dev)
-
-    def step_e2e():
-        if graphed is not None:
-            graphed.load(host, host_t)  # pinned host -> static device buffers
-            loss = graphed()
-        else:
-            d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()}
-            t = {k: v.to(dev, non_blocking=True) for k, v in host_t.items()}
-            loss = step(d, t)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
-        return float(loss_host[0])
-
+    peak, which = _peaks()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    keep_alive = []  # captured graphs holding NCCL work are dropped explicitly at shutdown
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, with_kernel_timing=False):
+    def timed(fn, steps, warmup, kernel_timing=False):
         for _ in range(warmup):
             fn()
         barrier()
-        if with_kernel_timing:
+        if kernel_timing:
             ops.enable_kernel_timing(["pml_tp_fwd", "pml_tp_bwd"])
         n0 = ops.LAUNCHES[0]
         evs = []
@@ -250,7 +252,7 @@ def main() -> None:
             e1.record()
             evs.append((e0, e1))
         barrier()
-        launches = ops.LAUNCHES[0] - n0
+        launches = (ops.LAUNCHES[0] - n0) // max(1, steps)
         ms = sum(a.elapsed_time(b) for a, b in evs) / steps
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -258,36 +260,210 @@ def main() -> None:
             ms = float(t[0])
         return ms, launches
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, launches = timed(step_resident, args.steps, args.warmup, with_kernel_timing=(graphed is None))
-    clocks = sampler.stop() if sampler is not None else None
-    if graphed is not None:
+    def edge_kernel_table(n_atoms, n_edges, steps):
+        """per (kernel, signature, requested cotangents): launches per step, average launch time (CUDA events around each
+        launch of the eager pass of the SAME step), algorithmic bytes, achieved GB/s, fraction of the measured HBM peak"""
+        agg: dict = {}
+        for name, recs in ops.KERNEL_TIMING.items():
+            for tag, a, b in recs:
+                agg.setdefault((name, tag), []).append(a.elapsed_time(b))
+        ops.enable_kernel_timing([])
+        rows = []
+        for (name, tag), ts in agg.items():
+            spec, mask = (tag, None) if name == "pml_tp_fwd" else (tag[0], tuple(bool(x) for x in tag[1:]))
+            pl = next(p for p in plans._PLANS if getattr(p, "spec_id", None) == spec and hasattr(p, "NP") and hasattr(p, "DIN"))
+            byts = edge_kernel_bytes(pl, n_atoms, n_edges, mask)
+            avg = sum(ts) / len(ts)
+            ach = byts / (avg * 1e-3) / 1e9
+            rows.append({"kernel": "tp_fwd" if mask is None else "tp_bwd", "signature": pl.spec.key, "channels": pl.C,
+                         "cotangents": None if mask is None else "".join(c for c, m in zip("hYR", mask) if m),
+                         "launches_per_step": len(ts) / steps, "avg_launch_ms": avg, "ms_per_step": sum(ts) / steps,
+                         "algorithmic_bytes_per_launch": byts, "achieved_gbs": ach, "frac": ach / peak})
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        return rows
+
+    def run_config(name: str, steps: int, warmup: int, headline: bool) -> dict:
+        cfg = wl.CONFIGS[name]
+        training = cfg["kind"] == "training"
+        data, targets, _, _ = wl.make_batch(name, rank)
+        model = wl.build_model(name).to(dev)
+        if not training:
+            model.eval()
+        res: dict = {"kind": cfg["kind"], "family": cfg["family"]}
+        d_dev = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in data.items()}
+        nl_ms = None
+        if "edge_index" not in d_dev:  # the water box: edges come from the GPU neighbour list (timed by itself)
+            from physicsml_b200.neighbour_list import radius_graph
+
+            rc = cfg["model"]["cut_off"]
+            for _ in range(2):
+                ei, sh, plan = radius_graph(d_dev["coordinates"], rc, pbc=(True, True, True), cell=d_dev["cell"])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ei, sh, plan = radius_graph(d_dev["coordinates"], rc, pbc=(True, True, True), cell=d_dev["cell"])
+            torch.cuda.synchronize()
+            nl_ms = (time.perf_counter() - t0) / 5 * 1e3
+            d_dev.update(edge_index=ei, cell_shift_vector=sh)
+            data = dict(data, edge_index=ei.cpu(), cell_shift_vector=sh.cpu())
+        t_dev = {k: v.to(dev) for k, v in targets.items()}
+        n_atoms, n_edges = int(d_dev["coordinates"].shape[0]), int(d_dev["edge_index"].shape[1])
+        host = {k: (v.pin_memory() if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in data.items()}
+        host_t = {k: v.pin_memory() for k, v in targets.items()}
+        h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v) and v.dim() > 0)
+        use_graph = (not args.eager) and n_atoms <= 6000  # large single structures are not launch-bound
+
+        if training:
+            h2d += sum(v.numel() * v.element_size() for v in host_t.values())
+            reducer = parallel.GradientReducer([p for p in model.parameters() if p.requires_grad and p.numel() > 0]) if world > 1 else None
+            opt = wl.make_optimizer(model, grad_scale=1.0 / world)
+            if reducer is not None:
+                reducer.attach(opt)
+
+            def step(d, t):
+                opt.zero_grad(set_to_none=True)
+                loss = wl.training_loss(model, d, t)
+                loss.backward()
+                if reducer is not None:
+                    reducer.finish()
+                opt.step()
+                return loss.detach()
+
+            graphed = None
+            if use_graph:
+                try:
+                    graphed = GraphedStep(model, opt, d_dev, t_dev, wl.training_loss,
+                                          after_backward=(reducer.finish if reducer is not None else None), warmup=3)
+                    keep_alive.append(graphed)
+                except Exception as exc:  # capture is an optimisation: report and continue eagerly
+                    print(f"[bench] {name}: CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+                    graphed = None
+
+            def resident():
+                return graphed() if graphed is not None else step(d_dev, t_dev)
+
+            out_host = torch.zeros(1).pin_memory()
+
+            def e2e():
+                if graphed is not None:
+                    graphed.load(host, host_t)  # pinned host -> static device buffers
+                    loss = graphed()
+                else:
+                    d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()}
+                    t = {k: v.to(dev, non_blocking=True) for k, v in host_t.items()}
+                    loss = step(d, t)
+                out_host.copy_(loss.reshape(1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
+                return float(out_host[0])
+
+            d2h = 4
+
+            def eager():
+                return step(d_dev, t_dev)
+        else:
+            graphed = None
+            if use_graph:
+                try:
+                    graphed = GraphedEval(model, d_dev, wl.energy_forces, warmup=3)
+                    keep_alive.append(graphed)
+                except Exception as exc:
+                    print(f"[bench] {name}: CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+                    graphed = None
+            d_plain = dict(d_dev)
+            if nl_ms is not None:
+                d_plain["_edge_plan"] = plan
+
+            def resident():
+                return graphed() if graphed is not None else wl.energy_forces(model, d_plain)
+
+            G = int(data["num_graphs"])
+            e_host = torch.zeros(G, 1).pin_memory()
+            f_host = torch.zeros(n_atoms, 3).pin_memory()
+
+            def e2e():
+                if graphed is not None:
+                    graphed.load(host)
+                    e, f = graphed()
+                elif nl_ms is not None:  # single structure from host coordinates: copy, neighbour list, evaluate
+                    from physicsml_b200.neighbour_list import radius_graph
+
+                    d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()
+                         if k not in ("edge_index", "cell_shift_vector")}
+                    ei2, sh2, plan2 = radius_graph(d["coordinates"], cfg["model"]["cut_off"], pbc=(True, True, True), cell=d["cell"])
+                    d.update(edge_index=ei2, cell_shift_vector=sh2, _edge_plan=plan2)
+                    e, f = wl.energy_forces(model, d)
+                else:
+                    d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()}
+                    e, f = wl.energy_forces(model, d)
+                e_host.copy_(e, non_blocking=True)
+                f_host.copy_(f, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return e_host
+
+            d2h = 4 * G + 12 * n_atoms
+            if nl_ms is not None:  # the e2e leg of the box ships coordinates, species, cell; edges are built on the device
+                h2d -= sum(host[k].numel() * host[k].element_size() for k in ("edge_index", "cell_shift_vector"))
+
+            def eager():
+                return wl.energy_forces(model, d_plain)
+
+        sampler = ClockSampler(local) if (rank == 0 and headline) else None
+        ms_dev, launches = timed(resident, steps, warmup)
+        if sampler is not None:
+            res["clocks"] = sampler.stop()
         # a replayed graph cannot carry per-kernel events: time the fused edge kernels in an eager pass of the SAME step
         # (same inputs, same kernels), and count the kernels of one step the same way
-        opt_e = wl.make_optimizer(model, capturable=False)
-        opt_saved, opt = opt, opt_e
-        _, launches = timed(lambda: step(d_dev, t_dev), args.steps, 3, with_kernel_timing=True)
-        opt = opt_saved
-    # per-kernel times of the fused edge kernels, recorded live inside the timed region
-    ktimes: dict = {}
-    for name, recs in ops.KERNEL_TIMING.items():
-        for spec, a, b in recs:
-            ktimes.setdefault((name, spec), []).append(a.elapsed_time(b))
-    ops.enable_kernel_timing([])
-    ms_e2e = float("nan")
-    if not args.no_e2e:
-        ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+        _, launches = timed(eager, min(steps, 10), 2, kernel_timing=True)
+        table = edge_kernel_table(n_atoms, n_edges, min(steps, 10))
+        ms_e2e = None
+        if not args.no_e2e:
+            ms_e2e, _ = timed(e2e, steps, warmup)
+        total_atoms = float(n_atoms)
+        if world > 1:
+            t = torch.tensor([float(n_atoms), float(n_edges)], device=dev)
+            per_rank = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(per_rank, t)
+            total_atoms = float(sum(x[0] for x in per_rank))
+            res["per_rank"] = [{"atoms": int(x[0]), "edges": int(x[1])} for x in per_rank]
+            if training and reducer is not None:
+                res["allreduce"] = reducer.describe()
+        res.update({"ms_per_step": ms_dev, "atoms_per_s": total_atoms / (ms_dev * 1e-3), "atoms": n_atoms, "edges": n_edges,
+                    "total_atoms": total_atoms, "cuda_graph": graphed is not None, "gpu_launches": launches,
+                    "e2e_ms_per_step": ms_e2e, "e2e_atoms_per_s": (total_atoms / (ms_e2e * 1e-3)) if ms_e2e else None,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "edge_kernels": table})
+        if nl_ms is not None:
+            res["neighbour_list_ms"] = nl_ms
+            res["atoms_per_s_with_neighbour_list"] = total_atoms / ((ms_dev + nl_ms) * 1e-3)
+        if headline and rank == 0 and not args.no_cpu_baseline and world == 1:
+            res["parity"] = parity_vs_oracle(name, model, data, targets, dev)
+        return res
 
-    total_atoms = n_atoms
-    if world > 1:
-        t = torch.tensor([float(n_atoms)], device=dev)
-        dist.all_reduce(t)
-        total_atoms = float(t[0])
+    def parity_vs_oracle(name, model, data, targets, dev):
+        """step-0 check inside the benchmark run: the GPU model vs the CPU oracle (same weights) on the first
+        PARITY_MOLECULES molecules of the timed batch: energies, forces and the training loss"""
+        ref, kind = _cpu_model(name)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        ref.load_state_dict(sd, strict=False)
+        n_mol = PARITY_MOLECULES
+        keep = data["batch"] < n_mol
+        n = int(keep.sum())
+        em = data["edge_index"][0] < n
+        sub = {"coordinates": data["coordinates"][:n], "node_attrs": data["node_attrs"][:n], "batch": data["batch"][:n],
+               "num_graphs": torch.tensor(n_mol), "edge_index": data["edge_index"][:, em]}
+        sub_t = {"energy": targets["energy"][:n_mol], "forces": targets["forces"][:n]}
+        e_ref, f_ref = wl.energy_forces(ref, sub)
+        l_ref = wl.training_loss(ref, sub, sub_t)
+        sub_d = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in sub.items()}
+        e, f = wl.energy_forces(model, sub_d)
+        l = wl.training_loss(model, sub_d, {k: v.to(dev) for k, v in sub_t.items()})
+        scale = e_ref.abs().max().item()
+        return {"against": kind, "molecules": n_mol, "atoms": n, "energy_rel": (e.cpu() - e_ref).abs().max().item() / scale,
+                "force_abs": (f.cpu() - f_ref).abs().max().item(), "loss_rel": abs(l.item() - l_ref.item()) / abs(l_ref.item()),
+                "tolerance": {"energy_rel": 1e-5, "force_abs": 1e-4}}
 
     def shutdown():
-        """Leave the process group without hanging: the captured step holds NCCL work, so drop the graph first; a
+        """Leave the process group without hanging: the captured steps hold NCCL work, so drop the graphs first; a
         watchdog forces the exit if the communicator teardown still blocks (the JSON line is already flushed)."""
-        nonlocal graphed
         if world == 1:
             return
         import gc
@@ -295,67 +471,69 @@ def main() -> None:
 
         sys.stdout.flush()
         threading.Timer(30.0, lambda: os._exit(0)).start()
-        graphed = None
+        keep_alive.clear()
         gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
         os._exit(0)
 
+    head = run_config(WORKLOAD, args.steps, args.warmup, headline=True)
+    others: dict = {}
+    wanted = OTHERS if args.configs == "all" else ([] if args.configs == "headline" else args.configs.split(","))
+    for name in wanted:
+        if world > 1 and wl.CONFIGS[name]["kind"] != "training":
+            continue  # single-structure / batched inference is reported at one GPU (replicas only)
+        try:
+            r = run_config(name, min(args.steps, 10), 3, headline=False)
+        except Exception as exc:  # never lose the headline line to a secondary workload
+            r = {"error": f"{type(exc).__name__}: {exc}"}
+            if world > 1:
+                raise
+        others[name] = r
+        torch.cuda.empty_cache()
+
     if rank != 0:
         shutdown()
         return
 
-    # roofline of the dominant fused edge kernel (forward, the layer with the most traffic)
-    peak, which = _peaks()
+    # headline roofline: the fused edge kernel that takes the most time of the step (forward or cotangent)
     roof = None
-    best = None
-    for (name, spec), ts in ktimes.items():
-        if name != "pml_tp_fwd":
-            continue
-        pl = next(p for p in plans._PLANS if getattr(p, "spec_id", None) == spec and hasattr(p, "NP") and hasattr(p, "DIN"))
-        # bytes_fwd = E*(4*P*C + 4*S + 16) + N*4*(d_in + d_tp)
-        byts = n_edges * (4 * pl.NP * pl.C + 4 * pl.NSH + 16) + n_atoms * 4 * (pl.C * pl.DIN + pl.C * pl.DOUT)
-        avg_ms = sum(ts) / len(ts)
-        if best is None or byts > best[0]:
-            best = (byts, avg_ms, len(ts), pl.spec.key)
-    if best is not None:
-        byts, avg_ms, n, key = best
-        ach = byts / (avg_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the committed ncu --set full
-        # capture (profiles/README.md says which command produced it); null when no capture of this signature exists
+    if head["edge_kernels"]:
+        top = head["edge_kernels"][0]
         traffic, tsrc = None, None
         tpath = os.path.join(ROOT, "profiles", "k4_dram_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                rec = json.load(f).get(f"{WORKLOAD}:tp_fwd:{key}")
+                rec = json.load(f).get(f"{WORKLOAD}:{top['kernel']}:{top['signature']}" + (f":{top['cotangents']}" if top["cotangents"] else ""))
             if rec:
                 traffic, tsrc = rec["dram_bytes_per_launch"], rec["source"]
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": tsrc, "kernel": f"tp_fwd_pipe_kernel<{key}>", "algorithmic_bytes_per_launch": byts,
-                "avg_launch_ms": avg_ms, "launches_timed": n, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})"}
-    kernel_share = {f"{n}[{s}]": {"launches": len(ts), "total_ms_per_step": sum(ts) / args.steps} for (n, s), ts in ktimes.items()}
+        roof = {"bound": "hbm", "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
+                "traffic": traffic, "traffic_source": tsrc,
+                "kernel": f"{top['kernel']}<{top['signature']}>" + (f" cotangents {top['cotangents']}" if top["cotangents"] else ""),
+                "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "avg_launch_ms": top["avg_launch_ms"],
+                "launches_per_step": top["launches_per_step"], "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                "all_edge_kernels": [{k: r[k] for k in ("kernel", "signature", "cotangents", "launches_per_step", "avg_launch_ms", "frac")}
+                                     for r in head["edge_kernels"]]}
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
-        rate, cores, sample, _ = cpu_reference_step_rate(args.ref_molecules, 2, 1)
-        cpu = {"value": rate, "unit": "atoms/s", "cores": cores, "kind": "port", "sample": sample}
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only, on a bounded sample
+        rate, cores, sample, _, kind = cpu_reference_step_rate(args.cpu_baseline_molecules, 2, 1)
+        cpu = {"value": rate, "unit": "atoms/s", "cores": cores, "kind": kind, "sample": sample}
 
+    config = shared_config(world)
     line = {
-        "metric": METRIC, "value": total_atoms / (ms_dev * 1e-3), "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": "training: fwd + forces(create_graph) + MSE(E)+MSE(F) + bwd + allreduce + Adam(amsgrad, fused kernel)",
-                   "molecules_per_gpu": 32, "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "parallelism": f"dp{world}",
-                   "l2": "flushed between steps (256 MiB memset outside the per-step event pair)"},
-        "e2e": {"value": total_atoms / (ms_e2e * 1e-3), "unit": "atoms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e},
-        "gpu_launches": launches,
-        "cuda_graph": graphed is not None,
-        "clocks": clocks,
-        "roofline": roof,
-        "cpu_baseline": cpu,
-        "edge_kernels": kernel_share,
+        "metric": METRIC, "value": head["atoms_per_s"], "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "parallelism": f"dp{world}",
+        "l2": "flushed between steps (256 MiB memset outside the per-step event pair)",
+        "e2e": {"value": head["e2e_atoms_per_s"], "unit": "atoms/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": head["d2h_bytes_per_step"], "ms_per_step": head["e2e_ms_per_step"]},
+        "gpu_launches": head["gpu_launches"] * args.steps, "gpu_launches_per_step": head["gpu_launches"],
+        "cuda_graph": head["cuda_graph"], "clocks": head.get("clocks"), "roofline": roof, "cpu_baseline": cpu,
+        "parity": head.get("parity"), "per_rank": head.get("per_rank"), "allreduce": head.get("allreduce"),
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
     shutdown()

@@ -48,6 +48,12 @@ int pml_edge_featurise_bwd(const float* pos, const int* snd, const int* rcv, con
 int pml_edge_featurise_jvp(const float* pos, const int* snd, const int* rcv, const float* shift, const float* cell,
                            const float* bessel_w, float r_max, float prefactor, float w_scale, int p, int nb, int lmax,
                            const float* t, float* tY, float* tB, int E, pml_stream_t stream);
+/* Gradient w.r.t. trainable Bessel frequencies (nequip/modules/radial.py:9-19, mace/modules/radial.py:17-20):
+ * t == NULL: gw[n] += sum_e gB[e,n] dB_n/dw_n; t != NULL ([N,3]): gw[n] += sum_e gB[e,n] d2B_n/(dd dw_n) u.(t[r]-t[s])
+ * (the parameter gradient of the force pass / of its tangent map).  gw [nb] zero-initialised by the caller; nb <= 16. */
+int pml_bessel_weight_grad(const float* pos, const int* snd, const int* rcv, const float* shift, const float* cell,
+                           const float* bessel_w, float r_max, float prefactor, float w_scale, int p, int nb,
+                           const float* gB, const float* t, float* gw, int E, pml_stream_t stream);
 
 /* ---- K4: fused channelwise tensor product + gather + segmented scatter-sum ----------------------------------------
  * Replaces w_h[sender] -> conv_tp -> scatter (models/mace/modules/blocks.py:214-226; models/nequip/modules/interaction_block.py:95-96).
@@ -205,6 +211,31 @@ typedef struct {
 } pml_adam_chunk;
 int pml_adam_amsgrad(const pml_adam_tensor* tensors, const pml_adam_chunk* chunks, int nchunks, float* step, float lr,
                      float b1, float b2, float one_minus_b1, float one_minus_b2, float eps, float wd, pml_stream_t stream);
+/* Same update with per-tensor hyper-parameters and step counters: the reference builds one param group per parameter
+ * with its own weight_decay (models/mace/supervised/mace_module.py:131-157).  gscale multiplies the gradient first
+ * (1/world_size after a summed all-reduce).  steps: device table of the nsteps distinct counters, incremented first. */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* vmax;
+  long long n;
+  const float* step;
+  float lr, b1, b2, omb1, omb2, eps, wd, gscale;
+} pml_adam_tensor2;
+int pml_adam_amsgrad_groups(const pml_adam_tensor2* tensors, const pml_adam_chunk* chunks, int nchunks, float* const* steps,
+                            int nsteps, pml_stream_t stream);
+
+/* Gradient packing for the data-parallel all-reduce (the reference delegates it to Lightning DDP,
+ * lightning/model.py:159-163): flat[offset_t + i] = src_t ? src_t[i] : 0 for all tensors of a bucket in one launch
+ * (chunks of 4096 elements as for pml_adam_amsgrad; tables in device memory). */
+typedef struct {
+  const float* src;
+  long long offset;
+  long long n;
+} pml_pack_tensor;
+int pml_pack_f32(const pml_pack_tensor* tensors, const pml_adam_chunk* chunks, int nchunks, float* flat, pml_stream_t stream);
 
 /* Test utility: overwrite the shared memory of every SM with NaN (exposes kernels that read shared memory they never
  * wrote). */
@@ -215,6 +246,10 @@ int pml_pool_sum(const float* x, const long long* batch, float* out, int N, int 
 int pml_pool_gather(const float* g, const long long* batch, float* out, int N, int F, pml_stream_t stream);
 /* CSR row pointer over an int64 index vector (counts: zeroed scratch [N]) */
 int pml_csr_rowptr(const long long* idx, int* counts, int* rowptr, int E, int N, pml_stream_t stream);
+/* Edge ids grouped by an index vector, ascending inside every group (a stable counting sort: replaces the
+ * torch.argsort(stable=True) a scatter over an unsorted index needs; blocks.py:221 / interaction_block.py:96 leave the
+ * grouping to scatter_add's atomics).  cursor: zeroed scratch [N]; perm [E]. */
+int pml_csr_group(const long long* idx, const int* rowptr, int* cursor, int* perm, int E, int N, pml_stream_t stream);
 int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int E, pml_stream_t stream);
 /* [N, C*S] irreps layout <-> [N, C, S] (models/mace/modules/irreps_tools.py:47-67) */
 int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse, pml_stream_t stream);

@@ -1,8 +1,9 @@
-"""Import the reference's OWN hot-path source files, unmodified, from /root/reference over the oracle shims.
+"""Import the reference's OWN hot-path source files, unmodified, from /root/reference (or from the staged copy
+``oracle/_ref/src`` made by ``oracle/build_ref.py`` where /root/reference does not exist) over the oracle shims.
 
-TEST INFRASTRUCTURE ONLY.  Works only in the build container (``/root/reference`` does not exist on the GPU box);
-used to validate the standalone restatement in ``oracle/`` and by ``tests/golden/make_golden.py`` to generate
-the committed golden vectors.  Package ``__init__`` files of the reference are bypassed with stub packages because
+TEST / BASELINE INFRASTRUCTURE ONLY: used to validate the standalone restatement in ``oracle/``, by
+``tests/golden/make_golden.py`` to generate the committed golden vectors, and by ``bench.py --impl reference`` /
+``cpu_baseline`` to time the reference's own code on the host cores.  Package ``__init__`` files of the reference are bypassed with stub packages because
 ``src/physicsml/__init__.py:3`` imports a setuptools-scm generated ``version.py`` that does not exist in a source checkout
 and the model-level ``__init__`` files import molflux / lightning.
 """
@@ -13,7 +14,10 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = "/root/reference/src"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference checkout (build container) or, where that does not exist (GPU box), the staged copy of the same
+# unmodified files under oracle/_ref/ (oracle/build_ref.py)
+REFERENCE_SRC = "/root/reference/src" if os.path.isdir("/root/reference/src/physicsml") else os.path.join(_HERE, "_ref", "src")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 _STUB_PACKAGES = [
@@ -54,7 +58,7 @@ def _stub(name: str) -> None:
 def load(module: str):
     """e.g. load("physicsml.models.mace.modules.mace") -> the reference module object (unmodified source)."""
     if not available():
-        raise RuntimeError("/root/reference is not present on this machine")
+        raise RuntimeError("neither /root/reference nor oracle/_ref (python -m oracle.build_ref) is present on this machine")
     install_shims()
     for name in _STUB_PACKAGES:
         _stub(name)

@@ -98,6 +98,7 @@ SIGNATURES = {
     "pml_edge_featurise_fwd": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P],
     "pml_edge_featurise_bwd": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P],
     "pml_edge_featurise_jvp": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _I, _P, _P, _P, _I, _P],
+    "pml_bessel_weight_grad": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _I, _P, _P, _P, _I, _P],
     "pml_tp_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "pml_tp_bwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "pml_tp_fwd_ex": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
@@ -119,9 +120,12 @@ SIGNATURES = {
     "pml_gate": [_P, _P, _P, C.POINTER(GatePlanStruct), _I, _P, _P, _I, _P],
     "pml_debug_poison_smem": [_P],
     "pml_adam_amsgrad": [_P, _P, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P],
+    "pml_adam_amsgrad_groups": [_P, _P, _I, _P, _I, _P],
+    "pml_pack_f32": [_P, _P, _I, _P, _P],
     "pml_pool_sum": [_P, _P, _P, _I, _I, _P],
     "pml_pool_gather": [_P, _P, _P, _I, _I, _P],
     "pml_csr_rowptr": [_P, _P, _P, _I, _I, _P],
+    "pml_csr_group": [_P, _P, _P, _P, _I, _I, _P],
     "pml_split_edge_index": [_P, _P, _P, _I, _P],
     "pml_irreps_to_channel": [_P, _P, _LL, _I, _I, _I, _P],
     "pml_scan_i32": [_P, _P, _I, _P],

@@ -234,6 +234,63 @@ __global__ void __launch_bounds__(128) featurise_jvp_kernel(const float* __restr
   }
 }
 
+// Gradient w.r.t. the (trainable) Bessel frequencies bessel_w[n] (reference nequip/modules/radial.py:9-19, the NequIP
+// default; mace/modules/radial.py:17-20).  With w = bessel_w[n] * w_scale and B_n = pref sin(w d)/d f(d):
+//   t == null :  gw[n] += sum_e gB[e,n] * dB_n/dbw            = pref w_scale cos(w d) f
+//   t != null :  gw[n] += sum_e gB[e,n] * d2B_n/(dd dbw) * (u . (t[r] - t[s]))  with
+//                d2B_n/(dd dbw) = pref w_scale (cos(w d) f' - w sin(w d) f)
+// The second form is the parameter gradient of the force pass (gpos is linear in dB/dd) and of its tangent map.
+__global__ void __launch_bounds__(256) bessel_weight_grad_kernel(const float* __restrict__ pos, const int* __restrict__ snd,
+                                                                 const int* __restrict__ rcv, const float* __restrict__ shift,
+                                                                 const float* __restrict__ cell,
+                                                                 const float* __restrict__ bessel_w, RadialCfg cfg,
+                                                                 const float* __restrict__ gB, const float* __restrict__ t,
+                                                                 float* __restrict__ gw, int E) {
+  constexpr int MAXNB = 16;
+  float acc[MAXNB];
+#pragma unroll
+  for (int n = 0; n < MAXNB; ++n) acc[n] = 0.f;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    float v[3];
+    int s, r;
+    edge_vec(pos, snd, rcv, shift, cell, e, v, s, r);
+    const float d = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (!(d > 1e-8f)) continue;
+    float f, df;
+    cutoff(d, cfg, f, df);
+    float udv = 1.f;
+    if (t != nullptr) {
+      const float inv = 1.f / d;
+      udv = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) udv = fmaf(v[a] * inv, __ldg(t + 3 * (size_t)r + a) - __ldg(t + 3 * (size_t)s + a), udv);
+    }
+#pragma unroll
+    for (int n = 0; n < MAXNB; ++n) {
+      if (n < cfg.nb) {
+        const float w = __ldg(bessel_w + n) * cfg.w_scale;
+        float sn, cs;
+        sincosf(w * d, &sn, &cs);
+        const float k = (t == nullptr) ? cs * f : (cs * df - w * sn * f) * udv;
+        acc[n] = fmaf(__ldg(gB + (size_t)e * cfg.nb + n), cfg.prefactor * cfg.w_scale * k, acc[n]);
+      }
+    }
+  }
+  __shared__ float red[MAXNB][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int n = 0; n < MAXNB; ++n) {
+    const float x = warp_sum(acc[n]);
+    if (lane == 0) red[n][wid] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < cfg.nb) {
+    float x = 0.f;
+    for (int w = 0; w < 8; ++w) x += red[threadIdx.x][w];
+    atomicAdd(gw + threadIdx.x, x);
+  }
+}
+
 }  // namespace pml
 
 #define PML_FEAT_DISPATCH(KERNEL, ...)                                                      \
@@ -288,6 +345,21 @@ extern "C" int pml_edge_featurise_jvp(const float* pos, const int* snd, const in
   const int grid = pml::ceil_div(E, 128);
   const pml::RadialCfg cfg = make_cfg(r_max, prefactor, w_scale, p, nb);
   PML_FEAT_DISPATCH(featurise_jvp_kernel, pos, snd, rcv, shift, cell, bessel_w, cfg, t, tY, tB, E)
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+// gw [nb] must be zero-initialised (or hold a value to accumulate onto); t [N,3] may be null (see the kernel).  nb <= 16.
+extern "C" int pml_bessel_weight_grad(const float* pos, const int* snd, const int* rcv, const float* shift,
+                                      const float* cell, const float* bessel_w, float r_max, float prefactor,
+                                      float w_scale, int p, int nb, const float* gB, const float* t, float* gw, int E,
+                                      cudaStream_t stream) {
+  if (E <= 0) return PML_OK;
+  if (nb > 16 || nb < 1) return PML_ERR_UNSUPPORTED;
+  const pml::RadialCfg cfg = make_cfg(r_max, prefactor, w_scale, p, nb);
+  int grid = pml::ceil_div(E, 256);
+  if (grid > 1184) grid = 1184;  // 8 CTAs x 148 SMs: grid-stride beyond that, fewer atomics
+  pml::bessel_weight_grad_kernel<<<grid, 256, 0, stream>>>(pos, snd, rcv, shift, cell, bessel_w, cfg, gB, t, gw, E);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

@@ -466,11 +466,12 @@ static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_pr
   const long long gz = (long long)max_batch * splitk;
   if (gz > 65535 || nprobs > 65535) return PML_ERR_BAD_ARG;
   const size_t smem = sizeof(TcSmem<BN>) + 128;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int slot = device_slot();
+  if (!configured[slot]) {
     if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return PML_ERR_LAUNCH;
-    configured = true;
+    configured[slot] = true;
   }
   dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)nprobs, (unsigned)gz);
   gemm_grouped_tc_kernel<BN, PROMOTE><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);

@@ -782,17 +782,17 @@ extern "C" int pml_wide_fwd(const float* A, long long lda, int K, const float* i
   if (K <= 0 || K > KP || (K & 3) || (N % BN) || (lda & 3) || (ldc & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
       (reinterpret_cast<uintptr_t>(C) & 15) || (reinterpret_cast<uintptr_t>(image) & 15))
     return PML_ERR_UNSUPPORTED;
-  static int sms = 0;
-  static bool configured = false;
+  static int sms_dev[pml::kMaxDevices] = {};
+  const int slot = pml::device_slot();
   const int smem = (int)sizeof(FwdSmem) + 128;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms_dev[slot] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot);
     if (cudaFuncSetAttribute(wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return PML_ERR_LAUNCH;
-    configured = true;
+    sms_dev[slot] = n;
   }
+  const int sms = sms_dev[slot];
   const int tiles_m = (M + BM - 1) / BM, ntiles_n = N / BN;
   // split the columns of a row block between CTAs when that evens out the rounds (325 row blocks on 148 SMs: 3 rounds
   // of whole blocks = 73 % busy; halves: 5 rounds of half blocks = 88 %)
@@ -829,27 +829,27 @@ extern "C" int pml_wide_bwd_x(const float* G, long long ldg, int N, const float*
   if (K <= 0 || K > KP || (K & 3) || (N % XC) || (ldg & 3) || (lda & 3) || (reinterpret_cast<uintptr_t>(G) & 15) ||
       (reinterpret_cast<uintptr_t>(dA) & 15) || (reinterpret_cast<uintptr_t>(image) & 15))
     return PML_ERR_UNSUPPORTED;
-  static int sms = 0;
-  static bool configured = false;
+  static int sms_dev[pml::kMaxDevices] = {};
+  const int slot = pml::device_slot();
   const int smem = (int)sizeof(BwdXSmem) + 128;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms_dev[slot] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot);
     if (cudaFuncSetAttribute(wide_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return PML_ERR_LAUNCH;
-    configured = true;
+    sms_dev[slot] = n;
   }
+  const int sms = sms_dev[slot];
   const int nitems = (M + BM - 1) / BM;
   static int use_tmem = -1;  // PML_WIDE_X_TMEM=0 selects the first version (operands in shared memory) for A/B runs
   if (use_tmem < 0) use_tmem = getenv("PML_WIDE_X_TMEM") ? atoi(getenv("PML_WIDE_X_TMEM")) : 1;
   if (use_tmem) {
-    static bool configured_t = false;
+    static bool configured_t[pml::kMaxDevices] = {};
     const int smem_t = (int)sizeof(BwdXTSmem) + 128;
-    if (!configured_t) {
+    if (!configured_t[slot]) {
       if (cudaFuncSetAttribute(wide_bwd_x_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t) != cudaSuccess)
         return PML_ERR_LAUNCH;
-      configured_t = true;
+      configured_t[slot] = true;
     }
     wide_bwd_x_tmem_kernel<<<min(sms, nitems), X_THREADS, smem_t, stream>>>(G, ldg, N, image, dA, lda, K, M, alpha);
     PML_CHECK_LAUNCH();

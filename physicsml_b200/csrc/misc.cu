@@ -161,11 +161,12 @@ extern "C" int pml_debug_poison_smem(cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[pml::kMaxDevices] = {};
+  const int slot = pml::device_slot();
+  if (!configured[slot]) {
     if (cudaFuncSetAttribute(pml::poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin) != cudaSuccess)
       return PML_ERR_LAUNCH;
-    configured = true;
+    configured[slot] = true;
   }
   pml::poison_smem_kernel<<<sms, 256, max_optin, stream>>>(max_optin / 4);
   PML_CHECK_LAUNCH();
@@ -206,6 +207,65 @@ extern "C" int pml_pool_sum(const float* x, const long long* batch, float* out, 
 extern "C" int pml_pool_gather(const float* g, const long long* batch, float* out, int N, int F, cudaStream_t stream) {
   if (N <= 0 || F <= 0) return PML_OK;
   pml::pool_gather_kernel<<<pml::ceil_div((long long)N * F, 256), 256, 0, stream>>>(g, batch, out, N, F);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+// perm[rowptr[n] + k] = id of the k-th edge (ascending id = stable order) whose index is n.  Step 1 fills every segment
+// in arrival order with an atomic cursor; step 2 sorts each segment by edge id in shared memory (one CTA per node), which
+// makes the grouping — and with it the summation order of the scatter kernels — deterministic.  Segments longer than
+// 2048 take an in-place odd-even transposition sort in global memory (slow, rare, still exact).
+namespace pml {
+__global__ void __launch_bounds__(256) csr_group_fill_kernel(const long long* __restrict__ idx, const int* __restrict__ rowptr,
+                                                             int* __restrict__ cursor, int* __restrict__ perm, int E) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int n = (int)idx[e];
+  perm[rowptr[n] + atomicAdd(cursor + n, 1)] = e;
+}
+constexpr int kGroupSortMax = 2048;
+__global__ void __launch_bounds__(128) csr_group_sort_kernel(int* __restrict__ perm, const int* __restrict__ rowptr, int N) {
+  __shared__ int s[kGroupSortMax];
+  const int beg = rowptr[blockIdx.x], len = rowptr[blockIdx.x + 1] - beg;
+  if (len <= 1) return;
+  if (len > kGroupSortMax) {
+    int* a = perm + beg;
+    for (int phase = 0; phase < len; ++phase) {
+      for (int t = 2 * threadIdx.x + (phase & 1); t + 1 < len; t += 2 * blockDim.x) {
+        const int x = a[t], y = a[t + 1];
+        if (x > y) a[t] = y, a[t + 1] = x;
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  int P = 2;
+  while (P < len) P <<= 1;
+  for (int t = threadIdx.x; t < P; t += blockDim.x) s[t] = t < len ? perm[beg + t] : 0x7fffffff;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < P; t += blockDim.x) {
+        const int u = t ^ j;
+        if (u > t) {
+          const bool up = (t & k) == 0;
+          const int a = s[t], b = s[u];
+          if ((a > b) == up) s[t] = b, s[u] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = threadIdx.x; t < len; t += blockDim.x) perm[beg + t] = s[t];
+}
+}  // namespace pml
+
+// cursor: scratch [N], zero-initialised by the caller; perm [E]
+extern "C" int pml_csr_group(const long long* idx, const int* rowptr, int* cursor, int* perm, int E, int N,
+                             cudaStream_t stream) {
+  if (E <= 0 || N <= 0) return PML_OK;
+  pml::csr_group_fill_kernel<<<pml::ceil_div(E, 256), 256, 0, stream>>>(idx, rowptr, cursor, perm, E);
+  pml::csr_group_sort_kernel<<<N, 128, 0, stream>>>(perm, rowptr, N);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

@@ -9,10 +9,11 @@
 #define PML_ERR_LAUNCH (-3)
 
 // Every entry point returns 0 or a negative error code and never throws; launch errors are reported
-// (without synchronising) via cudaPeekAtLastError so that CUDA-graph capture keeps working.
+// (without synchronising) via cudaGetLastError, which also CLEARS a non-sticky launch error so that one failed launch
+// does not make every later entry point report PML_ERR_LAUNCH; CUDA-graph capture keeps working.
 #define PML_CHECK_LAUNCH()                                   \
   do {                                                       \
-    cudaError_t e__ = cudaPeekAtLastError();                 \
+    cudaError_t e__ = cudaGetLastError();                    \
     if (e__ != cudaSuccess) return PML_ERR_LAUNCH;           \
   } while (0)
 
@@ -53,5 +54,13 @@ __device__ __forceinline__ void st_stream2(float* p, float2 v) {
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncSetAttribute / SM counts are per device: launchers cache their one-time configuration per device ordinal
+constexpr int kMaxDevices = 64;
+static inline int device_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
 
 }  // namespace pml

@@ -626,16 +626,16 @@ struct PipeCfg {
 // streams shorten it (cfg2 59% vs 54%).
 template <auto kernel>  // one cache per kernel instantiation
 static bool pipe_config(int threads, int stage_bytes, int C, bool small, PipeCfg* cfg) {
-  static int cached_C[2] = {-1, -1};
-  static PipeCfg cached[2];
-  static bool cached_ok[2] = {false, false};
-  const int slot = small ? 1 : 0;
+  static int cached_C[2 * kMaxDevices];  // zero-initialised: C == 0 never occurs, so 0 means "empty"
+  static PipeCfg cached[2 * kMaxDevices];
+  static bool cached_ok[2 * kMaxDevices];
+  int dev = 0, sms = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  const int slot = 2 * device_slot() + (small ? 1 : 0);  // per device: function attributes and SM counts are per device
   if (C == cached_C[slot]) {
     *cfg = cached[slot];
     return cached_ok[slot];
   }
-  int dev = 0, sms = 0, max_optin = 0;
-  cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   int nstage = ((small ? 44 : 56) * 1024) / stage_bytes;

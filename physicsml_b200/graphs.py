@@ -1,9 +1,9 @@
 """Whole-step CUDA-graph capture.
 
-A MACE training step on molecule batches is launch-bound: a few hundred kernels of tens of microseconds each.
-Capturing forward + forces + loss + backward (+ gradient all-reduce) + optimiser into one CUDA graph removes the host
-from the loop ("CUDA streams and graphs instead of a tracing compiler").  Inputs live in static device buffers; a
-new batch of the same shape is copied into them before each replay.
+A MACE training step (or an energy+forces evaluation) on molecule batches is launch-bound: a few hundred kernels of
+tens of microseconds each.  Capturing forward + forces (+ loss + backward + gradient all-reduce + optimiser) into one
+CUDA graph removes the host from the loop ("CUDA streams and graphs instead of a tracing compiler").  Inputs live in
+static device buffers; a new batch of the same shape is copied into them before each replay.
 """
 from __future__ import annotations
 
@@ -12,12 +12,30 @@ from typing import Callable, Optional
 import torch
 
 
-class GraphedStep:
-    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, data: dict, targets: dict,
-                 loss_fn: Callable, after_backward: Optional[Callable] = None, warmup: int = 3) -> None:
-        self.model, self.optimizer, self.loss_fn, self.after_backward = model, optimizer, loss_fn, after_backward
-        self.data = {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v) for k, v in data.items()}
-        self.targets = {k: v.clone() for k, v in targets.items()}
+def _static_copy(d: dict) -> dict:
+    out = {}
+    for k, v in d.items():
+        if torch.is_tensor(v) and v.is_cuda:
+            out[k] = v.clone()
+        elif torch.is_tensor(v) or isinstance(v, (int, float, bool, str)) or v is None:
+            out[k] = v
+        else:
+            # derived Python objects (e.g. a cached EdgePlan) refer to the caller's tensors, not to the static buffers:
+            # they would silently go stale on load(); the body rebuilds what it needs from the static tensors
+            raise TypeError(f"graph-captured batches may hold tensors and scalars only; got {type(v).__name__} under '{k}'")
+    return out
+
+
+def _load(static: dict, new: dict) -> None:
+    for k, v in new.items():
+        if torch.is_tensor(v) and torch.is_tensor(static.get(k)) and static[k].is_cuda:
+            if static[k].shape != v.shape:
+                raise ValueError(f"'{k}': a captured graph replays fixed shapes ({tuple(static[k].shape)} != {tuple(v.shape)})")
+            static[k].copy_(v, non_blocking=True)
+
+
+class _Captured:
+    def _capture(self, warmup: int, pre_capture: Optional[Callable] = None) -> None:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -26,12 +44,28 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        if pre_capture is not None:
+            pre_capture()
         with torch.cuda.graph(self.graph):
-            self.loss = self._body(zero=False)
+            self.out = self._body(captured=True)
 
-    def _body(self, zero: bool = True) -> torch.Tensor:
-        if zero:
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
+class GraphedStep(_Captured):
+    """one training step: zero_grad, loss_fn(model, data, targets), backward, after_backward(), optimizer.step()"""
+
+    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, data: dict, targets: dict,
+                 loss_fn: Callable, after_backward: Optional[Callable] = None, warmup: int = 3) -> None:
+        self.model, self.optimizer, self.loss_fn, self.after_backward = model, optimizer, loss_fn, after_backward
+        self.data, self.targets = _static_copy(data), _static_copy(targets)
+        self._capture(warmup, pre_capture=lambda: self.optimizer.zero_grad(set_to_none=True))
+        self.loss = self.out
+
+    def _body(self, captured: bool = False) -> torch.Tensor:
+        if not captured:
             self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model, self.data, self.targets)
         loss.backward()
@@ -42,12 +76,21 @@ class GraphedStep:
 
     def load(self, data: dict, targets: dict) -> None:
         """copy a new batch of identical shapes into the static buffers (async on the current stream)"""
-        for k, v in data.items():
-            if torch.is_tensor(v) and torch.is_tensor(self.data.get(k)) and self.data[k].is_cuda:
-                self.data[k].copy_(v, non_blocking=True)
-        for k, v in targets.items():
-            self.targets[k].copy_(v, non_blocking=True)
+        _load(self.data, data)
+        _load(self.targets, targets)
 
-    def __call__(self) -> torch.Tensor:
-        self.graph.replay()
-        return self.loss
+
+class GraphedEval(_Captured):
+    """one evaluation ``fn(model, data) -> tensor or tuple of tensors`` (e.g. energy + forces) on static buffers"""
+
+    def __init__(self, model: torch.nn.Module, data: dict, fn: Callable, warmup: int = 3) -> None:
+        self.model, self.fn = model, fn
+        self.data = _static_copy(data)
+        self._capture(warmup)
+
+    def _body(self, captured: bool = False):
+        out = self.fn(self.model, self.data)
+        return tuple(o.detach() for o in out) if isinstance(out, (tuple, list)) else out.detach()
+
+    def load(self, data: dict) -> None:
+        _load(self.data, data)

@@ -286,9 +286,7 @@ class MACE(torch.nn.Module):
         if "cell" in data:
             cell = data["cell"][:3].contiguous()  # one cell for the whole batch: only rows 0-2 are read (utils.py:88-90)
             shift = data["cell_shift_vector"].contiguous()
-        plan = data.get("_edge_plan")
-        if plan is None:
-            plan = ops.EdgePlan(edge_index, pos.shape[0], scatter_row=1)
+        plan = ops.edge_plan_for(data, pos.shape[0], scatter_row=1)
         re = self.radial_embedding
         Y, B = ops.edge_featurise(pos, plan.snd, plan.rcv, shift, cell, re.bessel_fn.bessel_weights, re.r_max,
                                   re.prefactor, 1.0, re.p, self.max_ell)
@@ -375,8 +373,13 @@ class PooledMACEModule(torch.nn.Module):
         return {"y_graph_scalars": e}
 
 
-def compute_forces_by_gradient(energy: torch.Tensor, coordinates: torch.Tensor, training: bool = False) -> torch.Tensor:
-    """reference lightning/module.py:28-48"""
+def compute_forces_by_gradient(energy: torch.Tensor, coordinates: torch.Tensor, training=False) -> torch.Tensor:
+    """reference lightning/module.py:28-48.  The reference method reads ``self.training``; this free function takes it
+    as ``training`` — a bool, or the module itself (its ``.training`` flag is read), so that force-matching training
+    (``create_graph``) written against the reference keeps working: ``compute_forces_by_gradient(e, pos, module)``."""
+    if isinstance(training, torch.nn.Module):
+        training = training.training
+    training = bool(training)
     with ops.input_grads_only():  # only d/d coordinates is asked for: no weight gradients in the force pass
         (grad,) = torch.autograd.grad([energy], [coordinates], grad_outputs=[torch.ones_like(energy)],
                                       retain_graph=training, create_graph=training, allow_unused=True)

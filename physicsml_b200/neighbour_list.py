@@ -109,6 +109,7 @@ def radius_graph(positions: torch.Tensor, cutoff: float, pbc=None, cell: Optiona
     if err is not None and int(err.item()) != 0:
         raise RuntimeError("an atom has more than 2048 neighbours; the per-sender sort does not support that")
     plan_out = ops.EdgePlan.from_sorted(snd, rcv, rowptr, perm, N)
+    plan_out._src = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape))
     return edge_index, shift, plan_out
 
 

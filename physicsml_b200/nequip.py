@@ -99,10 +99,8 @@ class InteractionBlock(torch.nn.Module):
         self.self_connection_layer = ElementLinear(node, so3.irreps_dim(attrs), out) if self_connection else None
 
     def forward(self, data: dict) -> dict:
-        plan = data.get("_edge_plan")
         x = data["node_feats"]
-        if plan is None:
-            plan = ops.EdgePlan(data["edge_index"], x.shape[0], scatter_row=0)
+        plan = ops.edge_plan_for(data, x.shape[0], scatter_row=0)
         gather, rowptr, perm = plan.view(0)  # gather edge_index[1], scatter to edge_index[0]
         weight = self.fc(data["edge_feats"])
         sc = None
@@ -183,22 +181,25 @@ class Nequip(torch.nn.Module):
         if "cell" in data:
             cell = data["cell"][:3].contiguous()
             shift = data["cell_shift_vector"].contiguous()
-        plan = data.get("_edge_plan")
-        if plan is None:
-            plan = ops.EdgePlan(data["edge_index"], pos.shape[0], scatter_row=0)
-            data["_edge_plan"] = plan
+        # the plan travels to the layers under a private key that lives in `data` for the duration of this call only, so
+        # a caller that reuses the dict after rebuilding its neighbour list never sees a stale plan (the reference
+        # recomputes everything from edge_index on every call)
+        supplied = data.get("_edge_plan")
+        plan = ops.edge_plan_for(data, pos.shape[0], scatter_row=0)
+        data["_edge_plan"] = plan
         re = self.radial_embedding
         w = re.bessel_fn.bessel_weights
-        if re.trainable and w.requires_grad and torch.is_grad_enabled() and self.training:
-            raise NotImplementedError("trainable Bessel frequencies (bessel_basis_trainable=True) are not differentiated "
-                                      "by the fused featurisation kernel; freeze them or use inference mode")
         data["node_feats"] = self.node_embedding(data["node_attrs"])
-        Y, B = ops.edge_featurise(pos, plan.snd, plan.rcv, shift, cell, w.detach(), re.r_max, re.bessel_fn.prefactor,
+        Y, B = ops.edge_featurise(pos, plan.snd, plan.rcv, shift, cell, w, re.r_max, re.bessel_fn.prefactor,
                                   1.0 / re.r_max, re.p, self.max_ell)
         data["edge_feats"] = torch.cat([B, data["edge_attrs"]], dim=-1) if "edge_attrs" in data else B
         data["edge_attrs"] = Y
         for layer in self.conv_layers:
             data = layer(data)
+        if supplied is None:
+            data.pop("_edge_plan", None)
+        else:
+            data["_edge_plan"] = supplied
         return data
 
 

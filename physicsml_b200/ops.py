@@ -12,6 +12,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
+import threading
 from typing import List, Optional, Tuple
 
 import torch
@@ -64,7 +65,8 @@ def enable_kernel_timing(names) -> None:
         KERNEL_TIMING[n] = []
 
 
-def _call(name: str, *args, launches: int = 1) -> None:
+def _call(name: str, *args, launches: int = 1, tag=None) -> None:
+    """launch through the C ABI; ``tag`` (default: the first argument) labels the launch in KERNEL_TIMING records"""
     LAUNCHES[0] += launches
     rec = KERNEL_TIMING.get(name[:-3] if name.endswith("_ex") else name)  # pml_tp_fwd_ex is timed as pml_tp_fwd
     if rec is None:
@@ -74,7 +76,7 @@ def _call(name: str, *args, launches: int = 1) -> None:
     e0.record()
     _lib.check(getattr(_lib.lib(), name)(*args), name)
     e1.record()
-    rec.append((args[0], e0, e1))
+    rec.append((args[0] if tag is None else tag, e0, e1))
 
 
 # ======================================================================================================================
@@ -141,13 +143,32 @@ def _(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax, 
     return _new_empty(pos, E, (lmax + 1) ** 2), _new_empty(pos, E, bessel_w.numel())
 
 
-def _feat_save(ctx, inputs):
-    ctx.save_for_backward(*inputs[:6])  # pos, snd, rcv, shift, cell, bessel_w (None allowed)
+@torch.library.custom_op(f"{NS}::bessel_weight_grad", mutates_args=(), device_types="cuda")
+def bessel_weight_grad(pos: Tensor, snd: Tensor, rcv: Tensor, shift: Optional[Tensor], cell: Optional[Tensor],
+                       bessel_w: Tensor, r_max: float, prefactor: float, w_scale: float, p: int, lmax: int,
+                       gB: Tensor, t: Optional[Tensor]) -> Tensor:
+    """gradient w.r.t. trainable Bessel frequencies (reference nequip/modules/radial.py:9-19): of <gB, B> (t None) or of
+    <gB, dB/dd * u.(t[r]-t[s])> (the force pass / its tangent map); see pml_bessel_weight_grad"""
+    pos, gB = _f32c(pos), _f32c(gB)
+    t = None if t is None else _f32c(t)
+    gw = torch.zeros_like(bessel_w, dtype=torch.float32)
+    _call("pml_bessel_weight_grad", _p(pos), _p(snd), _p(rcv), _p(shift), _p(cell), _p(bessel_w), float(r_max),
+          float(prefactor), float(w_scale), int(p), int(bessel_w.numel()), _p(gB), _p(t), _p(gw), snd.numel(), _stream())
+    return gw
+
+
+@bessel_weight_grad.register_fake
+def _(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax, gB, t):
+    return torch.empty_like(bessel_w, dtype=torch.float32)
+
+
+def _feat_save(ctx, inputs, extra=None):
+    ctx.save_for_backward(*inputs[:6], extra)  # pos, snd, rcv, shift, cell, bessel_w (None allowed) + one extra tensor
     ctx.consts = tuple(inputs[6:11])
 
 
 def _feat_args_from(ctx):
-    return tuple(ctx.saved_tensors) + ctx.consts
+    return tuple(ctx.saved_tensors[:6]) + ctx.consts
 
 
 def _feat_setup(ctx, inputs, output):
@@ -156,10 +177,12 @@ def _feat_setup(ctx, inputs, output):
 
 
 def _feat_bwd(ctx, gY, gB):
-    g = None
+    g = gw = None
     if ctx.needs_input_grad[0] and (gY is not None or gB is not None):
         g = edge_featurise_bwd(*_feat_args_from(ctx), gY, gB)
-    return (g,) + (None,) * 10
+    if ctx.needs_input_grad[5] and gB is not None and _PARAM_GRADS[0]:  # trainable Bessel frequencies
+        gw = bessel_weight_grad(*_feat_args_from(ctx), gB, None)
+    return (g, None, None, None, None, gw) + (None,) * 5
 
 
 edge_featurise.register_autograd(_feat_bwd, setup_context=_feat_setup)
@@ -167,7 +190,7 @@ edge_featurise.register_autograd(_feat_bwd, setup_context=_feat_setup)
 
 def _feat_bwd_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)
-    _feat_save(ctx, inputs)
+    _feat_save(ctx, inputs, inputs[12] if (inputs[12] is not None and inputs[5].requires_grad) else None)
     ctx.has = (inputs[11] is not None, inputs[12] is not None)
 
 
@@ -175,10 +198,15 @@ def _feat_bwd_bwd(ctx, v):
     # gpos is linear in (gY, gB): their cotangents are the tangent map applied to v.  The second derivative of the
     # harmonics / radial basis w.r.t. the coordinates only feeds d(loss)/d(coordinates), which nothing consumes
     # (SURVEY §7 "hard parts"); it is not propagated.
+    # (Consequence: d(force loss)/d(coordinates) is NOT available from this path; parameter gradients are exact.)
     if v is None:
         return (None,) * 13
     tY, tB = edge_featurise_jvp(*_feat_args_from(ctx), v)
-    return (None,) * 11 + (tY if ctx.has[0] else None, tB if ctx.has[1] else None)
+    gw = None
+    gB = ctx.saved_tensors[6]
+    if ctx.needs_input_grad[5] and gB is not None:  # d<v, gpos>/d bessel_w: gpos is linear in dB/dd
+        gw = bessel_weight_grad(*_feat_args_from(ctx), gB, v)
+    return (None,) * 5 + (gw,) + (None,) * 5 + (tY if ctx.has[0] else None, tB if ctx.has[1] else None)
 
 
 edge_featurise_bwd.register_autograd(_feat_bwd_bwd, setup_context=_feat_bwd_setup)
@@ -186,14 +214,17 @@ edge_featurise_bwd.register_autograd(_feat_bwd_bwd, setup_context=_feat_bwd_setu
 
 def _feat_jvp_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)
-    _feat_save(ctx, inputs)
+    _feat_save(ctx, inputs, inputs[11] if inputs[5].requires_grad else None)
 
 
 def _feat_jvp_bwd(ctx, gtY, gtB):
-    g = None
+    g = gw = None
     if gtY is not None or gtB is not None:
         g = edge_featurise_bwd(*_feat_args_from(ctx), gtY, gtB)
-    return (None,) * 11 + (g,)
+    t = ctx.saved_tensors[6]
+    if ctx.needs_input_grad[5] and gtB is not None and t is not None:  # tB = dB/dd * u.(t[r]-t[s])
+        gw = bessel_weight_grad(*_feat_args_from(ctx), gtB, t)
+    return (None,) * 5 + (gw,) + (None,) * 5 + (g,)
 
 
 edge_featurise_jvp.register_autograd(_feat_jvp_bwd, setup_context=_feat_jvp_setup)
@@ -232,7 +263,7 @@ def tp_scatter_bwd(h: Tensor, Y: Tensor, R: Tensor, g: Tensor, gather: Tensor, r
     if need_h or need_y or need_r:
         _call("pml_tp_bwd_ex", pl.spec_id, _p(h), _p(Y), _p(R), _p(g), _p(gather), _p(rowptr), _p(perm),
               _p(dh) if need_h else None, _p(dY) if need_y else None, _p(dR) if need_r else None, N, pl.C,
-              pl.out_layout_id, _stream())
+              pl.out_layout_id, _stream(), tag=(pl.spec_id, need_h, need_y, need_r))
     return dh, dY, dR
 
 
@@ -334,19 +365,31 @@ def _gemm(name: str, a, b, c, table, nprob: int, m_runtime: int, max_m: int, max
         _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, _stream())
 
 
-_SMS = 148
+_SM_COUNT: dict = {}
+
+
+def _sms() -> int:
+    """SM count of the current device (148 on B200; also the value assumed when no device is visible: host-side tests)"""
+    if not torch.cuda.is_available():
+        return 148
+    dev = torch.cuda.current_device()
+    if dev not in _SM_COUNT:
+        _SM_COUNT[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _SM_COUNT[dev]
 
 
 def _tc_slots(bn: int, promote: bool) -> int:
     """CTAs of gemm_grouped_tc_kernel<bn, promote> resident on the GPU (registers bound it: 96-126 registers x 256
     threads -> 2 per SM; the 80-register non-promoting BN <= 64 variants -> 3 per SM)"""
-    return _SMS * (2 if (promote or bn >= 128) else 3)
+    return _sms() * (2 if (promote or bn >= 128) else 3)
 
 
-def _splitk_for(k_extent: int, ctas_without_split: int, slots: int = 4 * _SMS) -> int:
+def _splitk_for(k_extent: int, ctas_without_split: int, slots: Optional[int] = None) -> int:
     """split the reduction so that the grid fills `slots` CTAs without spilling into a nearly empty extra wave
     (floor, not ceil: 10 tiles x 60 splits = 600 CTAs on 592 slots ran three rounds instead of two), keeping >= 4
     k-tiles (of 16) per CTA"""
+    if slots is None:
+        slots = 4 * _sms()
     want = slots // max(1, ctas_without_split)
     return max(1, min(want, max(1, k_extent // 64), 4096))
 
@@ -480,7 +523,7 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
         else:
             ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
         sk = _splitk_for(n, ctas, 2 * _tc_slots(bn, False) if name.endswith("_tc") and bn >= 128 else
-                         (_tc_slots(bn, False) if name.endswith("_tc") else 4 * _SMS))
+                         (_tc_slots(bn, False) if name.endswith("_tc") else 4 * _sms()))
         k_cta = (n + sk - 1) // sk + 16
         # Weight gradients are sums over nodes / edges whose fp32 evaluation order already carries ~sqrt(n) eps; up to
         # 1024 terms per CTA they run on the plain TMEM accumulator (worst-case truncation bias 2e-5 relative, measured
@@ -506,20 +549,35 @@ def _lin_setup(ctx, inputs, output):
 # every evaluation and of every training step.  PyTorch prunes those branches for its own ops (one node per gradient);
 # a fused op cannot be pruned from outside, so ``compute_forces_by_gradient`` says so explicitly.  (Config 4: 19.5 of
 # 62.8 ms of an energy+forces evaluation were weight gradients nobody asked for.)
-_PARAM_GRADS = [True]
+class _ParamGrads(threading.local):
+    """thread-local switch (autograd runs the formulas of an ``autograd.grad`` call made on this thread on this thread
+    for CUDA graphs of one device; another Python thread's backward is not affected)"""
+
+    def __init__(self) -> None:
+        self.on = True
+
+    def __getitem__(self, _i):  # `_PARAM_GRADS[0]` reads the current thread's value
+        return self.on
+
+
+_PARAM_GRADS = _ParamGrads()
 
 
 @contextlib.contextmanager
 def input_grads_only():
     """inside: first-order cotangent formulas skip the parameter gradients (the caller asks for input gradients only,
     e.g. forces = -dE/dx); the recorded graph (create_graph=True) still reaches the parameters through the input
-    gradients, which is all force-matching training differentiates"""
-    old = _PARAM_GRADS[0]
-    _PARAM_GRADS[0] = False
+    gradients, which is all force-matching training differentiates.
+
+    Only wrap ``torch.autograd.grad(..., inputs=[coordinates])`` calls in it: a ``backward()`` or a gradient w.r.t.
+    parameters taken INSIDE the context would silently miss the weight gradients of the fused ops, which is why the
+    context is entered by ``compute_forces_by_gradient`` / ``workloads.training_loss`` themselves and nowhere else."""
+    old = _PARAM_GRADS.on
+    _PARAM_GRADS.on = False
     try:
         yield
     finally:
-        _PARAM_GRADS[0] = old
+        _PARAM_GRADS.on = old
 
 
 def _lin_bwd(ctx, g):
@@ -996,6 +1054,15 @@ irreps_to_channel.register_autograd(
 # ======================================================================================================================
 # graph structure (index plumbing only — no floating-point work)
 # ======================================================================================================================
+def edge_plan_for(data: dict, num_nodes: int, scatter_row: int) -> "EdgePlan":
+    """the caller-supplied ``data["_edge_plan"]`` (e.g. from ``neighbour_list.radius_graph``) if it still describes
+    ``data["edge_index"]``, else a fresh plan; never written back into the caller's dict"""
+    plan = data.get("_edge_plan")
+    if plan is not None and plan.matches(data["edge_index"], num_nodes):
+        return plan
+    return EdgePlan(data["edge_index"], num_nodes, scatter_row=scatter_row)
+
+
 class EdgePlan:
     """int32 copies of the edge list and the CSR over the scatter index, built once per batch and shared by every
     layer's forward and backward kernels.  ``gather`` / ``rowptr`` / ``perm`` are the view for MACE's convention
@@ -1011,6 +1078,7 @@ class EdgePlan:
         _call("pml_split_edge_index", _p(ei), _p(self.snd), _p(self.rcv), E, _stream())
         self._views = {}
         self._ei = ei
+        self._src = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape))
         self._assume_grouped = assume_grouped
         self.scatter_row = scatter_row
         self.gather, self.rowptr, self.perm = self.view(scatter_row)
@@ -1023,19 +1091,33 @@ class EdgePlan:
         self.snd, self.rcv = snd, rcv
         self._views = {1: (snd, rowptr, perm_by_receiver), 0: (rcv, rowptr, None)}
         self._ei = None
+        self._src = None  # set by the neighbour list to the edge_index tensor it returned alongside
         self._assume_grouped = False
         self.scatter_row = 1
         self.gather, self.rowptr, self.perm = self._views[1]
         return self
 
+    def matches(self, edge_index: Tensor, num_nodes: int) -> bool:
+        """False when this plan was derived from a different (or since modified) edge_index tensor: a caller that
+        reuses a batch dict after a neighbour-list rebuild must not silently get the old edges"""
+        if self.N != num_nodes or self.E != edge_index.shape[1]:
+            return False
+        if self._src is None:
+            return True
+        return self._src == (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape))
+
     def view(self, scatter_row: int):
         """(gather index, CSR row pointer over the scatter index, edge ids grouped by scatter index or None)"""
         if scatter_row not in self._views:
             ei, dev = self._ei, self._ei.device
-            counts = torch.zeros(self.N, dtype=torch.int32, device=dev)
+            scratch = torch.zeros(2, self.N, dtype=torch.int32, device=dev)  # counts, cursor
             rowptr = torch.empty(self.N + 1, dtype=torch.int32, device=dev)
-            _call("pml_csr_rowptr", _p(ei[scatter_row]), _p(counts), _p(rowptr), self.E, self.N, _stream(), launches=2)
-            perm = None if self._assume_grouped else torch.argsort(ei[scatter_row], stable=True).to(torch.int32)
+            _call("pml_csr_rowptr", _p(ei[scatter_row]), _p(scratch[0]), _p(rowptr), self.E, self.N, _stream(), launches=2)
+            perm = None
+            if not self._assume_grouped:  # stable counting sort by the scatter index (own kernels: graph-capturable)
+                perm = torch.empty(self.E, dtype=torch.int32, device=dev)
+                _call("pml_csr_group", _p(ei[scatter_row]), _p(rowptr), _p(scratch[1]), _p(perm), self.E, self.N, _stream(),
+                      launches=2)
             gather = self.snd if scatter_row == 1 else self.rcv
             self._views[scatter_row] = (gather, rowptr, perm)
         return self._views[scatter_row]
