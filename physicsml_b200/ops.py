@@ -12,7 +12,6 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
-import threading
 from typing import List, Optional, Tuple
 
 import torch
@@ -549,14 +548,17 @@ def _lin_setup(ctx, inputs, output):
 # every evaluation and of every training step.  PyTorch prunes those branches for its own ops (one node per gradient);
 # a fused op cannot be pruned from outside, so ``compute_forces_by_gradient`` says so explicitly.  (Config 4: 19.5 of
 # 62.8 ms of an energy+forces evaluation were weight gradients nobody asked for.)
-class _ParamGrads(threading.local):
-    """thread-local switch (autograd runs the formulas of an ``autograd.grad`` call made on this thread on this thread
-    for CUDA graphs of one device; another Python thread's backward is not affected)"""
+class _ParamGrads:
+    """process-wide switch.  NOT thread-local on purpose: autograd evaluates the formulas of a CUDA graph on the engine's
+    device worker thread, not on the thread that called ``autograd.grad`` — a thread-local set by the caller would never
+    be seen by the formulas (measured: the force pass then computes every weight gradient again, +0.6 ms per config-2
+    step).  The price: a backward() started concurrently from ANOTHER Python thread while this context is active would
+    also skip its weight gradients; the context is therefore entered only around the force-pass ``autograd.grad`` call."""
 
     def __init__(self) -> None:
         self.on = True
 
-    def __getitem__(self, _i):  # `_PARAM_GRADS[0]` reads the current thread's value
+    def __getitem__(self, _i):
         return self.on
 
 

@@ -1,0 +1,218 @@
+"""``patch(module)``: run a REFERENCE physicsml MACE / NequIP module on the B200 kernels, in place.
+
+The reference's plugin API stays untouched: a stock ``mace_model`` / ``nequip_model`` built by molflux
+(``mz.load_from_dict({"name": "mace_model", ...})`` -> ``PooledMACEModule``) keeps its class, its ``forward(data)``
+contract, its parameters and its state dict; only the backbone's ``forward`` (``models/mace/modules/mace.py:133-175`` —
+the featurisation prologue plus ``InteractionBlock.forward`` ``blocks.py:195-237``, ``MessageBlock.forward``
+``blocks.py:117-121``, ``NodeUpdateBlock.forward`` ``blocks.py:82-96``; NequIP ``nequip.py:100-127`` /
+``interaction_block.py:84-108``) is swapped for the one of :class:`physicsml_b200.mace.MACE` /
+:class:`physicsml_b200.nequip.Nequip`, whose parameters are TIED to the reference's own ``Parameter`` objects (same state-dict
+keys), so optimisers, checkpoints and ``.to(device)`` keep working on the reference module.
+
+The module is duck-typed (hyper-parameters are read from the instance), so it works on the real reference as well as
+on the reference sources imported over the oracle shims (``oracle/import_reference.py``) — which is how the CPU
+tests check plan construction and parameter tying without a GPU.
+"""
+from __future__ import annotations
+
+import types
+from typing import Any
+
+import torch
+
+from . import so3
+
+
+def _irreps_str(x) -> str:
+    return str(x)
+
+
+def _lmax_of(irreps) -> int:
+    return max(l for _, l, _ in so3.parse_irreps(_irreps_str(irreps)))
+
+
+def _first_layer_in(fc) -> int:
+    """input width of an e3nn ``FullyConnectedNet`` (first layer weight [h_in, h_out])"""
+    for name, p in fc.named_parameters():
+        if name.endswith("weight") and p.dim() == 2:
+            return int(p.shape[0])
+    raise ValueError("cannot read the radial MLP's input width")
+
+
+def infer_mace_kwargs(mace: torch.nn.Module) -> dict:
+    """constructor arguments of ``MACE`` (reference mace.py:23-36) read back from an instance"""
+    re = mace.radial_embedding
+    num_bessel = int(re.bessel_fn.bessel_weights.numel())
+    inter0 = mace.interactions[0]
+    contraction0 = mace.messages[0].symmetric_contractions.contractions[0]
+    correlation = getattr(contraction0, "correlation", None)
+    if correlation is None:
+        correlation = 1 + len(getattr(contraction0, "weights", []))
+    return dict(
+        cut_off=float(mace.r_max),
+        num_bessel=num_bessel,
+        num_polynomial_cutoff=int(re.cutoff_fn.p),
+        max_ell=_lmax_of(mace.spherical_harmonics.irreps_out),
+        num_interactions=len(mace.interactions),
+        num_node_feats=so3.irreps_dim(so3.parse_irreps(_irreps_str(mace.node_embedding.irreps_in))),
+        num_edge_feats=_first_layer_in(inter0.net_R_channels) - num_bessel,
+        hidden_irreps=_irreps_str(mace.hidden_irreps),
+        avg_num_neighbours=float(inter0.avg_num_neighbours),
+        correlation=int(correlation),
+    )
+
+
+def infer_nequip_kwargs(nequip: torch.nn.Module) -> dict:
+    """constructor arguments of ``Nequip`` (reference nequip.py:14-30) read back from an instance"""
+    re = nequip.radial_embedding
+    num_bessel = int(re.bessel_fn.bessel_weights.numel())
+    sh = so3.parse_irreps(_irreps_str(nequip.spherical_harmonics.irreps_out))
+    layer0 = nequip.conv_layers[0]
+    conv0 = layer0.conv
+    feats = so3.parse_irreps(_irreps_str(nequip.node_embedding.irreps_out))
+    return dict(
+        cut_off=float(nequip.r_max),
+        num_layers=len(nequip.conv_layers),
+        max_ell=max(l for _, l, _ in sh),
+        parity=any(p == -1 for _, _, p in sh),
+        num_features=feats[0][0],
+        num_bessel=num_bessel,
+        bessel_basis_trainable=isinstance(re.bessel_fn.bessel_weights, torch.nn.Parameter),
+        num_polynomial_cutoff=int(re.cutoff_fn.p),
+        self_connection=getattr(conv0, "self_connection_layer", None) is not None,
+        resnet=bool(getattr(layer0, "resnet", False)) or any(bool(getattr(l, "resnet", False)) for l in nequip.conv_layers),
+        num_node_feats=so3.irreps_dim(so3.parse_irreps(_irreps_str(nequip.node_embedding.irreps_in))),
+        num_edge_feats=_first_layer_in(conv0.fc) - num_bessel,
+        avg_num_neighbours=conv0.avg_num_neighbours,
+    )
+
+
+def _walk(root: torch.nn.Module, dotted: str):
+    mod = root
+    parts = dotted.split(".")
+    for p in parts[:-1]:
+        mod = getattr(mod, p)
+    return mod, parts[-1]
+
+
+def tie_parameters(mirror: torch.nn.Module, reference: torch.nn.Module) -> list:
+    """make every parameter / buffer of `mirror` that `reference` also has THE SAME tensor object; returns the list of
+    tied names.  Raises if a trainable parameter of either side has no counterpart or a shape differs."""
+    ref_params = dict(reference.named_parameters())
+    ref_bufs = dict(reference.named_buffers())
+    tied = []
+    for name, p in list(mirror.named_parameters()):
+        if name not in ref_params:
+            if name in ref_bufs:  # e.g. frozen Bessel frequencies registered as a buffer on one side
+                src = ref_bufs[name]
+            elif p.numel() == 0:
+                continue
+            else:
+                raise KeyError(f"reference module has no parameter '{name}'")
+        else:
+            src = ref_params[name]
+        if tuple(src.shape) != tuple(p.shape):
+            raise ValueError(f"'{name}': shape {tuple(src.shape)} (reference) != {tuple(p.shape)} (B200 mirror)")
+        owner, leaf = _walk(mirror, name)
+        if isinstance(src, torch.nn.Parameter):
+            owner._parameters[leaf] = src
+        else:
+            owner._parameters.pop(leaf, None)
+            owner._buffers[leaf] = src
+        tied.append(name)
+    for name, b in list(mirror.named_buffers()):
+        src = ref_bufs.get(name, ref_params.get(name))
+        if src is None or tuple(src.shape) != tuple(b.shape):
+            continue  # buffers only one side keeps (3j tables, output masks): not read by the kernels
+        owner, leaf = _walk(mirror, name)
+        if isinstance(src, torch.nn.Parameter):
+            owner._buffers.pop(leaf, None)
+            owner._parameters[leaf] = src
+        else:
+            owner._buffers[leaf] = src
+        tied.append(name)
+    missing = [n for n, p in ref_params.items() if p.requires_grad and p.numel() > 0 and n not in set(tied)]
+    if missing:
+        raise KeyError(f"reference parameters without a B200 counterpart: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+    return tied
+
+
+def _find_backbone(module: torch.nn.Module):
+    for attr, kind in (("mace", "mace"), ("nequip", "nequip")):
+        if hasattr(module, attr) and isinstance(getattr(module, attr), torch.nn.Module):
+            return getattr(module, attr), kind
+    if hasattr(module, "interactions") and hasattr(module, "messages") and hasattr(module, "node_updates"):
+        return module, "mace"
+    if hasattr(module, "conv_layers") and hasattr(module, "radial_embedding"):
+        return module, "nequip"
+    raise TypeError("patch() expects a physicsml MACE / NequIP module (or a Pooled*/…Module wrapping one under .mace / .nequip)")
+
+
+def patch(module: torch.nn.Module, patch_forces: bool = True) -> torch.nn.Module:
+    """Swap the backbone forward of a reference MACE / NequIP module for the B200 kernels (in place; returns `module`).
+
+    * parameters stay the reference's own objects (tied), the state dict is unchanged;
+    * the reference's readout heads keep running as they are (plain per-node linears + ``scatter``);
+    * ``patch_forces``: if the module has the reference's ``compute_forces_by_gradient`` method
+      (``lightning/module.py:28-48``) it is replaced by the B200 one, which computes input gradients only in the force pass;
+    * there is no CPU fallback: a patched module raises on CPU tensors; :func:`unpatch` restores the original."""
+    backbone, kind = _find_backbone(module)
+    if getattr(backbone, "_b200_mirror", None) is not None:
+        return module
+    if kind == "mace":
+        from .mace import MACE as Mirror
+
+        kwargs = infer_mace_kwargs(backbone)
+    else:
+        from .nequip import Nequip as Mirror
+
+        kwargs = infer_nequip_kwargs(backbone)
+    mirror = Mirror(**kwargs)
+    dev = next((p.device for p in backbone.parameters()), torch.device("cpu"))
+    mirror.to(dev)
+    tied = tie_parameters(mirror, backbone)
+    mirror.train(backbone.training)
+
+    def forward(self, data: dict) -> dict:
+        m = self._b200_mirror
+        if m.training != self.training:
+            m.train(self.training)
+        return m.forward(data)
+
+    # plain attributes (not registered sub-modules): the state dict and .parameters() of the reference stay as they were
+    object.__setattr__(backbone, "_b200_mirror", mirror)
+    object.__setattr__(backbone, "_b200_original_forward", backbone.forward)
+    object.__setattr__(backbone, "_b200_kwargs", kwargs)
+    object.__setattr__(backbone, "_b200_tied", tied)
+    backbone.forward = types.MethodType(forward, backbone)
+    if patch_forces and hasattr(module, "compute_forces_by_gradient"):
+        from .mace import compute_forces_by_gradient as cfg
+
+        object.__setattr__(module, "_b200_original_forces", module.compute_forces_by_gradient)
+
+        def forces(self, energy: torch.Tensor, coordinates: torch.Tensor) -> torch.Tensor:
+            return cfg(energy, coordinates, self)
+
+        module.compute_forces_by_gradient = types.MethodType(forces, module)
+    return module
+
+
+def unpatch(module: torch.nn.Module) -> torch.nn.Module:
+    backbone, _ = _find_backbone(module)
+    if getattr(backbone, "_b200_mirror", None) is None:
+        return module
+    backbone.__dict__.pop("forward", None)  # the class's own forward shows through again
+    for a in ("_b200_mirror", "_b200_original_forward", "_b200_kwargs", "_b200_tied"):
+        object.__delattr__(backbone, a)
+    if getattr(module, "_b200_original_forces", None) is not None:
+        module.__dict__.pop("compute_forces_by_gradient", None)
+        object.__delattr__(module, "_b200_original_forces")
+    return module
+
+
+def is_patched(module: Any) -> bool:
+    try:
+        backbone, _ = _find_backbone(module)
+    except TypeError:
+        return False
+    return getattr(backbone, "_b200_mirror", None) is not None
