@@ -131,7 +131,7 @@ class _Gate(torch.nn.Module):
         self.irreps_out = scalars + self.mul.irreps_out
 
     @staticmethod
-    def _apply(x, irreps, acts):
+    def _activate(x, irreps, acts):
         out, off = [], 0
         for (mul, _), a in zip(irreps, acts):
             out.append(a(x[..., off : off + mul]))
@@ -140,9 +140,9 @@ class _Gate(torch.nn.Module):
 
     def forward(self, x):
         s, g, y = self.cut(x)
-        s = self._apply(s, self.irreps_scalars, self.act_s)
+        s = self._activate(s, self.irreps_scalars, self.act_s)
         if g.shape[-1]:
-            g = self._apply(g, self.irreps_gates, self.act_g)
+            g = self._activate(g, self.irreps_gates, self.act_g)
             return torch.cat([s, self.mul(y, g)], dim=-1)
         return s
 

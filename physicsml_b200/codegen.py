@@ -79,6 +79,8 @@ def _emit_tp(spec: so3.TPSpec, ident: int) -> str:
     L.append(f"// {spec.key}")
     L.append(f"template <> struct TPCode<{ident}> {{")
     L.append(f"  static constexpr int NP = {NP}, DIN = {DIN}, DOUT = {DOUT}, NSH = {NSH};")
+    L.append(f"  // the whole signature seen as one path group (see TPGroup below)")
+    L.append(f"  static constexpr int P0 = 0, NP_FULL = {NP}, H_OFF = 0, DIN_FULL = {DIN}, DOUT_FULL = {DOUT}, NGROUPS = 1;")
     # ---- per-channel gather / scatter of the irreps layout (blocks [C, 2l+1], mul-major)
     L.append("  // h_row points at node_feats[s, 0]; block b of irrep l sits at C*in_off_b + u*(2l+1) + i")
     L.append("  __device__ __forceinline__ static void load_h(const float* __restrict__ hrow, int C, int u, float (&h)[DIN]) {")
@@ -166,9 +168,44 @@ def _emit_tp(spec: so3.TPSpec, ident: int) -> str:
         L.append("      }")
         L.append("    }")
     L.append("  }")
-    _emit_tp_packed(spec, by_path, L)
+    _emit_tp_packed(spec, by_path, L, list(range(NP)), 1)
     L.append("};")
+    groups = tp_path_groups(spec)
+    L.append(f"template <> struct TPGroups<{ident}> {{ static constexpr int N = {len(groups)}; }};")
+    if len(groups) == 1:
+        L.append(f"template <> struct TPGroup<{ident}, 0> : TPCode<{ident}> {{}};")
+    else:
+        for g, paths in enumerate(groups):
+            L.append(f"// {spec.key}: path group {g} = paths {paths[0]}..{paths[-1]}")
+            L.append(f"template <> struct TPGroup<{ident}, {g}> {{")
+            _emit_tp_packed(spec, by_path, L, paths, len(groups))
+            L.append("};")
     return "\n".join(L)
+
+
+PIPE_MAX_DOUT = 48  # two channels of accumulators (or of the cotangent row) per thread must fit the register file
+
+
+def tp_path_groups(spec: so3.TPSpec) -> list:
+    """contiguous path ranges whose output width is <= PIPE_MAX_DOUT each (balanced), so that signatures with wide
+    output rows (MACE large L=2: 71 components; NequIP layers >= 2: 93 / 102) run the pipelined kernels group by group:
+    every group reads its own contiguous slice of the R row and of the gathered h row and owns its output blocks"""
+    widths = [2 * q.l3 + 1 for q in spec.paths]
+    total = sum(widths)
+    n_groups = max(1, -(-total // PIPE_MAX_DOUT))
+    while True:
+        target = total / n_groups
+        groups, cur, acc = [], [], 0
+        for p, w in enumerate(widths):
+            if cur and len(groups) < n_groups - 1 and acc + w / 2 > target:
+                groups.append(cur)
+                cur, acc = [], 0
+            cur.append(p)
+            acc += w
+        groups.append(cur)
+        if all(sum(widths[p] for p in g) <= PIPE_MAX_DOUT for g in groups):
+            return groups
+        n_groups += 1
 
 
 def _f32_is(c: float, v: float) -> bool:
@@ -177,14 +214,38 @@ def _f32_is(c: float, v: float) -> bool:
     return float(np.float32(c)) == v
 
 
-def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
+def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list, paths: list, n_groups: int) -> None:
     """Two channels per thread on the packed fp32x2 pipe (FFMA2 / FMUL2, sm_100): every operand is a float2 holding
     the same quantity for channels (2t, 2t+1); Y arrives as duplicated pairs (Y_j, Y_j).  The arithmetic is factored
     to ~1 packed instruction per non-zero 3j entry and cotangent:
       fwd : rh_i = R_p h_i ;  acc_k += (|c| rh_i) (+-Y_j)
       bwd : a = |c| g_k ;  dh'_i += a Y_j ;  dY'_j += a h_i ;  then per path  dR_p = sum_i h_i dh'_i,
-            dh_i += R_p dh'_i,  dY_j += R_p . dY'_j  (the two channels are summed here: dY is per edge)."""
-    NP, DIN, DOUT, NSH = spec.n_paths, spec.d_in, spec.d_out, spec.n_sh
+            dh_i += R_p dh'_i,  dY_j += R_p . dY'_j  (the two channels are summed here: dY is per edge).
+
+    `paths` selects a contiguous PATH GROUP of the signature (all paths for the main TPCode struct).  A group sees
+    compact local arrays: R / dR [len(paths)], the slice [H_OFF, H_OFF + DIN) of the gathered h row, and acc / g over
+    the output blocks of its own paths only; row addressing (load_out2 / store_out2 / atomic_add_h2) uses the offsets
+    of the FULL rows."""
+    NP_FULL, DIN_FULL, DOUT_FULL, NSH = spec.n_paths, spec.d_in, spec.d_out, spec.n_sh
+    grouped = n_groups > 1
+    P0 = paths[0]
+    ins_used = sorted({i for p in paths for _, i, _, _ in by_path[p]})
+    H_OFF, H_END = 0, DIN_FULL
+    if grouped:  # the slice of the h row from the first to the last node block this group reads (whole blocks)
+        touched, off = [], 0
+        for l, _ in spec.node_ls:
+            d = 2 * l + 1
+            if any(off <= i < off + d for i in ins_used):
+                touched.append((off, off + d))
+            off += d
+        H_OFF, H_END = touched[0][0], touched[-1][1]
+    DIN = H_END - H_OFF
+    out_slots = sorted({o for p in paths for o, _, _, _ in by_path[p]}) if grouped else list(range(DOUT_FULL))
+    omap = {o: k for k, o in enumerate(out_slots)}
+    DOUT, NP = len(out_slots), len(paths)
+    if grouped:
+        L.append(f"  static constexpr int NP = {NP}, DIN = {DIN}, DOUT = {DOUT}, NSH = {NSH};")
+        L.append(f"  static constexpr int P0 = {P0}, NP_FULL = {NP_FULL}, H_OFF = {H_OFF}, DIN_FULL = {DIN_FULL}, DOUT_FULL = {DOUT_FULL}, NGROUPS = {n_groups};")
 
     def scaled(cache, tag, c, base, lines, indent):
         """name of |c|*base (a float2 expression name), emitting the multiply once per distinct (|c|, base)"""
@@ -201,17 +262,17 @@ def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
     # ---------------- forward
     L.append("  // packed: h, R, acc hold channels (2t, 2t+1); Y[j] = (Y_j, Y_j)")
     L.append("  __device__ __forceinline__ static void fwd2(const float2 (&h)[DIN], const float2 (&Y)[NSH], const float2 (&R)[NP], float2 (&acc)[DOUT]) {")
-    for p in range(NP):
+    for p in paths:
         terms = by_path[p]
         L.append("    {")
         ins = sorted({i for _, i, _, _ in terms})
         for i in ins:
-            L.append(f"      const float2 rh{i} = f2mul(R[{p}], h[{i}]);")
+            L.append(f"      const float2 rh{i} = f2mul(R[{p - P0}], h[{i - H_OFF}]);")
         cache = {}
         for o, i, j, c in terms:
             sname = scaled(cache, "s", c, f"rh{i}", L, "      ")
             y = f"Y[{j}]" if c > 0 else f"f2neg(Y[{j}])"
-            L.append(f"      acc[{o}] = f2fma({sname}, {y}, acc[{o}]);")
+            L.append(f"      acc[{omap[o]}] = f2fma({sname}, {y}, acc[{omap[o]}]);")
         L.append("    }")
     L.append("  }")
 
@@ -220,7 +281,7 @@ def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
     L.append("  template <bool WANT_H, bool WANT_Y, bool WANT_R, int NY>")
     L.append("  __device__ __forceinline__ static void bwd2(const float2 (&h)[DIN], const float2 (&Y)[NSH], const float2 (&R)[NP], const float2 (&g)[DOUT],")
     L.append("                                              float2 (&dh)[DIN], float (&dY)[NY], float2 (&dR)[NP]) {")
-    for p in range(NP):
+    for p in paths:
         terms = by_path[p]
         ins = sorted({i for _, i, _, _ in terms})
         js = sorted({j for _, _, j, _ in terms})
@@ -229,7 +290,7 @@ def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
         pre = []
         names = {}
         for o, i, j, c in terms:
-            names[(o, i, j)] = scaled(cache, "a", c, f"g[{o}]", pre, "      ")
+            names[(o, i, j)] = scaled(cache, "a", c, f"g[{omap[o]}]", pre, "      ")
         L.extend(pre)
         L.append("      if (WANT_H || WANT_R) {")
         seen = set()
@@ -241,25 +302,23 @@ def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
                 seen.add(i)
             else:
                 L.append(f"        dhp{i} = f2fma({a}, {y}, dhp{i});")
-        if True:
-            L.append("        if (WANT_R) {")
-            expr = None
-            for n, i in enumerate(ins):
-                if n == 0:
-                    L.append(f"          float2 r = f2mul(h[{i}], dhp{i});")
-                else:
-                    L.append(f"          r = f2fma(h[{i}], dhp{i}, r);")
-            L.append(f"          dR[{p}] = r;")
-            L.append("        }")
-            L.append("        if (WANT_H) {")
-            for i in ins:
-                L.append(f"          dh[{i}] = f2fma(R[{p}], dhp{i}, dh[{i}]);")
-            L.append("        }")
+        L.append("        if (WANT_R) {")
+        for n, i in enumerate(ins):
+            if n == 0:
+                L.append(f"          float2 r = f2mul(h[{i - H_OFF}], dhp{i});")
+            else:
+                L.append(f"          r = f2fma(h[{i - H_OFF}], dhp{i}, r);")
+        L.append(f"          dR[{p - P0}] = r;")
+        L.append("        }")
+        L.append("        if (WANT_H) {")
+        for i in ins:
+            L.append(f"          dh[{i - H_OFF}] = f2fma(R[{p - P0}], dhp{i}, dh[{i - H_OFF}]);")
+        L.append("        }")
         L.append("      }")
         L.append("      if (WANT_Y) {")
         seen = set()
         for o, i, j, c in terms:
-            hh = f"h[{i}]" if c > 0 else f"f2neg(h[{i}])"
+            hh = f"h[{i - H_OFF}]" if c > 0 else f"f2neg(h[{i - H_OFF}])"
             a = names[(o, i, j)]
             if j not in seen:
                 L.append(f"        float2 dyp{j} = f2mul({a}, {hh});")
@@ -267,50 +326,58 @@ def _emit_tp_packed(spec: so3.TPSpec, by_path, L: list) -> None:
             else:
                 L.append(f"        dyp{j} = f2fma({a}, {hh}, dyp{j});")
         for j in js:
-            L.append(f"        dY[{j}] = fmaf(R[{p}].x, dyp{j}.x, fmaf(R[{p}].y, dyp{j}.y, dY[{j}]));")
+            L.append(f"        dY[{j}] = fmaf(R[{p - P0}].x, dyp{j}.x, fmaf(R[{p - P0}].y, dyp{j}.y, dY[{j}]));")
         L.append("      }")
         L.append("    }")
     L.append("  }")
 
-    # ---------------- packed row access: channels (u, u+1), u even
+    # ---------------- packed row access: channels (u, u+1), u even.  hrow points at the group's slice of the staged row
+    # (slot H_OFF of the full row sits at hrow[0]); the node blocks inside the slice keep their [C, 2l+1] layout
     L.append("  __device__ __forceinline__ static void load_h2_smem(const float* hrow, int C, int u, float2 (&h)[DIN]) {")
     off = 0
     for l, _ in spec.node_ls:
         d = 2 * l + 1
         for i in range(d):
-            L.append(f"    h[{off + i}] = make_float2(hrow[C * {off} + u * {d} + {i}], hrow[C * {off} + (u + 1) * {d} + {i}]);")
+            s_ = off + i
+            if H_OFF <= s_ < H_END:
+                L.append(f"    h[{s_ - H_OFF}] = make_float2(hrow[C * {off - H_OFF} + u * {d} + {i}], hrow[C * {off - H_OFF} + (u + 1) * {d} + {i}]);")
         off += d
     L.append("  }")
-    L.append("  template <bool MM> __device__ __forceinline__ static void load_out2(const float* __restrict__ row, int C, int u, float2 (&a)[DOUT]) {")
+    # output blocks of the group's paths, addressed in the FULL row
+    blocks = []
     off = 0
     for l, _ in spec.out_ls:
         d = 2 * l + 1
-        for m in range(d):
-            L.append(f"    if (MM) a[{off + m}] = __ldg(reinterpret_cast<const float2*>(row + (size_t)C * {off} + (size_t){m} * C + u));")
-            L.append(f"    else a[{off + m}] = make_float2(__ldg(row + (size_t)C * {off} + (size_t)u * {d} + {m}), __ldg(row + (size_t)C * {off} + (size_t)(u + 1) * {d} + {m}));")
+        if any((off + m) in omap for m in range(d)):
+            blocks.append((off, d))
         off += d
+    L.append("  template <bool MM> __device__ __forceinline__ static void load_out2(const float* __restrict__ row, int C, int u, float2 (&a)[DOUT]) {")
+    for off, d in blocks:
+        for m in range(d):
+            k = omap[off + m]
+            L.append(f"    if (MM) a[{k}] = __ldg(reinterpret_cast<const float2*>(row + (size_t)C * {off} + (size_t){m} * C + u));")
+            L.append(f"    else a[{k}] = make_float2(__ldg(row + (size_t)C * {off} + (size_t)u * {d} + {m}), __ldg(row + (size_t)C * {off} + (size_t)(u + 1) * {d} + {m}));")
     L.append("  }")
     L.append("  template <bool MM> __device__ __forceinline__ static void store_out2(float* __restrict__ row, int C, int u, const float2 (&a)[DOUT]) {")
-    off = 0
-    for l, _ in spec.out_ls:
-        d = 2 * l + 1
+    for off, d in blocks:
         for m in range(d):
-            L.append(f"    if (MM) *reinterpret_cast<float2*>(row + (size_t)C * {off} + (size_t){m} * C + u) = a[{off + m}];")
+            k = omap[off + m]
+            L.append(f"    if (MM) *reinterpret_cast<float2*>(row + (size_t)C * {off} + (size_t){m} * C + u) = a[{k}];")
             L.append("    else {")
-            L.append(f"      row[(size_t)C * {off} + (size_t)u * {d} + {m}] = a[{off + m}].x;")
-            L.append(f"      row[(size_t)C * {off} + (size_t)(u + 1) * {d} + {m}] = a[{off + m}].y;")
+            L.append(f"      row[(size_t)C * {off} + (size_t)u * {d} + {m}] = a[{k}].x;")
+            L.append(f"      row[(size_t)C * {off} + (size_t)(u + 1) * {d} + {m}] = a[{k}].y;")
             L.append("    }")
-        off += d
     L.append("  }")
-    # fp32 reductions into dh[s]: the 2(2l+1) floats of channels (u, u+1) of one block are contiguous and 8-byte
-    # aligned (u even) -> (2l+1) vector reds instead of 2(2l+1) scalar ones
+    # fp32 reductions into dh[s] (FULL row pointer): the 2(2l+1) floats of channels (u, u+1) of one block are contiguous
+    # and 8-byte aligned (u even) -> (2l+1) vector reds instead of 2(2l+1) scalar ones; only the blocks this group feeds
     L.append("  __device__ __forceinline__ static void atomic_add_h2(float* __restrict__ hrow, int C, int u, const float2 (&h)[DIN], uint64_t pol) {")
     off = 0
     for l, _ in spec.node_ls:
         d = 2 * l + 1
-        flat = [f"h[{off + i}].x" for i in range(d)] + [f"h[{off + i}].y" for i in range(d)]
-        for v in range(d):
-            L.append(f"    red_add_f32x2(hrow + (size_t)C * {off} + (size_t)u * {d} + {2 * v}, {flat[2 * v]}, {flat[2 * v + 1]}, pol);")
+        if all(H_OFF <= off + i < H_END for i in range(d)) and any((off + i) in ins_used for i in range(d)):
+            flat = [f"h[{off + i - H_OFF}].x" for i in range(d)] + [f"h[{off + i - H_OFF}].y" for i in range(d)]
+            for v in range(d):
+                L.append(f"    red_add_f32x2(hrow + (size_t)C * {off} + (size_t)u * {d} + {2 * v}, {flat[2 * v]}, {flat[2 * v + 1]}, pol);")
         off += d
     L.append("  }")
 
@@ -513,10 +580,12 @@ def generate(out_dir: str = GEN_DIR) -> dict:
 
     parts = ["// GENERATED by physicsml_b200/codegen.py — do not edit.", "#pragma once",
              "using pml::f2mul; using pml::f2fma; using pml::f2dup; using pml::f2neg; using pml::red_add_f32x2;",
-             "template <int ID> struct TPCode;"]
+             "template <int ID> struct TPCode;", "template <int ID> struct TPGroups;",
+             "template <int ID, int G> struct TPGroup;"]
     for ident, spec in enumerate(tp_specs):
         parts.append(_emit_tp(spec, ident))
-        registry["tp"][spec.key] = {"id": ident, "np": spec.n_paths, "din": spec.d_in, "dout": spec.d_out, "nsh": spec.n_sh}
+        registry["tp"][spec.key] = {"id": ident, "np": spec.n_paths, "din": spec.d_in, "dout": spec.d_out, "nsh": spec.n_sh,
+                                   "groups": len(tp_path_groups(spec))}
     _write_if_changed(os.path.join(out_dir, "tp_gen.cuh"), "\n".join(parts) + "\n")
 
     parts = ["// GENERATED by physicsml_b200/codegen.py — do not edit.", "#pragma once", "template <int ID> struct SymCode;"]

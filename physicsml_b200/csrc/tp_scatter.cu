@@ -259,16 +259,19 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 
 constexpr int kPipeMaxStages = 8;
 
-template <int ID>
+// T is a path group (TPGroup<ID, g>; the whole signature when it has a single group): it sees its own contiguous slice
+// of the R row (paths P0 .. P0+NP) and of the gathered h row (slots H_OFF .. H_OFF+DIN) and owns its output blocks.
+template <class T>
 struct PipeLayout {
-  using T = TPCode<ID>;
   static constexpr int YPAD = (2 * T::NSH + 3) & ~3;  // Y is staged as duplicated pairs (Y_j, Y_j): packed operands
   __host__ __device__ static int r_floats(int C) { return T::NP * C; }
   __host__ __device__ static int h_floats(int C) { return T::DIN * C; }
   __host__ __device__ static int stage_floats(int C) { return r_floats(C) + h_floats(C) + YPAD + 4; }  // + {edge id, gather id}
   __host__ __device__ static bool supported(int C) {
     // DOUT <= 48: two channels of accumulators (or of the cotangent row) must fit the register file without spilling
-    return (r_floats(C) % 4 == 0) && (h_floats(C) % 4 == 0) && (C % 2 == 0) && C <= 1984 && 2 * T::NSH <= 32 && T::DOUT <= 48;
+    // (wider signatures are cut into path groups by the code generator); slices of a row must start 16-byte aligned
+    return (r_floats(C) % 4 == 0) && (h_floats(C) % 4 == 0) && (C % 2 == 0) && C <= 1984 && 2 * T::NSH <= 32 && T::DOUT <= 48 &&
+           (T::NGROUPS == 1 || C % 4 == 0);
   }
   __host__ __device__ static int consumer_threads(int C) { return ((C / 2 + 31) / 32) * 32; }
 };
@@ -318,10 +321,9 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 // tile ahead, so no load is ever waited for right after it was issued; edges are handed out with shuffles.
 constexpr int kPipeHeaderBytes = 256;  // 16 mbarriers (128 B) + spare, then the stage ring
 
-template <int ID, bool LOAD_R>
+template <class T, bool LOAD_R>
 struct PipeProducer {
-  using L = PipeLayout<ID>;
-  using T = TPCode<ID>;
+  using L = PipeLayout<T>;
   const float *h, *Y, *R;
   const int *gather, *perm, *rowptr;
   float* stages;
@@ -393,8 +395,9 @@ struct PipeProducer {
       if (lane == 0) {
         reinterpret_cast<int2*>(st + rfl + hfl + L::YPAD)[0] = make_int2(e, s);  // released by the arrive below
         mbar_expect_tx(fb, (LOAD_R ? (uint32_t)rfl * 4u : 0u) + (uint32_t)hfl * 4u);
-        if (LOAD_R) bulk_g2s_hint(smem_u32(st), R + (size_t)e * rfl, (uint32_t)rfl * 4u, fb, l2_policy_evict_first());
-        bulk_g2s_hint(smem_u32(st + rfl), h + (size_t)s * hfl, (uint32_t)hfl * 4u, fb, l2_policy_evict_last());
+        if (LOAD_R)
+          bulk_g2s_hint(smem_u32(st), R + ((size_t)e * T::NP_FULL + T::P0) * C, (uint32_t)rfl * 4u, fb, l2_policy_evict_first());
+        bulk_g2s_hint(smem_u32(st + rfl), h + ((size_t)s * T::DIN_FULL + T::H_OFF) * C, (uint32_t)hfl * 4u, fb, l2_policy_evict_last());
       }
       if (lane < 2 * T::NSH) cp_async4(smem_u32(st + rfl + hfl + lane), Y + (size_t)e * T::NSH + (lane >> 1));
       cp_async_mbar_arrive_noinc(fb);
@@ -460,7 +463,7 @@ __device__ __forceinline__ void load_y2_smem(const float* ys, float2 (&Yv)[NSH])
   __syncthreads();                                                                                                     \
   const int lane = threadIdx.x & 31;                                                                                   \
   const bool is_producer = !DEDICATED && threadIdx.x < 32;                                                             \
-  PipeProducer<ID, LOAD_R_> prod;                                                                                      \
+  PipeProducer<T, LOAD_R_> prod;                                                                                      \
   prod.h = h, prod.Y = Y, prod.R = R, prod.gather = gather, prod.perm = perm, prod.rowptr = rowptr;                    \
   prod.stages = stages, prod.full = full, prod.empty = empty, prod.N = N, prod.C = C, prod.nstage = nstage, prod.ts = ts; \
   if (DEDICATED && (int)threadIdx.x >= nthr_c) {                                                                       \
@@ -479,12 +482,11 @@ __device__ __forceinline__ void load_y2_smem(const float* ys, float2 (&Yv)[NSH])
   int stage = 0, consumed = 0;                                                                                         \
   uint32_t phase = 0;
 
-template <int ID, bool DEDICATED>
+template <class T, bool DEDICATED>
 __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                    const int* __restrict__ gather, const int* __restrict__ rowptr,
                                    const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage, int mm) {
-  using T = TPCode<ID>;
-  using L = PipeLayout<ID>;
+  using L = PipeLayout<T>;
   PML_PIPE_PROLOGUE(true, false)
   for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
     const int n0 = ts.first_node(tile), n1 = min(N, n0 + ts.TN);
@@ -515,24 +517,23 @@ __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __r
         T::fwd2(hv, Yv, Rv, acc);
       }
       if (active) {
-        if (mm) T::template store_out2<true>(out + (size_t)n * T::DOUT * C, C, u, acc);
-        else T::template store_out2<false>(out + (size_t)n * T::DOUT * C, C, u, acc);
+        if (mm) T::template store_out2<true>(out + (size_t)n * T::DOUT_FULL * C, C, u, acc);
+        else T::template store_out2<false>(out + (size_t)n * T::DOUT_FULL * C, C, u, acc);
       }
       end = end_next;
     }
   }
 }
 
-template <int ID, bool DEDICATED, bool WANT_H, bool WANT_Y, bool WANT_R>
+template <class T, bool DEDICATED, bool WANT_H, bool WANT_Y, bool WANT_R>
 __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                    const float* __restrict__ g, const int* __restrict__ gather,
                                    const int* __restrict__ rowptr, const int* __restrict__ perm, float* __restrict__ dh,
                                    float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage, int mm) {
-  using T = TPCode<ID>;
-  using L = PipeLayout<ID>;
+  using L = PipeLayout<T>;
   constexpr int NV = next_pow2(T::NSH);
   PML_PIPE_PROLOGUE((WANT_H || WANT_Y), true)
-  const size_t rstride = (size_t)rfl, hstride = (size_t)hfl;
+  const size_t rstride = (size_t)T::NP_FULL * C, hstride = (size_t)T::DIN_FULL * C;  // rows of the FULL tensors
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   // The cotangent pass has no per-node output (dR, dY are per edge, dh is accumulated atomically), so a node's edges
   // may be split between CTAs: every CTA gets the same number of edges whatever the node degrees are.
@@ -552,8 +553,8 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
       const int end_next = (n + 2 <= N) ? min(__ldg(rowptr + n + 2), q_hi) : q_hi;
       float2 gv[T::DOUT];
       if (q < end) {
-        if (mm) T::template load_out2<true>(g + (size_t)n * T::DOUT * C, C, uc, gv);
-        else T::template load_out2<false>(g + (size_t)n * T::DOUT * C, C, uc, gv);
+        if (mm) T::template load_out2<true>(g + (size_t)n * T::DOUT_FULL * C, C, uc, gv);
+        else T::template load_out2<false>(g + (size_t)n * T::DOUT_FULL * C, C, uc, gv);
         if (!active) {
 #pragma unroll
           for (int k = 0; k < T::DOUT; ++k) gv[k] = make_float2(0.f, 0.f);
@@ -589,7 +590,7 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
         T::template bwd2<WANT_H, WANT_Y, WANT_R, NV>(hv, Yv, Rv, gv, dhv, dYv, dRv);
 
         if (WANT_R && active) {
-          float* drow = dR + (size_t)e * rstride + u;
+          float* drow = dR + (size_t)e * rstride + (size_t)T::P0 * C + u;
 #pragma unroll
           for (int p = 0; p < T::NP; ++p) st_stream2_hint(drow + p * C, dRv[p], pol_stream);
         }
@@ -601,9 +602,9 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
           constexpr int sh = 5 - Log2<NV>::value;
           const int j = lane >> sh;
           if ((lane & ((1 << sh) - 1)) == 0 && j < T::NSH) {
-            if (consumer_warps == 1)
+            if (consumer_warps == 1 && T::NGROUPS == 1)
               dY[(size_t)e * T::NSH + j] = dYv[0];
-            else
+            else  // several consumer warps, or several path groups (one launch each), add into the same row
               atomicAdd(dY + (size_t)e * T::NSH + j, dYv[0]);
           }
         }
@@ -672,33 +673,119 @@ __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr
 // test / profiling hook (capi.cu): PML_TP_SIMPLE=1 in the environment selects the non-pipelined kernels
 extern "C" int pml_tp_force_simple(void);
 
+namespace pml {
+
+// ---- pipelined launches, one per path group ------------------------------------------------------------------------
+template <int ID, int G = 0>
+static bool groups_supported(int C) {
+  if constexpr (G >= TPGroups<ID>::N) {
+    return true;
+  } else {
+    return PipeLayout<TPGroup<ID, G>>::supported(C) && groups_supported<ID, G + 1>(C);
+  }
+}
+
+template <class T, bool DEDICATED>
+static bool launch_fwd_pipe(const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
+                            const int* perm, float* out, int N, int C, int mm, cudaStream_t stream) {
+  using PL = PipeLayout<T>;
+  PipeCfg cfg;
+  const int threads = PL::consumer_threads(C) + (DEDICATED ? 32 : 0);
+  const int sbytes = PL::stage_floats(C) * 4;
+  if (!pipe_config<tp_fwd_pipe_kernel<T, DEDICATED>>(threads, sbytes, C, N < kSmallGraphNodes, &cfg)) return false;
+  // small graphs: one CTA per node (tile), more CTAs than slots: the hardware hands a free slot the next node, so
+  // nodes of different degree balance themselves instead of being paired statically
+  // (config 2, 1304 nodes on 740 slots: 65.6 -> 57.3 us, 57.5 -> 65.8 % of HBM peak)
+  if (DEDICATED && N < kSmallGraphNodes) cfg.grid = N < 4 * cfg.grid ? N : 4 * cfg.grid;
+  tp_fwd_pipe_kernel<T, DEDICATED><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
+  return true;
+}
+
+template <int ID, int G = 0>
+static bool fwd_pipe_groups(bool dedicated, const float* h, const float* Y, const float* R, const int* gather,
+                            const int* rowptr, const int* perm, float* out, int N, int C, int mm, cudaStream_t stream) {
+  if constexpr (G >= TPGroups<ID>::N) {
+    return true;
+  } else {
+    using T = TPGroup<ID, G>;
+    bool ok;
+    if constexpr (TPGroups<ID>::N == 1) {  // the producer-placement flip is a profiling aid of single-group signatures
+      ok = dedicated ? launch_fwd_pipe<T, true>(h, Y, R, gather, rowptr, perm, out, N, C, mm, stream)
+                     : launch_fwd_pipe<T, false>(h, Y, R, gather, rowptr, perm, out, N, C, mm, stream);
+    } else {
+      ok = launch_fwd_pipe<T, true>(h, Y, R, gather, rowptr, perm, out, N, C, mm, stream);
+    }
+    return ok && fwd_pipe_groups<ID, G + 1>(dedicated, h, Y, R, gather, rowptr, perm, out, N, C, mm, stream);
+  }
+}
+
+template <class T, bool D, bool H_, bool Y_, bool R_>
+static bool launch_bwd_pipe_one(const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                                const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, int mm,
+                                cudaStream_t stream) {
+  using PL = PipeLayout<T>;
+  PipeCfg cfg;
+  const int threads = PL::consumer_threads(C) + (D ? 32 : 0);
+  const int sbytes = PL::stage_floats(C) * 4;
+  if (!pipe_config<tp_bwd_pipe_kernel<T, D, H_, Y_, R_>>(threads, sbytes, C, N < kSmallGraphNodes, &cfg)) return false;
+  tp_bwd_pipe_kernel<T, D, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N,
+                                                                                 C, cfg.nstage, mm);
+  return true;
+}
+
+template <class T, bool D>
+static bool launch_bwd_pipe(int mask, const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                            const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, int mm,
+                            cudaStream_t stream) {
+#define PML_TP_BWD_PIPE(M, H_, Y_, R_) \
+  case M:                              \
+    return launch_bwd_pipe_one<T, D, H_, Y_, R_>(h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream);
+  switch (mask) {
+    PML_TP_BWD_PIPE(1, true, false, false)
+    PML_TP_BWD_PIPE(2, false, true, false)
+    PML_TP_BWD_PIPE(3, true, true, false)
+    PML_TP_BWD_PIPE(4, false, false, true)
+    PML_TP_BWD_PIPE(5, true, false, true)
+    PML_TP_BWD_PIPE(6, false, true, true)
+    PML_TP_BWD_PIPE(7, true, true, true)
+  }
+#undef PML_TP_BWD_PIPE
+  return false;
+}
+
+template <int ID, int G = 0>
+static bool bwd_pipe_groups(bool dedicated, int mask, const float* h, const float* Y, const float* R, const float* g,
+                            const int* gather, const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N,
+                            int C, int mm, cudaStream_t stream) {
+  if constexpr (G >= TPGroups<ID>::N) {
+    return true;
+  } else {
+    using T = TPGroup<ID, G>;
+    bool ok;
+    if constexpr (TPGroups<ID>::N == 1) {
+      ok = dedicated ? launch_bwd_pipe<T, true>(mask, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream)
+                     : launch_bwd_pipe<T, false>(mask, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream);
+    } else {
+      ok = launch_bwd_pipe<T, false>(mask, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream);
+    }
+    return ok && bwd_pipe_groups<ID, G + 1>(dedicated, mask, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream);
+  }
+}
+
+}  // namespace pml
+
 // Launchers (one pair per compiled signature; dispatched by id in capi.cu).  Streams are the caller's.
 extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const float* Y, const float* R, const int* gather,
                                                        const int* rowptr, const int* perm, float* out, int N, int C,
                                                        int mm, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
-  using PL = pml::PipeLayout<PML_TP_ID>;
   const int mode = pml_tp_force_simple();  // bit0: streaming kernels; bit1 / bit2: flip the fwd / bwd producer placement
-  if (PL::supported(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
-    pml::PipeCfg cfg;
-    const bool dedicated = !(mode & 2);
-    const int threads = PL::consumer_threads(C) + (dedicated ? 32 : 0);
-    const int sbytes = PL::stage_floats(C) * 4;
-    if (dedicated) {
-      if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, true>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {
-        // small graphs: one CTA per node (tile), more CTAs than slots: the hardware hands a free slot the next node, so
-        // nodes of different degree balance themselves instead of being paired statically
-        // (config 2, 1304 nodes on 740 slots: 65.6 -> 57.3 us, 57.5 -> 65.8 % of HBM peak)
-        if (N < pml::kSmallGraphNodes) cfg.grid = N < 4 * cfg.grid ? N : 4 * cfg.grid;
-        pml::tp_fwd_pipe_kernel<PML_TP_ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
-        PML_CHECK_LAUNCH();
-        return PML_OK;
-      }
-    } else if (pml::pipe_config<pml::tp_fwd_pipe_kernel<PML_TP_ID, false>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {
-      pml::tp_fwd_pipe_kernel<PML_TP_ID, false><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
+  if (pml::groups_supported<PML_TP_ID>(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
+    if (pml::fwd_pipe_groups<PML_TP_ID>(!(mode & 2), h, Y, R, gather, rowptr, perm, out, N, C, mm, stream)) {
       PML_CHECK_LAUNCH();
       return PML_OK;
     }
+    cudaGetLastError();
   }
   const int nslab = (C + 31) / 32;
   const int wpb = 4;
@@ -708,49 +795,20 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
   return PML_OK;
 }
 
-// dh and (when C > 32) dY must be zero-initialised by the caller; dR is fully overwritten.
+// dh and dY must be zero-initialised by the caller when C > 32 or the signature has several path groups (pml_tp_num_groups);
+// dR is fully overwritten.
 extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const float* Y, const float* R, const float* g,
                                                        const int* gather, const int* rowptr, const int* perm, float* dh,
                                                        float* dY, float* dR, int N, int C, int mm, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
   const int mask = (dh ? 1 : 0) | (dY ? 2 : 0) | (dR ? 4 : 0);
-  using PL = pml::PipeLayout<PML_TP_ID>;
   const int mode = pml_tp_force_simple();
-  if (mask != 0 && PL::supported(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
-    const bool dedicated = (mode & 4) != 0;
-    const int threads = PL::consumer_threads(C) + (dedicated ? 32 : 0);
-    const int sbytes = PL::stage_floats(C) * 4;
-    pml::PipeCfg cfg;
-    bool done = false;
-#define PML_TP_BWD_PIPE_D(D_, H_, Y_, R_)                                                                               \
-  if (pml::pipe_config<pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_>>(threads, sbytes, C, N < pml::kSmallGraphNodes, &cfg)) {                  \
-    pml::tp_bwd_pipe_kernel<PML_TP_ID, D_, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(                         \
-        h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, cfg.nstage, mm);                                             \
-    done = true;                                                                                                        \
-  }
-#define PML_TP_BWD_PIPE(M, H_, Y_, R_)           \
-  case M:                                        \
-    if (dedicated) {                             \
-      PML_TP_BWD_PIPE_D(true, H_, Y_, R_)        \
-    } else {                                     \
-      PML_TP_BWD_PIPE_D(false, H_, Y_, R_)       \
-    }                                            \
-    break;
-    switch (mask) {
-      PML_TP_BWD_PIPE(1, true, false, false)
-      PML_TP_BWD_PIPE(2, false, true, false)
-      PML_TP_BWD_PIPE(3, true, true, false)
-      PML_TP_BWD_PIPE(4, false, false, true)
-      PML_TP_BWD_PIPE(5, true, false, true)
-      PML_TP_BWD_PIPE(6, false, true, true)
-      PML_TP_BWD_PIPE(7, true, true, true)
-    }
-#undef PML_TP_BWD_PIPE_D
-#undef PML_TP_BWD_PIPE
-    if (done) {
+  if (mask != 0 && pml::groups_supported<PML_TP_ID>(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
+    if (pml::bwd_pipe_groups<PML_TP_ID>((mode & 4) != 0, mask, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream)) {
       PML_CHECK_LAUNCH();
       return PML_OK;
     }
+    cudaGetLastError();
   }
   const int nslab = (C + 31) / 32;
   const int wpb = 4;

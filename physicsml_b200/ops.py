@@ -257,7 +257,7 @@ def tp_scatter_bwd(h: Tensor, Y: Tensor, R: Tensor, g: Tensor, gather: Tensor, r
     h, Y, R, g = _f32c(h), _f32c(Y), _f32c(R), _f32c(g)
     N = rowptr.numel() - 1
     dh = torch.zeros_like(h) if need_h else _new_empty(h, 0)
-    dY = (torch.zeros_like(Y) if pl.C > 32 else _empty_like(Y)) if need_y else _new_empty(Y, 0)
+    dY = (torch.zeros_like(Y) if (pl.C > 32 or pl.n_groups > 1) else _empty_like(Y)) if need_y else _new_empty(Y, 0)
     dR = _empty_like(R) if need_r else _new_empty(R, 0)
     if need_h or need_y or need_r:
         _call("pml_tp_bwd_ex", pl.spec_id, _p(h), _p(Y), _p(R), _p(g), _p(gather), _p(rowptr), _p(perm),

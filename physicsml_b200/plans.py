@@ -271,6 +271,7 @@ class TPPlan:
                 "physicsml_b200.codegen.default_tp_specs() and rebuild"
             )
         self.spec_id = reg[self.spec.key]["id"]
+        self.n_groups = int(reg[self.spec.key].get("groups", 1))  # path groups of the pipelined kernels (one launch each)
         self.NP, self.DIN, self.DOUT, self.NSH = self.spec.n_paths, self.spec.d_in, self.spec.d_out, self.spec.n_sh
         # irreps of the aggregated message, sorted, one block per path (mul C each)
         self.out_irreps = [(self.C, l, p) for l, p in self.spec.out_ls]
