@@ -262,20 +262,24 @@ int pml_scan_i32(const int* counts, int* out, int n, pml_stream_t stream);
  * linked_cell.py:129-355).  Two-phase (E is data dependent): *_count -> deg[N]; caller scans to rowptr[N+1], reads
  * E = rowptr[N], allocates; *_fill -> packed keys; sort_segments; emit.  Output sorted by (sender, receiver, shift);
  * PBC predicate d^2 < rc^2, open-boundary predicate d^2 <= rc^2; shifts refer to the unwrapped coordinates. */
-typedef struct {
-  double inv[9]; /* inverse cell (row-major): frac = pos . inv */
-  float cell[9]; /* lattice vectors as rows */
-  int nb[3];     /* bins per axis in fractional space */
-  int R[3];      /* stencil half-width per axis */
-  float rc2;
-} pml_nl_cell;
-int pml_nl_pbc_bin(const float* pos, const pml_nl_cell* cell, float* wpos, int* fl, int* bin, int* bincount, int N,
-                   pml_stream_t stream);
+/* Periodic path: the geometry of every structure of a (collated) batch is derived ON THE DEVICE by pml_nl_setup — cell
+ * inverse in fp64, bins, stencil widths, a private bin range per structure — so there is no host round trip and a whole
+ * batch of structures (one shared cell: cell_stride 0, the reference's batch contract graph_dataset.py:197-200,385; or
+ * one cell each: cell_stride 9) is binned and walked in ONE pass.  graphs_out: opaque device table of
+ * G * PML_NL_GRAPH_BYTES bytes; gptr [G+1] atom offsets; batch: int64 structure id per atom (sorted) or NULL when G == 1;
+ * bin arrays sized by the caller with the bound 64*G + 4*N; *err (device, zeroed) gets bit 1 if a stencil would span
+ * more than 127 images. */
+#define PML_NL_GRAPH_BYTES 144
+int pml_nl_setup(const float* cells, int cell_stride, const int* gptr, int G, float cutoff, void* graphs_out,
+                 int* nbins_total, int* err, pml_stream_t stream);
+int pml_nl_pbc_bin(const float* pos, const long long* batch, const void* graphs, float* wpos, int* fl, int* bin,
+                   int* bincount, int N, pml_stream_t stream);
 int pml_nl_pbc_fill_bins(const int* bin, const int* binptr, int* cursor, int* sorted, int N, pml_stream_t stream);
-int pml_nl_pbc_count(const float* wpos, const int* bin, const int* binptr, const int* sorted, const pml_nl_cell* cell,
-                     int self_interaction, int* deg, int N, pml_stream_t stream);
-int pml_nl_pbc_fill(const float* wpos, const int* bin, const int* binptr, const int* sorted, const pml_nl_cell* cell,
-                    int self_interaction, const int* rowptr, unsigned long long* keys, int N, pml_stream_t stream);
+int pml_nl_pbc_count(const float* wpos, const long long* batch, const int* bin, const int* binptr, const int* sorted,
+                     const void* graphs, float rc2, int self_interaction, int* deg, int N, pml_stream_t stream);
+int pml_nl_pbc_fill(const float* wpos, const long long* batch, const int* bin, const int* binptr, const int* sorted,
+                    const void* graphs, float rc2, int self_interaction, const int* rowptr, unsigned long long* keys, int N,
+                    pml_stream_t stream);
 int pml_nl_open_count(const float* pos, const long long* batch, const int* gptr, float rc2, int self_interaction, int* deg,
                       int N, pml_stream_t stream);
 int pml_nl_open_fill(const float* pos, const long long* batch, const int* gptr, float rc2, int self_interaction,

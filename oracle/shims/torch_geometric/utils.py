@@ -13,9 +13,14 @@ def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = 0, dim_size=None,
 
 
 def coalesce(edge_index, edge_attr=None, num_nodes=None, reduce: str = "sum"):
-    """Sort edges by (row, col) and merge duplicates by summation (only needed so the reference file imports;
-    the bond-edge merge branch itself is out of scope)."""
-    n = int(num_nodes) if num_nodes is not None else int(edge_index.max()) + 1
+    """Sort edges by (row, col) and merge duplicates by summation (PyG 2.5.3 coalesce, reduce="sum"): used by the
+    bond-edge merge branch of the reference's neighbour list (neighbourhood_list_torch.py:98-156).  num_nodes stays a
+    tensor when it is one: the reference wraps this function in torch.jit.trace, which would bake int() of the example
+    input into the graph."""
+    if num_nodes is None:
+        n = edge_index.max() + 1
+    else:
+        n = num_nodes if torch.is_tensor(num_nodes) else int(num_nodes)
     key = edge_index[0] * n + edge_index[1]
     uniq, inv = torch.unique(key, return_inverse=True)
     out_index = torch.stack([torch.div(uniq, n, rounding_mode="floor"), uniq % n], dim=0)

@@ -10,8 +10,9 @@ import json
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libphysicsml_b200.so")
-REGISTRY_PATH = os.path.join(HERE, "csrc", "gen", "registry.json")
+# PML_LIB / PML_REGISTRY select a tuning variant built by `python -m physicsml_b200.build --variant <tag>` (A/B runs only)
+LIB_PATH = os.environ.get("PML_LIB") or os.path.join(HERE, "csrc", "libphysicsml_b200.so")
+REGISTRY_PATH = os.environ.get("PML_REGISTRY") or os.path.join(HERE, "csrc", "gen", "registry.json")
 
 GEMM_MAX_CHUNKS = 8
 EL_MAX_PATHS = 8
@@ -73,8 +74,7 @@ class GatePlanStruct(C.Structure):
     ]
 
 
-class NLCell(C.Structure):
-    _fields_ = [("inv", C.c_double * 9), ("cell", C.c_float * 9), ("nb", C.c_int * 3), ("R", C.c_int * 3), ("rc2", C.c_float)]
+NL_GRAPH_BYTES = 144  # PML_NL_GRAPH_BYTES: per-structure geometry record written by pml_nl_setup (opaque)
 
 
 class SymWeights(C.Structure):
@@ -129,10 +129,11 @@ SIGNATURES = {
     "pml_split_edge_index": [_P, _P, _P, _I, _P],
     "pml_irreps_to_channel": [_P, _P, _LL, _I, _I, _I, _P],
     "pml_scan_i32": [_P, _P, _I, _P],
-    "pml_nl_pbc_bin": [_P, C.POINTER(NLCell), _P, _P, _P, _P, _I, _P],
+    "pml_nl_setup": [_P, _I, _P, _I, _F, _P, _P, _P, _P],
+    "pml_nl_pbc_bin": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     "pml_nl_pbc_fill_bins": [_P, _P, _P, _P, _I, _P],
-    "pml_nl_pbc_count": [_P, _P, _P, _P, C.POINTER(NLCell), _I, _P, _I, _P],
-    "pml_nl_pbc_fill": [_P, _P, _P, _P, C.POINTER(NLCell), _I, _P, _P, _I, _P],
+    "pml_nl_pbc_count": [_P, _P, _P, _P, _P, _P, _F, _I, _P, _I, _P],
+    "pml_nl_pbc_fill": [_P, _P, _P, _P, _P, _P, _F, _I, _P, _P, _I, _P],
     "pml_nl_open_count": [_P, _P, _P, _F, _I, _P, _I, _P],
     "pml_nl_open_fill": [_P, _P, _P, _F, _I, _P, _P, _I, _P],
     "pml_nl_sort_segments": [_P, _P, _I, _P, _P],

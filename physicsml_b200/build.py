@@ -47,15 +47,24 @@ def _compile(job):
     return obj, True
 
 
-def build(verbose: bool = True, jobs: int | None = None) -> str:
+def build(verbose: bool = True, jobs: int | None = None, variant: str | None = None) -> str:
+    """variant: build a tuning variant next to the product library (csrc/libphysicsml_b200_<variant>.so with its own
+    generated tensor-product header under csrc/gen_<variant>/, e.g. another PML_TP_GROUP_DOUT); select it at run time
+    with PML_LIB=<.so> PML_REGISTRY=<gen dir>/registry.json.  The product build is variant=None."""
     from . import codegen
 
-    reg = codegen.generate()
+    global OBJ, LIB
+    gen_dir = os.path.join(CSRC, "gen" if not variant else f"gen_{variant}")
+    if variant:
+        OBJ = os.path.join(CSRC, f"build_{variant}")
+        LIB = os.path.join(CSRC, f"libphysicsml_b200_{variant}.so")
+    reg = codegen.generate(gen_dir)
     os.makedirs(OBJ, exist_ok=True)
     common = os.path.join(CSRC, "pml_common.cuh")
-    tp_gen = os.path.join(CSRC, "gen", "tp_gen.cuh")
+    tp_gen = os.path.join(gen_dir, "tp_gen.cuh")
     sym_gen = os.path.join(CSRC, "gen", "sym_gen.cuh")
     ids = os.path.join(CSRC, "gen", "pml_ids.h")
+    tp_defs = [f'-DPML_GEN_TP="{os.path.basename(gen_dir)}/tp_gen.cuh"'] if variant else []
     work = []
     for name in ("gemm", "gemm_tc", "gemm_wide", "featurise", "element_linear", "misc", "neighbour_list", "gate", "adam"):
         src = os.path.join(CSRC, name + ".cu")
@@ -64,7 +73,7 @@ def build(verbose: bool = True, jobs: int | None = None) -> str:
     work.append((os.path.join(CSRC, "capi.cu"), os.path.join(OBJ, "capi.o"), [], [common, ids]))
     for v in reg["tp"].values():
         i = v["id"]
-        work.append((os.path.join(CSRC, "tp_scatter.cu"), os.path.join(OBJ, f"tp_{i}.o"), [f"-DPML_TP_ID={i}"], [common, tp_gen]))
+        work.append((os.path.join(CSRC, "tp_scatter.cu"), os.path.join(OBJ, f"tp_{i}.o"), [f"-DPML_TP_ID={i}"] + tp_defs, [common, tp_gen]))
     # biggest symmetric-contraction specs first so the pool stays busy
     for v in sorted(reg["sym"].values(), key=lambda v: -sum(sum(r) for r in v["K"])):
         i = v["id"]
@@ -86,4 +95,4 @@ def build(verbose: bool = True, jobs: int | None = None) -> str:
 
 
 if __name__ == "__main__":
-    build()
+    build(variant=sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None)

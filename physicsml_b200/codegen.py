@@ -183,7 +183,9 @@ def _emit_tp(spec: so3.TPSpec, ident: int) -> str:
     return "\n".join(L)
 
 
-PIPE_MAX_DOUT = 48  # two channels of accumulators (or of the cotangent row) per thread must fit the register file
+# two channels of accumulators (or of the cotangent row) per thread must fit the register file: 48 is the hard limit of the
+# pipelined kernels; a smaller value cuts narrower signatures into groups too (more warps per edge, fewer registers each)
+PIPE_MAX_DOUT = int(os.environ.get("PML_TP_GROUP_DOUT", "48"))
 
 
 def tp_path_groups(spec: so3.TPSpec) -> list:

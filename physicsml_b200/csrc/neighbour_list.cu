@@ -17,13 +17,67 @@
 
 namespace pml {
 
+// Geometry of ONE periodic structure of a batch, computed on the device (nl_setup_kernel): no host round trip for the
+// cell inverse, and a collated batch of structures (each with its own cell, or all sharing one) is binned in one pass —
+// structure g owns the bins [bin_off, bin_off + nb0*nb1*nb2), so atoms only ever meet atoms of their own structure.
 struct NLCell {
   double inv[9];   // inverse cell, row-major: frac = pos . inv
   float cell[9];   // cell rows
   int nb[3];       // bins per axis (in fractional space)
   int R[3];        // stencil half-width per axis (in bins)
-  float rc2;
+  int bin_off;     // first bin of this structure
+  int pad;
 };
+static_assert(sizeof(NLCell) == 144, "pml_nl_graph layout");
+
+// cells: [3,3] (cell_stride 0: shared by every structure — the reference's batch contract, graph_dataset.py:197-200) or
+// [G,3,3] (cell_stride 9); gptr [G+1] atom offsets.  Same bin policy as the host version it replaces: bins at least
+// cutoff wide (in perpendicular height), at most 128 per axis and max(64, 4 n_g) per structure, stencil half-width
+// R = ceil(cutoff * nb / height).  err bit 1: a stencil spans more than 127 images (unsupported).
+__global__ void nl_setup_kernel(const float* __restrict__ cells, int cell_stride, const int* __restrict__ gptr, int G,
+                                float cutoff, NLCell* __restrict__ out, int* __restrict__ nbins_total, int* __restrict__ err) {
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float* cf = cells + (size_t)g * cell_stride;
+    double c[9];
+    for (int k = 0; k < 9; ++k) c[k] = (double)cf[k];
+    const double det = c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) + c[2] * (c[3] * c[7] - c[4] * c[6]);
+    const double id = 1.0 / det;
+    NLCell r;
+    r.inv[0] = (c[4] * c[8] - c[5] * c[7]) * id; r.inv[1] = (c[2] * c[7] - c[1] * c[8]) * id; r.inv[2] = (c[1] * c[5] - c[2] * c[4]) * id;
+    r.inv[3] = (c[5] * c[6] - c[3] * c[8]) * id; r.inv[4] = (c[0] * c[8] - c[2] * c[6]) * id; r.inv[5] = (c[2] * c[3] - c[0] * c[5]) * id;
+    r.inv[6] = (c[3] * c[7] - c[4] * c[6]) * id; r.inv[7] = (c[1] * c[6] - c[0] * c[7]) * id; r.inv[8] = (c[0] * c[4] - c[1] * c[3]) * id;
+    for (int k = 0; k < 9; ++k) r.cell[k] = cf[k];
+    double hgt[3];
+    const int n_g = gptr[g + 1] - gptr[g];
+    const int max_bins = max(64, 4 * n_g);
+    for (int k = 0; k < 3; ++k) {  // perpendicular height along axis k = 1 / |column k of inv|
+      hgt[k] = 1.0 / sqrt(r.inv[k] * r.inv[k] + r.inv[3 + k] * r.inv[3 + k] + r.inv[6 + k] * r.inv[6 + k]);
+      r.nb[k] = max(1, min(128, (int)floor(hgt[k] / (double)cutoff)));
+    }
+    while ((long long)r.nb[0] * r.nb[1] * r.nb[2] > max_bins) {
+      int k = 0;
+      if (r.nb[1] > r.nb[k]) k = 1;
+      if (r.nb[2] > r.nb[k]) k = 2;
+      r.nb[k] = max(1, r.nb[k] / 2);
+    }
+    for (int k = 0; k < 3; ++k) {
+      r.R[k] = (int)ceil((double)cutoff * r.nb[k] / hgt[k] - 1e-12);
+      if (r.R[k] > 127) atomicOr(err, 2);
+    }
+    r.bin_off = 0;
+    r.pad = 0;
+    out[g] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int g = 0; g < G; ++g) {
+      out[g].bin_off = off;
+      off += out[g].nb[0] * out[g].nb[1] * out[g].nb[2];
+    }
+    *nbins_total = off;
+  }
+}
 
 __device__ __forceinline__ unsigned long long pack_key(int j, int sx, int sy, int sz) {
   return ((unsigned long long)(unsigned)j << 32) | ((unsigned long long)(sx + 128) << 16) |
@@ -31,11 +85,13 @@ __device__ __forceinline__ unsigned long long pack_key(int j, int sx, int sy, in
 }
 
 // ---- stage 1: wrap + bin ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) nl_bin_kernel(const float* __restrict__ pos, NLCell c, float* __restrict__ wpos,
+__global__ void __launch_bounds__(256) nl_bin_kernel(const float* __restrict__ pos, const long long* __restrict__ batch,
+                                                     const NLCell* __restrict__ graphs, float* __restrict__ wpos,
                                                      int* __restrict__ fl, int* __restrict__ bin, int* __restrict__ counts,
                                                      int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  const NLCell& c = graphs[batch ? (int)batch[i] : 0];
   const double p[3] = {(double)pos[3 * i], (double)pos[3 * i + 1], (double)pos[3 * i + 2]};
   double f[3];
   int b[3];
@@ -52,7 +108,7 @@ __global__ void __launch_bounds__(256) nl_bin_kernel(const float* __restrict__ p
 #pragma unroll
   for (int a = 0; a < 3; ++a)
     wpos[3 * i + a] = (float)(f[0] * (double)c.cell[a] + f[1] * (double)c.cell[3 + a] + f[2] * (double)c.cell[6 + a]);
-  const int bl = (b[0] * c.nb[1] + b[1]) * c.nb[2] + b[2];
+  const int bl = c.bin_off + (b[0] * c.nb[1] + b[1]) * c.nb[2] + b[2];
   bin[i] = bl;
   atomicAdd(counts + bl, 1);
 }
@@ -67,16 +123,18 @@ __global__ void __launch_bounds__(256) nl_fill_bins_kernel(const int* __restrict
 
 // ---- stage 2: one warp per atom walks the stencil; FILL=false counts, FILL=true writes packed keys -------------------------
 template <bool FILL>
-__global__ void __launch_bounds__(256) nl_pbc_edges_kernel(const float* __restrict__ wpos, const int* __restrict__ bin,
-                                                           const int* __restrict__ binptr, const int* __restrict__ sorted,
-                                                           NLCell c, int self_interaction, int* __restrict__ deg,
+__global__ void __launch_bounds__(256) nl_pbc_edges_kernel(const float* __restrict__ wpos, const long long* __restrict__ batch,
+                                                           const int* __restrict__ bin, const int* __restrict__ binptr,
+                                                           const int* __restrict__ sorted, const NLCell* __restrict__ graphs,
+                                                           float rc2, int self_interaction, int* __restrict__ deg,
                                                            const int* __restrict__ rowptr, unsigned long long* __restrict__ keys,
                                                            int N) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= N) return;
+  const NLCell& c = graphs[batch ? (int)batch[i] : 0];
   const float xi = wpos[3 * i], yi = wpos[3 * i + 1], zi = wpos[3 * i + 2];
-  const int bl = bin[i];
+  const int bl = bin[i] - c.bin_off;
   const int b2 = bl % c.nb[2], b1 = (bl / c.nb[2]) % c.nb[1], b0 = bl / (c.nb[2] * c.nb[1]);
   int n_out = 0;
   const int base = FILL ? rowptr[i] : 0;
@@ -98,7 +156,7 @@ __global__ void __launch_bounds__(256) nl_pbc_edges_kernel(const float* __restri
         for (int a = 0; a < 3; ++a)
           tr[a] = __fadd_rn(__fadd_rn(__fmul_rn((float)s0, c.cell[a]), __fmul_rn((float)s1, c.cell[3 + a])),
                             __fmul_rn((float)s2, c.cell[6 + a]));
-        const int nbin = (q0 * c.nb[1] + q1) * c.nb[2] + q2;
+        const int nbin = c.bin_off + (q0 * c.nb[1] + q1) * c.nb[2] + q2;
         const int beg = binptr[nbin], end = binptr[nbin + 1];
         for (int q = beg; q < end; q += 32) {
           const int idx = q + lane;
@@ -111,7 +169,7 @@ __global__ void __launch_bounds__(256) nl_pbc_edges_kernel(const float* __restri
             const float dy = __fsub_rn(__fsub_rn(yi, wpos[3 * j + 1]), tr[1]);
             const float dz = __fsub_rn(__fsub_rn(zi, wpos[3 * j + 2]), tr[2]);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            ok = d2 < c.rc2;
+            ok = d2 < rc2;
             if (j == i && s0 == 0 && s1 == 0 && s2 == 0 && !self_interaction) ok = false;
           }
           const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -237,35 +295,26 @@ __global__ void __launch_bounds__(256) nl_emit_kernel(const unsigned long long* 
 // C ABI.  Two-phase because E is data dependent:  *_count fills deg[N] and the caller builds rowptr (pml_scan_i32) and
 // reads E = rowptr[N] on the host to allocate; *_fill then writes the sorted edge list.
 // =========================================================================================================================
-extern "C" {
-typedef struct {
-  double inv[9];
-  float cell[9];
-  int nb[3];
-  int R[3];
-  float rc2;
-} pml_nl_cell;
+// graphs_out: device buffer of G * 144 bytes (pml_nl_graph, opaque to the caller); nbins_total / err: device ints
+// (err zeroed by the caller; bit 1 = a stencil spans more than 127 images).  Bins per structure <= max(64, 4 n_g), so
+// 64 G + 4 N is an upper bound the caller can size the bin arrays with before the kernel has run.
+extern "C" int pml_nl_setup(const float* cells, int cell_stride, const int* gptr, int G, float cutoff, void* graphs_out,
+                            int* nbins_total, int* err, cudaStream_t stream) {
+  if (G <= 0) return PML_OK;
+  if (cell_stride != 0 && cell_stride != 9) return PML_ERR_BAD_ARG;
+  pml::nl_setup_kernel<<<1, 256, 0, stream>>>(cells, cell_stride, gptr, G, cutoff, reinterpret_cast<pml::NLCell*>(graphs_out),
+                                              nbins_total, err);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
 }
 
-static inline pml::NLCell to_cell(const pml_nl_cell* c) {
-  pml::NLCell r;
-  for (int k = 0; k < 9; ++k) {
-    r.inv[k] = c->inv[k];
-    r.cell[k] = c->cell[k];
-  }
-  for (int k = 0; k < 3; ++k) {
-    r.nb[k] = c->nb[k];
-    r.R[k] = c->R[k];
-  }
-  r.rc2 = c->rc2;
-  return r;
-}
-
-// wpos [N,3] f32, fl [N,3] i32, bin [N] i32, bincount [nbins] i32 (zeroed by the caller)
-extern "C" int pml_nl_pbc_bin(const float* pos, const pml_nl_cell* cell, float* wpos, int* fl, int* bin, int* bincount, int N,
-                              cudaStream_t stream) {
+// batch: int64 structure id per atom (sorted) or NULL (single structure); graphs from pml_nl_setup.
+// wpos [N,3] f32, fl [N,3] i32, bin [N] i32, bincount [>= nbins] i32 (zeroed by the caller)
+extern "C" int pml_nl_pbc_bin(const float* pos, const long long* batch, const void* graphs, float* wpos, int* fl, int* bin,
+                              int* bincount, int N, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
-  pml::nl_bin_kernel<<<pml::ceil_div(N, 256), 256, 0, stream>>>(pos, to_cell(cell), wpos, fl, bin, bincount, N);
+  pml::nl_bin_kernel<<<pml::ceil_div(N, 256), 256, 0, stream>>>(pos, batch, reinterpret_cast<const pml::NLCell*>(graphs), wpos, fl,
+                                                               bin, bincount, N);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -278,21 +327,21 @@ extern "C" int pml_nl_pbc_fill_bins(const int* bin, const int* binptr, int* curs
   return PML_OK;
 }
 
-extern "C" int pml_nl_pbc_count(const float* wpos, const int* bin, const int* binptr, const int* sorted,
-                                const pml_nl_cell* cell, int self_interaction, int* deg, int N, cudaStream_t stream) {
+extern "C" int pml_nl_pbc_count(const float* wpos, const long long* batch, const int* bin, const int* binptr, const int* sorted,
+                                const void* graphs, float rc2, int self_interaction, int* deg, int N, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
   pml::nl_pbc_edges_kernel<false><<<pml::ceil_div((long long)N * 32, 256), 256, 0, stream>>>(
-      wpos, bin, binptr, sorted, to_cell(cell), self_interaction, deg, nullptr, nullptr, N);
+      wpos, batch, bin, binptr, sorted, reinterpret_cast<const pml::NLCell*>(graphs), rc2, self_interaction, deg, nullptr, nullptr, N);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
 
-extern "C" int pml_nl_pbc_fill(const float* wpos, const int* bin, const int* binptr, const int* sorted,
-                               const pml_nl_cell* cell, int self_interaction, const int* rowptr, unsigned long long* keys,
-                               int N, cudaStream_t stream) {
+extern "C" int pml_nl_pbc_fill(const float* wpos, const long long* batch, const int* bin, const int* binptr, const int* sorted,
+                               const void* graphs, float rc2, int self_interaction, const int* rowptr,
+                               unsigned long long* keys, int N, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
   pml::nl_pbc_edges_kernel<true><<<pml::ceil_div((long long)N * 32, 256), 256, 0, stream>>>(
-      wpos, bin, binptr, sorted, to_cell(cell), self_interaction, nullptr, rowptr, keys, N);
+      wpos, batch, bin, binptr, sorted, reinterpret_cast<const pml::NLCell*>(graphs), rc2, self_interaction, nullptr, rowptr, keys, N);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

@@ -14,7 +14,10 @@
 //
 // Compiled once per tensor-product signature: -DPML_TP_ID=<id> selects the generated TPCode<id> (gen/tp_gen.cuh).
 #include "pml_common.cuh"
-#include "gen/tp_gen.cuh"
+#ifndef PML_GEN_TP  // a build variant (physicsml_b200.build --variant) points this at its own generated header
+#define PML_GEN_TP "gen/tp_gen.cuh"
+#endif
+#include PML_GEN_TP
 
 #ifndef PML_TP_ID
 #error "compile with -DPML_TP_ID=<spec id>"
@@ -267,11 +270,13 @@ struct PipeLayout {
   __host__ __device__ static int r_floats(int C) { return T::NP * C; }
   __host__ __device__ static int h_floats(int C) { return T::DIN * C; }
   __host__ __device__ static int stage_floats(int C) { return r_floats(C) + h_floats(C) + YPAD + 4; }  // + {edge id, gather id}
+  __host__ __device__ static bool rows_ok(int C) {
+    return (r_floats(C) % 4 == 0) && (h_floats(C) % 4 == 0) && (C % 2 == 0) && C <= 1984 && 2 * T::NSH <= 32;
+  }
   __host__ __device__ static bool supported(int C) {
     // DOUT <= 48: two channels of accumulators (or of the cotangent row) must fit the register file without spilling
     // (wider signatures are cut into path groups by the code generator); slices of a row must start 16-byte aligned
-    return (r_floats(C) % 4 == 0) && (h_floats(C) % 4 == 0) && (C % 2 == 0) && C <= 1984 && 2 * T::NSH <= 32 && T::DOUT <= 48 &&
-           (T::NGROUPS == 1 || C % 4 == 0);
+    return rows_ok(C) && T::DOUT <= 48 && (T::NGROUPS == 1 || C % 4 == 0);
   }
   __host__ __device__ static int consumer_threads(int C) { return ((C / 2 + 31) / 32) * 32; }
 };
@@ -616,6 +621,256 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
 }
 #undef PML_PIPE_PROLOGUE
 
+// =====================================================================================================================
+// Intra-CTA path groups: ONE ring of full rows per CTA, consumed by TPGroups<ID>::N warp sets, each running the code of
+// one path group (TPGroup<ID, g>) on its own slice of the staged rows.  Compared with one launch per group the R row,
+// the gathered h row and Y are staged once per edge, and compared with a single group a thread holds only its group's
+// part of the accumulator / cotangent row: half (or a third of) the registers, twice (three times) the warps per edge.
+// =====================================================================================================================
+struct PipeCtx {
+  float* stages;
+  uint64_t *full, *empty;
+  const int* rowptr;
+  TileSched ts;
+  int nstage, sfl, rfl, hfl, C, N, mm, tpg, lane, q_lo, q_hi;
+  bool is_producer;
+};
+
+template <int ID, class TG, class PROD>
+__device__ __forceinline__ void fwd_group_body(const PipeCtx& c, PROD& prod, int grp, float* __restrict__ out) {
+  using TF = TPCode<ID>;
+  using L = PipeLayout<TF>;
+  const int C = c.C, lane = c.lane;
+  const int u = 2 * ((int)threadIdx.x - grp * c.tpg);
+  const bool active = u < C;
+  const int uc = active ? u : C - 2;
+  int stage = 0, consumed = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < c.ts.ntiles; tile += c.ts.G) {
+    const int n0 = c.ts.first_node(tile), n1 = min(c.N, n0 + c.ts.TN);
+    int q = __ldg(c.rowptr + n0);
+    int end = __ldg(c.rowptr + n0 + 1);
+    for (int n = n0; n < n1; ++n) {
+      const int end_next = (n + 2 <= c.N) ? __ldg(c.rowptr + n + 2) : end;
+      float2 acc[TG::DOUT];
+#pragma unroll
+      for (int k = 0; k < TG::DOUT; ++k) acc[k] = make_float2(0.f, 0.f);
+      for (; q < end; ++q) {
+        const float* st = c.stages + (size_t)stage * c.sfl;
+        if (c.is_producer && prod.issued == consumed) prod.issue(1, consumed, 1, true, lane);
+        mbar_wait(smem_u32(c.full + stage), phase);
+        float2 Rv[TG::NP], Yv[TG::NSH], hv[TG::DIN];
+#pragma unroll
+        for (int p = 0; p < TG::NP; ++p) Rv[p] = *reinterpret_cast<const float2*>(st + (TG::P0 + p) * C + uc);
+        TG::load_h2_smem(st + c.rfl + TG::H_OFF * C, C, uc, hv);
+        load_y2_smem<TG::NSH, L::YPAD>(st + c.rfl + c.hfl, Yv);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(c.empty + stage));
+        if (++stage == c.nstage) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        ++consumed;
+        if (c.is_producer) prod.issue(2, consumed, c.nstage, false, lane);
+        TG::fwd2(hv, Yv, Rv, acc);
+      }
+      if (active) {
+        if (c.mm) TG::template store_out2<true>(out + (size_t)n * TG::DOUT_FULL * C, C, u, acc);
+        else TG::template store_out2<false>(out + (size_t)n * TG::DOUT_FULL * C, C, u, acc);
+      }
+      end = end_next;
+    }
+  }
+}
+
+template <int ID, int G, class PROD>
+__device__ __forceinline__ void fwd_group_dispatch(const PipeCtx& c, PROD& prod, int grp, float* __restrict__ out) {
+  if constexpr (G < TPGroups<ID>::N) {
+    if (grp == G) fwd_group_body<ID, TPGroup<ID, G>>(c, prod, grp, out);
+    else fwd_group_dispatch<ID, G + 1>(c, prod, grp, out);
+  }
+}
+
+template <int ID, bool DEDICATED>
+__global__ void tp_fwd_pipe_g_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
+                                     const int* __restrict__ gather, const int* __restrict__ rowptr,
+                                     const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage, int mm) {
+  using TF = TPCode<ID>;
+  using L = PipeLayout<TF>;
+  constexpr int NG = TPGroups<ID>::N;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + kPipeMaxStages;
+  PipeCtx c;
+  c.stages = reinterpret_cast<float*>(smem_raw + kPipeHeaderBytes);
+  c.full = full, c.empty = empty, c.rowptr = rowptr, c.nstage = nstage, c.C = C, c.N = N, c.mm = mm;
+  c.tpg = L::consumer_threads(C);
+  const int nthr_c = NG * c.tpg;
+  c.ts = tile_schedule(rowptr, N);
+  if ((int)blockIdx.x >= c.ts.G) return;
+  pipe_init(full, empty, nstage, nthr_c >> 5);
+  __syncthreads();
+  c.lane = threadIdx.x & 31;
+  c.rfl = L::r_floats(C), c.hfl = L::h_floats(C), c.sfl = L::stage_floats(C);
+  c.is_producer = !DEDICATED && threadIdx.x < 32;
+  PipeProducer<TF, true> prod;
+  prod.h = h, prod.Y = Y, prod.R = R, prod.gather = gather, prod.perm = perm, prod.rowptr = rowptr;
+  prod.stages = c.stages, prod.full = full, prod.empty = empty, prod.N = N, prod.C = C, prod.nstage = nstage, prod.ts = c.ts;
+  if (DEDICATED && (int)threadIdx.x >= nthr_c) {
+    prod.start(c.lane);
+    while (!prod.done()) prod.issue(1 << 30, 0, 1 << 30, true, c.lane);
+    return;
+  }
+  if (c.is_producer) {
+    prod.start(c.lane);
+    prod.issue(nstage, 0, nstage, true, c.lane);
+  }
+  fwd_group_dispatch<ID, 0>(c, prod, (int)threadIdx.x / c.tpg, out);
+}
+
+template <int ID, class TG, bool WANT_H, bool WANT_Y, bool WANT_R, class PROD>
+__device__ __forceinline__ void bwd_group_body(const PipeCtx& c, PROD& prod, int grp, const float* __restrict__ g,
+                                               float* __restrict__ dh, float* __restrict__ dY, float* __restrict__ dR) {
+  using TF = TPCode<ID>;
+  using L = PipeLayout<TF>;
+  constexpr int NV = next_pow2(TG::NSH);
+  constexpr int NG = TPGroups<ID>::N;
+  const int C = c.C, lane = c.lane, N = c.N;
+  const int u = 2 * ((int)threadIdx.x - grp * c.tpg);
+  const bool active = u < C;
+  const int uc = active ? u : C - 2;
+  const size_t rstride = (size_t)TG::NP_FULL * C, hstride = (size_t)TG::DIN_FULL * C;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  int stage = 0, consumed = 0;
+  uint32_t phase = 0;
+  int n;  // node holding edge q_lo
+  {
+    int lo = 0, hi = N;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(c.rowptr + mid) > c.q_lo) hi = mid; else lo = mid;
+    }
+    n = hi - 1;
+  }
+  int q = c.q_lo;
+  int end = min(__ldg(c.rowptr + n + 1), c.q_hi);
+  for (;; ++n) {
+    const int end_next = (n + 2 <= N) ? min(__ldg(c.rowptr + n + 2), c.q_hi) : c.q_hi;
+    float2 gv[TG::DOUT];
+    if (q < end) {
+      if (c.mm) TG::template load_out2<true>(g + (size_t)n * TG::DOUT_FULL * C, C, uc, gv);
+      else TG::template load_out2<false>(g + (size_t)n * TG::DOUT_FULL * C, C, uc, gv);
+      if (!active) {
+#pragma unroll
+        for (int k = 0; k < TG::DOUT; ++k) gv[k] = make_float2(0.f, 0.f);
+      }
+    }
+    for (; q < end; ++q) {
+      const float* st = c.stages + (size_t)stage * c.sfl;
+      if (c.is_producer && prod.issued == consumed) prod.issue(1, consumed, 1, true, lane);
+      mbar_wait(smem_u32(c.full + stage), phase);
+      const int2 es = reinterpret_cast<const int2*>(st + c.rfl + c.hfl + L::YPAD)[0];  // {edge id, gather id}
+      const int e = es.x;
+      float2 Rv[TG::NP], Yv[TG::NSH], hv[TG::DIN];
+#pragma unroll
+      for (int p = 0; p < TG::NP; ++p)
+        Rv[p] = (WANT_H || WANT_Y) ? *reinterpret_cast<const float2*>(st + (TG::P0 + p) * C + uc) : make_float2(0.f, 0.f);
+      TG::load_h2_smem(st + c.rfl + TG::H_OFF * C, C, uc, hv);
+      load_y2_smem<TG::NSH, L::YPAD>(st + c.rfl + c.hfl, Yv);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(c.empty + stage));
+      if (++stage == c.nstage) {
+        stage = 0;
+        phase ^= 1u;
+      }
+      ++consumed;
+      if (c.is_producer) prod.issue(2, consumed, c.nstage, false, lane);
+
+      float2 dhv[TG::DIN], dRv[TG::NP];
+      float dYv[NV];
+#pragma unroll
+      for (int i = 0; i < TG::DIN; ++i) dhv[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) dYv[j] = 0.f;
+      TG::template bwd2<WANT_H, WANT_Y, WANT_R, NV>(hv, Yv, Rv, gv, dhv, dYv, dRv);
+
+      if (WANT_R && active) {
+        float* drow = dR + (size_t)e * rstride + (size_t)TG::P0 * C + u;
+#pragma unroll
+        for (int p = 0; p < TG::NP; ++p) st_stream2_hint(drow + p * C, dRv[p], pol_stream);
+      }
+      if (WANT_H) {
+        if (active) TG::atomic_add_h2(dh + (size_t)es.y * hstride, C, u, dhv, pol_keep);
+      }
+      if (WANT_Y) {
+        warp_reduce_vec<NV>(dYv, lane);
+        constexpr int sh = 5 - Log2<NV>::value;
+        const int j = lane >> sh;
+        if ((lane & ((1 << sh) - 1)) == 0 && j < TG::NSH) {
+          if (NG == 1 && c.tpg == 32)
+            dY[(size_t)e * TG::NSH + j] = dYv[0];
+          else
+            atomicAdd(dY + (size_t)e * TG::NSH + j, dYv[0]);
+        }
+      }
+    }
+    if (q >= c.q_hi) break;
+    end = end_next;
+  }
+}
+
+template <int ID, int G, bool WANT_H, bool WANT_Y, bool WANT_R, class PROD>
+__device__ __forceinline__ void bwd_group_dispatch(const PipeCtx& c, PROD& prod, int grp, const float* __restrict__ g,
+                                                   float* __restrict__ dh, float* __restrict__ dY, float* __restrict__ dR) {
+  if constexpr (G < TPGroups<ID>::N) {
+    if (grp == G) bwd_group_body<ID, TPGroup<ID, G>, WANT_H, WANT_Y, WANT_R>(c, prod, grp, g, dh, dY, dR);
+    else bwd_group_dispatch<ID, G + 1, WANT_H, WANT_Y, WANT_R>(c, prod, grp, g, dh, dY, dR);
+  }
+}
+
+template <int ID, bool DEDICATED, bool WANT_H, bool WANT_Y, bool WANT_R>
+__global__ void tp_bwd_pipe_g_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
+                                     const float* __restrict__ g, const int* __restrict__ gather,
+                                     const int* __restrict__ rowptr, const int* __restrict__ perm, float* __restrict__ dh,
+                                     float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage, int mm) {
+  using TF = TPCode<ID>;
+  using L = PipeLayout<TF>;
+  constexpr int NG = TPGroups<ID>::N;
+  constexpr bool LOAD_R = WANT_H || WANT_Y;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + kPipeMaxStages;
+  PipeCtx c;
+  c.stages = reinterpret_cast<float*>(smem_raw + kPipeHeaderBytes);
+  c.full = full, c.empty = empty, c.rowptr = rowptr, c.nstage = nstage, c.C = C, c.N = N, c.mm = mm;
+  c.tpg = L::consumer_threads(C);
+  const int nthr_c = NG * c.tpg;
+  {  // even split of the edge list between the CTAs, walked from the end
+    const long long E_ = __ldg(rowptr + N), b_ = (long long)gridDim.x - 1 - blockIdx.x;
+    c.q_lo = (int)(E_ * b_ / gridDim.x), c.q_hi = (int)(E_ * (b_ + 1) / gridDim.x);
+    c.ts.TN = 1, c.ts.ntiles = 0, c.ts.G = (int)gridDim.x;
+    if (c.q_lo >= c.q_hi) return;
+  }
+  pipe_init(full, empty, nstage, nthr_c >> 5);
+  __syncthreads();
+  c.lane = threadIdx.x & 31;
+  c.rfl = L::r_floats(C), c.hfl = L::h_floats(C), c.sfl = L::stage_floats(C);
+  c.is_producer = !DEDICATED && threadIdx.x < 32;
+  PipeProducer<TF, LOAD_R> prod;
+  prod.h = h, prod.Y = Y, prod.R = R, prod.gather = gather, prod.perm = perm, prod.rowptr = rowptr;
+  prod.stages = c.stages, prod.full = full, prod.empty = empty, prod.N = N, prod.C = C, prod.nstage = nstage, prod.ts = c.ts;
+  if (DEDICATED && (int)threadIdx.x >= nthr_c) {
+    prod.start_range(c.lane, c.q_lo, c.q_hi);
+    while (!prod.done()) prod.issue(1 << 30, 0, 1 << 30, true, c.lane);
+    return;
+  }
+  if (c.is_producer) {
+    prod.start_range(c.lane, c.q_lo, c.q_hi);
+    prod.issue(nstage, 0, nstage, true, c.lane);
+  }
+  bwd_group_dispatch<ID, 0, WANT_H, WANT_Y, WANT_R>(c, prod, (int)threadIdx.x / c.tpg, g, dh, dY, dR);
+}
+
 struct PipeCfg {
   int nstage, smem, grid;
 };
@@ -702,6 +957,79 @@ static bool launch_fwd_pipe(const float* h, const float* Y, const float* R, cons
 }
 
 template <int ID, int G = 0>
+static int max_group_dout() {
+  if constexpr (G >= TPGroups<ID>::N) {
+    return 0;
+  } else {
+    const int rest = max_group_dout<ID, G + 1>();
+    return TPGroup<ID, G>::DOUT > rest ? TPGroup<ID, G>::DOUT : rest;
+  }
+}
+
+// all groups inside one CTA (one ring of full rows, TPGroups<ID>::N consumer warp sets)
+template <int ID>
+static bool intra_supported(int C) {
+  using L = PipeLayout<TPCode<ID>>;
+  return TPGroups<ID>::N > 1 && L::rows_ok(C) && max_group_dout<ID>() <= 48 &&
+         TPGroups<ID>::N * L::consumer_threads(C) + 32 <= 1024;
+}
+
+template <int ID>
+static bool launch_fwd_intra(const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
+                             const int* perm, float* out, int N, int C, int mm, cudaStream_t stream) {
+  if constexpr (TPGroups<ID>::N > 1) {
+    using L = PipeLayout<TPCode<ID>>;
+    PipeCfg cfg;
+    const int threads = TPGroups<ID>::N * L::consumer_threads(C) + 32;
+    const int sbytes = L::stage_floats(C) * 4;
+    if (!pipe_config<tp_fwd_pipe_g_kernel<ID, true>>(threads, sbytes, C, N < kSmallGraphNodes, &cfg)) return false;
+    if (N < kSmallGraphNodes) cfg.grid = N < 4 * cfg.grid ? N : 4 * cfg.grid;
+    tp_fwd_pipe_g_kernel<ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
+    return true;
+  } else {
+    return false;
+  }
+}
+
+template <int ID, bool H_, bool Y_, bool R_>
+static bool launch_bwd_intra_one(const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                                 const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, int mm,
+                                 cudaStream_t stream) {
+  if constexpr (TPGroups<ID>::N > 1) {
+    using L = PipeLayout<TPCode<ID>>;
+    PipeCfg cfg;
+    const int threads = TPGroups<ID>::N * L::consumer_threads(C);
+    const int sbytes = L::stage_floats(C) * 4;
+    if (!pipe_config<tp_bwd_pipe_g_kernel<ID, false, H_, Y_, R_>>(threads, sbytes, C, N < kSmallGraphNodes, &cfg)) return false;
+    tp_bwd_pipe_g_kernel<ID, false, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, g, gather, rowptr, perm, dh, dY,
+                                                                                         dR, N, C, cfg.nstage, mm);
+    return true;
+  } else {
+    return false;
+  }
+}
+
+template <int ID>
+static bool launch_bwd_intra(int mask, const float* h, const float* Y, const float* R, const float* g, const int* gather,
+                             const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, int mm,
+                             cudaStream_t stream) {
+#define PML_TP_BWD_INTRA(M, H_, Y_, R_) \
+  case M:                               \
+    return launch_bwd_intra_one<ID, H_, Y_, R_>(h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream);
+  switch (mask) {
+    PML_TP_BWD_INTRA(1, true, false, false)
+    PML_TP_BWD_INTRA(2, false, true, false)
+    PML_TP_BWD_INTRA(3, true, true, false)
+    PML_TP_BWD_INTRA(4, false, false, true)
+    PML_TP_BWD_INTRA(5, true, false, true)
+    PML_TP_BWD_INTRA(6, false, true, true)
+    PML_TP_BWD_INTRA(7, true, true, true)
+  }
+#undef PML_TP_BWD_INTRA
+  return false;
+}
+
+template <int ID, int G = 0>
 static bool fwd_pipe_groups(bool dedicated, const float* h, const float* Y, const float* R, const int* gather,
                             const int* rowptr, const int* perm, float* out, int N, int C, int mm, cudaStream_t stream) {
   if constexpr (G >= TPGroups<ID>::N) {
@@ -779,7 +1107,16 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
                                                        const int* rowptr, const int* perm, float* out, int N, int C,
                                                        int mm, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
-  const int mode = pml_tp_force_simple();  // bit0: streaming kernels; bit1 / bit2: flip the fwd / bwd producer placement
+  // mode bit0: streaming kernels; bit1 / bit2: flip the fwd / bwd producer placement; bit3: one launch per path group
+  // instead of all groups inside one CTA
+  const int mode = pml_tp_force_simple();
+  if (!(mode & (1 | 8)) && pml::intra_supported<PML_TP_ID>(C) && pml::aligned16(h) && pml::aligned16(R)) {
+    if (pml::launch_fwd_intra<PML_TP_ID>(h, Y, R, gather, rowptr, perm, out, N, C, mm, stream)) {
+      PML_CHECK_LAUNCH();
+      return PML_OK;
+    }
+    cudaGetLastError();
+  }
   if (pml::groups_supported<PML_TP_ID>(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
     if (pml::fwd_pipe_groups<PML_TP_ID>(!(mode & 2), h, Y, R, gather, rowptr, perm, out, N, C, mm, stream)) {
       PML_CHECK_LAUNCH();
@@ -803,6 +1140,13 @@ extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const floa
   if (N <= 0) return PML_OK;
   const int mask = (dh ? 1 : 0) | (dY ? 2 : 0) | (dR ? 4 : 0);
   const int mode = pml_tp_force_simple();
+  if (mask != 0 && !(mode & (1 | 8)) && pml::intra_supported<PML_TP_ID>(C) && pml::aligned16(h) && pml::aligned16(R)) {
+    if (pml::launch_bwd_intra<PML_TP_ID>(mask, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream)) {
+      PML_CHECK_LAUNCH();
+      return PML_OK;
+    }
+    cudaGetLastError();
+  }
   if (mask != 0 && pml::groups_supported<PML_TP_ID>(C) && pml::aligned16(h) && pml::aligned16(R) && !(mode & 1)) {
     if (pml::bwd_pipe_groups<PML_TP_ID>((mode & 4) != 0, mask, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N, C, mm, stream)) {
       PML_CHECK_LAUNCH();

@@ -34,20 +34,39 @@ def _load(static: dict, new: dict) -> None:
             static[k].copy_(v, non_blocking=True)
 
 
+def _device_of(d: dict):
+    for v in d.values():
+        if torch.is_tensor(v) and v.is_cuda:
+            return v.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 class _Captured:
+    def _run(self, captured: bool = False):
+        """the body inside the zero-arena scope: the ~110 zero-initialised outputs of a step come out of one buffer that
+        is cleared by one memset (ops.ZeroArena); only the declared outputs outlive a replay"""
+        from . import ops
+
+        with ops.zero_arena(self._arena, self._device):
+            return self._body(captured=captured)
+
     def _capture(self, warmup: int, pre_capture: Optional[Callable] = None) -> None:
+        from . import ops
+
+        self._arena = ops.ZeroArena()
+        self._device = _device_of(self.data)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._body()
+            for _ in range(max(warmup, 1)):  # at least one eager pass: it sizes the zero arena
+                self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         if pre_capture is not None:
             pre_capture()
         with torch.cuda.graph(self.graph):
-            self.out = self._body(captured=True)
+            self.out = self._run(captured=True)
 
     def __call__(self):
         self.graph.replay()

@@ -54,6 +54,76 @@ def _empty_like(t: Tensor) -> Tensor:
     return torch.full_like(t, float("nan")) if POISON_OUTPUTS[0] else torch.empty_like(t)
 
 
+# ---- zero-initialised outputs from one arena ---------------------------------------------------------------------------
+# A training step zero-initialises ~110 small outputs (atomically accumulated cotangents, split-K results, weight
+# gradients): as separate memsets they are ~110 graph nodes of ~1.5 us + dependency latency each (0.15 ms of a 5.6 ms
+# config-2 step).  Inside a ``zero_arena`` scope they are carved out of ONE buffer cleared by ONE memset at scope entry.
+# Opt-in and scoped on purpose: a tensor handed out here is re-zeroed at the next entry, so the scope is used by the
+# CUDA-graph bodies (graphs.py), where nothing but the declared outputs outlives a replay.  Outside a scope (and on
+# overflow) plain ``torch.zeros`` is used.  Process-wide, not thread-local: cotangent formulas run on the autograd
+# engine's device thread.
+class ZeroArena:
+    ALIGN = 256
+
+    def __init__(self) -> None:
+        self.buf: Optional[Tensor] = None
+        self.off = 0
+        self.want = 0   # bytes requested during the current / last scope (sizes the buffer of the next one)
+        self.served = 0
+
+    def begin(self, device) -> None:
+        need = int(self.want * 1.25) + (1 << 20)
+        if (self.buf is None or self.buf.numel() < need or self.buf.device != device) and not torch.cuda.is_current_stream_capturing():
+            self.buf = torch.empty(need, dtype=torch.uint8, device=device)
+        self.off, self.want = 0, 0
+        if self.buf is not None:
+            self.buf.zero_()
+
+    def take(self, ref: Tensor, shape, dtype) -> Optional[Tensor]:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        padded = (nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.want += padded
+        if self.buf is None or ref.device != self.buf.device or self.off + padded > self.buf.numel():
+            return None
+        t = self.buf[self.off : self.off + nbytes].view(dtype).view(tuple(int(d) for d in shape))
+        self.off += padded
+        self.served += 1
+        return t
+
+
+_ARENA: list = [None]
+
+
+@contextlib.contextmanager
+def zero_arena(arena: ZeroArena, device):
+    prev = _ARENA[0]
+    arena.begin(device)
+    _ARENA[0] = arena
+    try:
+        yield arena
+    finally:
+        _ARENA[0] = prev
+
+
+def _zeros(ref: Tensor, *shape, dtype=None) -> Tensor:
+    if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+        shape = tuple(shape[0])
+    dtype = dtype or ref.dtype
+    a = _ARENA[0]
+    if a is not None:
+        t = a.take(ref, shape, dtype)
+        if t is not None:
+            return t
+    return torch.zeros(shape, dtype=dtype, device=ref.device)
+
+
+def _zeros_like(t: Tensor) -> Tensor:
+    return _zeros(t, tuple(t.shape))
+
+
 # optional per-kernel device timing (bench.py): name -> list of (tag, start_event, end_event)
 KERNEL_TIMING: dict = {}
 
@@ -110,7 +180,7 @@ def edge_featurise_bwd(pos: Tensor, snd: Tensor, rcv: Tensor, shift: Optional[Te
                        bessel_w: Tensor, r_max: float, prefactor: float, w_scale: float, p: int, lmax: int,
                        gY: Optional[Tensor], gB: Optional[Tensor]) -> Tensor:
     pos = _f32c(pos)
-    gpos = torch.zeros_like(pos)
+    gpos = _zeros_like(pos)
     gY = None if gY is None else _f32c(gY)
     gB = None if gB is None else _f32c(gB)
     _call("pml_edge_featurise_bwd", *_feat_args(pos, snd, rcv, shift, cell, bessel_w, r_max, prefactor, w_scale, p, lmax),
@@ -150,7 +220,7 @@ def bessel_weight_grad(pos: Tensor, snd: Tensor, rcv: Tensor, shift: Optional[Te
     <gB, dB/dd * u.(t[r]-t[s])> (the force pass / its tangent map); see pml_bessel_weight_grad"""
     pos, gB = _f32c(pos), _f32c(gB)
     t = None if t is None else _f32c(t)
-    gw = torch.zeros_like(bessel_w, dtype=torch.float32)
+    gw = _zeros(bessel_w, tuple(bessel_w.shape), dtype=torch.float32)
     _call("pml_bessel_weight_grad", _p(pos), _p(snd), _p(rcv), _p(shift), _p(cell), _p(bessel_w), float(r_max),
           float(prefactor), float(w_scale), int(p), int(bessel_w.numel()), _p(gB), _p(t), _p(gw), snd.numel(), _stream())
     return gw
@@ -256,8 +326,8 @@ def tp_scatter_bwd(h: Tensor, Y: Tensor, R: Tensor, g: Tensor, gather: Tensor, r
     pl = plans.get(plan)
     h, Y, R, g = _f32c(h), _f32c(Y), _f32c(R), _f32c(g)
     N = rowptr.numel() - 1
-    dh = torch.zeros_like(h) if need_h else _new_empty(h, 0)
-    dY = (torch.zeros_like(Y) if (pl.C > 32 or pl.n_groups > 1) else _empty_like(Y)) if need_y else _new_empty(Y, 0)
+    dh = _zeros_like(h) if need_h else _new_empty(h, 0)
+    dY = (_zeros_like(Y) if (pl.C > 32 or pl.n_groups > 1) else _empty_like(Y)) if need_y else _new_empty(Y, 0)
     dR = _empty_like(R) if need_r else _new_empty(R, 0)
     if need_h or need_y or need_r:
         _call("pml_tp_bwd_ex", pl.spec_id, _p(h), _p(Y), _p(R), _p(g), _p(gather), _p(rowptr), _p(perm),
@@ -455,7 +525,7 @@ def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
         image = _wide_image(w, k, nn, nn, 1)
         _call("pml_wide_fwd", _p(x), k, k, _p(image), _p(out), nn, n, nn, alpha, _stream())
         return out
-    out = x.new_zeros(shape) if pl.has_unfed_output else _new_empty(x, shape)
+    out = _zeros(x, shape) if pl.has_unfed_output else _new_empty(x, shape)
     fwd, _, _ = pl.tables(x.device)
     if fwd is not None and n > 0:
         nprob = len(pl._fwd)
@@ -494,7 +564,7 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
         bn = 32 if pl.max_mul_in <= 32 else 64
         tiles = ((n + 127) // 128) * ((pl.max_mul_in + bn - 1) // bn) * len(pl._bwd_x) * pl.max_d
         sk = _splitk_rows(tiles, pl.max_k_bwd_x, _tc_slots(bn, True))
-    dx = g.new_zeros(n, pl.d_in) if (pl.has_unfed_input or sk > 1) else _new_empty(g, n, pl.d_in)
+    dx = _zeros(g, n, pl.d_in) if (pl.has_unfed_input or sk > 1) else _new_empty(g, n, pl.d_in)
     _, bx, _ = pl.tables(g.device)
     if bx is not None and n > 0:
         _gemm(name, _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, sk,
@@ -512,7 +582,7 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
     pl = plans.get(plan)
     x, g = _f32c(x), _f32c(g)
     n = x.shape[0]
-    dw = x.new_zeros(pl.weight_numel)
+    dw = _zeros(x, pl.weight_numel)
     _, _, bw = pl.tables(x.device)
     if bw is not None and n > 0:
         name = _gemm_name(n)
@@ -636,7 +706,7 @@ def element_linear(x: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tensor:
     if pl.out_layout == "channel":
         S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
         shape = (n, pl.d_out // S, S)
-    out = x.new_zeros(shape) if pl.has_unfed_output else _new_empty(x, shape)
+    out = _zeros(x, shape) if pl.has_unfed_output else _new_empty(x, shape)
     _call("pml_element_linear_fwd", _p(x), _p(attrs), _p(w), C.byref(pl.c_plan), _p(out), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return out
 
@@ -655,7 +725,7 @@ def element_linear_bwd_x(g: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tens
     pl = plans.get(plan)
     g, attrs, w = _f32c(g), _f32c(attrs), _f32c(w)
     n = g.shape[0]
-    dx = g.new_zeros(n, pl.d_in)  # accumulated atomically per (element, node chunk)
+    dx = _zeros(g, n, pl.d_in)  # accumulated atomically per (element, node chunk)
     _call("pml_element_linear_bwd_x", _p(g), _p(attrs), _p(w), C.byref(pl.c_plan), _p(dx), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return dx
 
@@ -669,7 +739,7 @@ def _(g, attrs, w, plan):
 def element_linear_bwd_w(x: Tensor, g: Tensor, attrs: Tensor, plan: int) -> Tensor:
     pl = plans.get(plan)
     x, g, attrs = _f32c(x), _f32c(g), _f32c(attrs)
-    dw = x.new_zeros(pl.weight_numel)
+    dw = _zeros(x, pl.weight_numel)
     _call("pml_element_linear_bwd_w", _p(x), _p(g), _p(attrs), C.byref(pl.c_plan), _p(dw), x.shape[0], pl.Z, 0, _stream(),
           launches=pl.n_launch)
     return dw
@@ -759,7 +829,7 @@ def sym_contract_bwd(x: Tensor, attrs: Tensor, weights: List[Tensor], g: Tensor,
     ws = [_f32c(w) for w in weights]
     n = x.shape[0]
     dx = _empty_like(x) if need_x else _new_empty(x, 0)
-    gws = [torch.zeros_like(w) for w in ws] if need_w else None
+    gws = [_zeros_like(w) for w in ws] if need_w else None
     st = pl.weight_struct(ws, gws)
     if need_x or need_w:
         _call("pml_sym_bwd", pl.spec_id, _p(x), _p(attrs), C.byref(st), _p(g), _p(dx) if need_x else None, n, pl.C, pl.Z,
@@ -784,7 +854,7 @@ def sym_contract_dbl(x: Tensor, v: Tensor, attrs: Tensor, weights: List[Tensor],
     n = x.shape[0]
     dg = _empty_like(g) if need_g else _new_empty(x, 0)
     ddx = _empty_like(x) if need_x else _new_empty(x, 0)
-    gws = [torch.zeros_like(w) for w in ws] if need_w else None
+    gws = [_zeros_like(w) for w in ws] if need_w else None
     st = pl.weight_struct(ws, gws)
     if need_g or need_x or need_w:
         _call("pml_sym_dbl", pl.spec_id, _p(x), _p(v), _p(attrs), C.byref(st), _p(g), _p(dg) if need_g else None,
@@ -989,7 +1059,7 @@ gate_bwd.register_autograd(_gate_bwd_bwd, setup_context=_gate_bwd_setup)
 @torch.library.custom_op(f"{NS}::pool_sum", mutates_args=(), device_types="cuda")
 def pool_sum(x: Tensor, batch: Tensor, num_graphs: int) -> Tensor:
     x = _f32c(x)
-    out = x.new_zeros(num_graphs, x.shape[1])
+    out = _zeros(x, num_graphs, x.shape[1])
     _call("pml_pool_sum", _p(x), _p(batch), _p(out), x.shape[0], x.shape[1], _stream())
     return out
 

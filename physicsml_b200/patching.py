@@ -148,6 +148,77 @@ def _find_backbone(module: torch.nn.Module):
     raise TypeError("patch() expects a physicsml MACE / NequIP module (or a Pooled*/…Module wrapping one under .mace / .nequip)")
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# block-level patching (the operator-level seam of SURVEY §8b): for backbones that are NOT the plain MACE class but are
+# assembled from the same blocks — the reference's ssf / adapter variants (models/mace/ssf/ssf_mace_utils.py:165-209,
+# models/mace/adapter/adapter_mace_utils.py) insert their own modules between the blocks, so their forward stays theirs
+# and only InteractionBlock / MessageBlock / NodeUpdateBlock run on the kernels.
+# ---------------------------------------------------------------------------------------------------------------------
+def _is_interaction_block(m) -> bool:
+    return all(hasattr(m, a) for a in ("linear_node_feats", "net_R_channels", "conv_tp", "linear", "avg_num_neighbours"))
+
+
+def _is_message_block(m) -> bool:
+    return hasattr(m, "symmetric_contractions") and hasattr(m.symmetric_contractions, "contractions")
+
+
+def _is_node_update_block(m) -> bool:
+    return hasattr(m, "linear") and hasattr(m, "residual_connection_layer") and not hasattr(m, "net_R_channels")
+
+
+def _mirror_block(block: torch.nn.Module):
+    from . import mace as M
+
+    if _is_interaction_block(block):
+        mix = getattr(block, "mix_layer", None)
+        attrs = _irreps_str(mix.irreps_in2) if mix is not None else "1x0e"
+        return M.InteractionBlock(
+            _irreps_str(block.linear_node_feats.irreps_in), attrs, _irreps_str(block.conv_tp.irreps_in2),
+            f"{_first_layer_in(block.net_R_channels)}x0e", _irreps_str(block.linear.irreps_out), float(block.avg_num_neighbours),
+            mix is not None)
+    if _is_message_block(block):
+        sc = block.symmetric_contractions
+        c0 = sc.contractions[0]
+        corr = getattr(c0, "correlation", None) or 1 + len(getattr(c0, "weights", []))
+        return M.MessageBlock(_irreps_str(sc.irreps_in), f"{int(c0.weights_max.shape[0])}x0e", _irreps_str(sc.irreps_out), int(corr))
+    if _is_node_update_block(block):
+        res = block.residual_connection_layer
+        hidden = _irreps_str(block.linear.irreps_out)
+        if res is None:
+            return M.NodeUpdateBlock("1x0e", hidden, hidden, False)
+        return M.NodeUpdateBlock(_irreps_str(res.irreps_in2), _irreps_str(res.irreps_in1), hidden, True)
+    return None
+
+
+def patch_blocks(module: torch.nn.Module) -> int:
+    """swap the forward of every reference InteractionBlock / MessageBlock / NodeUpdateBlock found under `module` (same
+    signatures: blocks.py:195-237, 117-121, 82-96) for a B200 mirror with tied parameters; returns how many were swapped"""
+    n = 0
+    for block in list(module.modules()):
+        if getattr(block, "_b200_mirror", None) is not None:
+            continue
+        mirror = _mirror_block(block)
+        if mirror is None:
+            continue
+        dev = next((p.device for p in block.parameters()), torch.device("cpu"))
+        mirror.to(dev)
+        tie_parameters(mirror, block)
+        object.__setattr__(block, "_b200_mirror", mirror)
+
+        def forward(self, *args, **kwargs):
+            return self._b200_mirror(*args, **kwargs)
+
+        block.forward = types.MethodType(forward, block)
+        n += 1
+    return n
+
+
+def _is_plain_backbone(backbone: torch.nn.Module, kind: str) -> bool:
+    known = {"mace": {"spherical_harmonics", "node_embedding", "radial_embedding", "interactions", "messages", "node_updates"},
+             "nequip": {"spherical_harmonics", "node_embedding", "radial_embedding", "conv_layers"}}[kind]
+    return {name for name, _ in backbone.named_children()} <= known
+
+
 def patch(module: torch.nn.Module, patch_forces: bool = True) -> torch.nn.Module:
     """Swap the backbone forward of a reference MACE / NequIP module for the B200 kernels (in place; returns `module`).
 
@@ -156,7 +227,18 @@ def patch(module: torch.nn.Module, patch_forces: bool = True) -> torch.nn.Module
     * ``patch_forces``: if the module has the reference's ``compute_forces_by_gradient`` method
       (``lightning/module.py:28-48``) it is replaced by the B200 one, which computes input gradients only in the force pass;
     * there is no CPU fallback: a patched module raises on CPU tensors; :func:`unpatch` restores the original."""
-    backbone, kind = _find_backbone(module)
+    try:
+        backbone, kind = _find_backbone(module)
+    except TypeError:
+        backbone, kind = None, None
+    if backbone is None or not _is_plain_backbone(backbone, kind):
+        # a variant backbone (ssf / adapter: extra modules between the blocks) or a bare block container: its forward
+        # stays, the blocks it calls are swapped one by one
+        if patch_blocks(module) == 0:
+            raise TypeError("patch() found neither a physicsml MACE / NequIP backbone nor any of its blocks under this module")
+        if patch_forces and hasattr(module, "compute_forces_by_gradient") and "compute_forces_by_gradient" not in module.__dict__:
+            _patch_forces(module)
+        return module
     if getattr(backbone, "_b200_mirror", None) is not None:
         return module
     if kind == "mace":
@@ -186,20 +268,34 @@ def patch(module: torch.nn.Module, patch_forces: bool = True) -> torch.nn.Module
     object.__setattr__(backbone, "_b200_tied", tied)
     backbone.forward = types.MethodType(forward, backbone)
     if patch_forces and hasattr(module, "compute_forces_by_gradient"):
-        from .mace import compute_forces_by_gradient as cfg
-
-        object.__setattr__(module, "_b200_original_forces", module.compute_forces_by_gradient)
-
-        def forces(self, energy: torch.Tensor, coordinates: torch.Tensor) -> torch.Tensor:
-            return cfg(energy, coordinates, self)
-
-        module.compute_forces_by_gradient = types.MethodType(forces, module)
+        _patch_forces(module)
     return module
 
 
+def _patch_forces(module: torch.nn.Module) -> None:
+    from .mace import compute_forces_by_gradient as cfg
+
+    object.__setattr__(module, "_b200_original_forces", module.compute_forces_by_gradient)
+
+    def forces(self, energy: torch.Tensor, coordinates: torch.Tensor) -> torch.Tensor:
+        return cfg(energy, coordinates, self)
+
+    module.compute_forces_by_gradient = types.MethodType(forces, module)
+
+
 def unpatch(module: torch.nn.Module) -> torch.nn.Module:
-    backbone, _ = _find_backbone(module)
-    if getattr(backbone, "_b200_mirror", None) is None:
+    for block in module.modules():  # block-level swaps
+        if getattr(block, "_b200_mirror", None) is not None and _mirror_block(block) is not None:
+            block.__dict__.pop("forward", None)
+            object.__delattr__(block, "_b200_mirror")
+    try:
+        backbone, _ = _find_backbone(module)
+    except TypeError:
+        backbone = None
+    if backbone is None or getattr(backbone, "_b200_mirror", None) is None:
+        if getattr(module, "_b200_original_forces", None) is not None:
+            module.__dict__.pop("compute_forces_by_gradient", None)
+            object.__delattr__(module, "_b200_original_forces")
         return module
     backbone.__dict__.pop("forward", None)  # the class's own forward shows through again
     for a in ("_b200_mirror", "_b200_original_forward", "_b200_kwargs", "_b200_tied"):
@@ -211,8 +307,4 @@ def unpatch(module: torch.nn.Module) -> torch.nn.Module:
 
 
 def is_patched(module: Any) -> bool:
-    try:
-        backbone, _ = _find_backbone(module)
-    except TypeError:
-        return False
-    return getattr(backbone, "_b200_mirror", None) is not None
+    return any(getattr(m, "_b200_mirror", None) is not None for m in module.modules())

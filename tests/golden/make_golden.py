@@ -9,6 +9,7 @@ Only runs in the build container (needs /root/reference).  Outputs (all small, f
   nequip_*.pt        the same for the reference NequIP (models/nequip/modules/nequip.py) + PooledReadoutHead
   nl_*.pt            inputs and sorted edge sets of the reference construct_edge_indices_and_attrs
                      (lightning/graph_datasets/neighbourhood_list_torch.py:53)
+  nl_bond_merge.pt   inputs and outputs of the same function's bond-feature merge branch (:98-156), open and periodic
   gdb9_edges.pt      first six molecules of the reference's tests/data/gdb9.sdf with the edge counts its tests assert
                      (tests/rdkit/core/data/test_graph_dataset.py:42,50; test_datamodule.py:28-35)
 
@@ -180,6 +181,23 @@ def main():
     assert counts[:2] == [20, 12] and sum(counts[:4]) == 50, counts
     torch.save({"positions": mols, "edge_counts": counts}, os.path.join(HERE, "gdb9_edges.pt"))
     print("gdb9 edge counts", counts)
+    bond_merge()
+
+
+def bond_merge():
+    """---- 5. the bond-feature merge branch of construct_edge_indices_and_attrs (neighbourhood_list_torch.py:98-156):
+    supplied edges + attributes merged into the radius graph, open and periodic"""
+    pos, _, _ = helpers.random_molecules(1, 9, 9, 3, seed=5)
+    bonds = torch.tensor([[0, 1], [1, 2], [2, 3], [3, 4], [0, 5]])
+    attrs = torch.tensor([[1.0, 0.0], [0.0, 1.0], [1.0, 0.0], [0.5, 0.5], [0.0, 2.0]])
+    out = {"pos": pos, "bonds": bonds, "attrs": attrs, "cutoff": 5.0}
+    ei, ea, sh = nl_mod.construct_edge_indices_and_attrs(pos, 5.0, bonds, attrs, None, None, False)
+    out["open"] = {"edge_index": ei, "edge_attrs": ea, "shift": sh}
+    cell = torch.eye(3) * 14.0
+    ei, ea, sh = nl_mod.construct_edge_indices_and_attrs(pos + 6.0, 5.0, bonds, attrs, (True, True, True), cell, False)
+    out["pbc"] = {"cell": cell, "offset": 6.0, "edge_index": ei, "edge_attrs": ea, "shift": sh}
+    torch.save(out, os.path.join(HERE, "nl_bond_merge.pt"))
+    print("nl_bond_merge: E", ei.shape[1], "attr sum", ea.sum(0).tolist())
 
 
 if __name__ == "__main__":

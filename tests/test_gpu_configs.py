@@ -187,18 +187,24 @@ def test_water_box_medium_periodic_parity(cuda):
     mine = mine.to(cuda)
     d = helpers.to_device(data, cuda)
     d.update(edge_index=ei, cell_shift_vector=sh, _edge_plan=plan)
+    # per-atom energies (batch = arange(N): every atom is its own "graph" for the pooled readout; the forces are unchanged
+    # because they are the gradient of the SUM of the outputs).  The total energy of a random-weight model on 375 atoms is
+    # a near-complete cancellation of per-atom terms (|E| ~ 0.02 with |e_i| ~ 0.05), so "1e-5 relative" is stated where it
+    # is well conditioned: per atom against max |e_i|, and for the total against sum |e_i|.
+    d.update(batch=torch.arange(N, device=cuda), num_graphs=torch.tensor(N))
     e, f = wl.energy_forces(mine, d)
-    cpu = dict(data, edge_index=ei.cpu(), cell_shift_vector=sh.cpu())
+    cpu = dict(data, edge_index=ei.cpu(), cell_shift_vector=sh.cpu(), batch=torch.arange(N), num_graphs=torch.tensor(N))
     e_ref, f_ref = energy_and_forces(ref, cpu)
     e64, f64 = energy_and_forces(ref.double(), helpers.to_device(cpu, "cpu", torch.float64))
-    scale = e64.abs().max().item()
-    de, df = (e.cpu().double() - e64).abs().max().item() / scale, (f.cpu().double() - f64).abs().max().item()
-    de_ref, df_ref = (e_ref.double() - e64).abs().max().item() / scale, (f_ref.double() - f64).abs().max().item()
-    print(f"water box: vs fp64 oracle: E rel err {de:.2e} (fp32 oracle itself {de_ref:.2e}), F abs err {df:.2e} (fp32 oracle "
-          f"{df_ref:.2e}), |F|max {f64.abs().max().item():.3f}, E {e64.item():.4f}")
-    # one total energy of 375 atoms whose per-atom terms cancel: the bar is 1e-5 relative, or the fp32 noise floor the
-    # reference's own fp32 evaluation shows on this input (x4) where that is larger
-    assert de <= max(1e-5, 4 * de_ref) and df <= 1e-4
+    e, f = e.cpu().double(), f.cpu().double()
+    top, tot = e64.abs().max().item(), e64.abs().sum().item()
+    de, de_ref = (e - e64).abs().max().item() / top, (e_ref.double() - e64).abs().max().item() / top
+    dt, dt_ref = abs((e - e64).sum().item()) / tot, abs((e_ref.double() - e64).sum().item()) / tot
+    df, df_ref = (f - f64).abs().max().item(), (f_ref.double() - f64).abs().max().item()
+    print(f"water box vs fp64 oracle: per-atom E rel err {de:.2e} (fp32 oracle itself {de_ref:.2e}); total E {e64.sum().item():.4f}, "
+          f"error / sum|e_i| {dt:.2e} (fp32 oracle {dt_ref:.2e}); F abs err {df:.2e} (fp32 oracle {df_ref:.2e}), |F|max {f64.abs().max().item():.3f}")
+    assert de <= 1e-5 and dt <= 1e-5 and df <= 1e-4
+    assert (e - e_ref.double()).abs().max().item() <= 1e-5 * top and (f - f_ref.double()).abs().max().item() <= 1e-4
 
 
 def test_small_qm9_full_batch_parity(cuda):

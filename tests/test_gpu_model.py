@@ -107,3 +107,37 @@ def test_training_step_gradients(cuda, prune):
         worst = max(worst, err)
         assert err < 2e-4, (k, err)
     print("worst relative parameter-gradient error", worst)
+
+
+def test_edge_attribute_inputs(cuda):
+    """num_edge_feats > 0 (reference mace.py:151-152): per-edge attributes (bond features merged into the
+    radius graph by construct_edge_indices_and_attrs) are concatenated to the Bessel features in front of the radial MLP"""
+    from oracle.ref_model import RefPooledMACE, energy_and_forces
+    from physicsml_b200.mace import PooledMACEModule, compute_forces_by_gradient
+    from physicsml_b200.neighbour_list import construct_edge_indices_and_attrs
+
+    kw = dict(CONFIGS["small"]["kw"], num_edge_feats=2)
+    torch.manual_seed(0)
+    ref = RefPooledMACE(mlp_irreps="16x0e", **kw)
+    mine = PooledMACEModule(mlp_irreps="16x0e", **kw)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine = mine.to(cuda)
+    pos, z, batch = helpers.random_molecules(1, 14, 14, 5, seed=77)
+    bonds = torch.tensor([[0, 1], [1, 2], [2, 3], [4, 5], [6, 7]])
+    d = (pos[bonds[:, 0]] - pos[bonds[:, 1]]).norm(dim=1)
+    bonds = bonds[d < 4.5]
+    attrs = torch.tensor([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0], [0.5, 0.0], [0.0, 2.0]])[d < 4.5]
+    ei, ea, sh = construct_edge_indices_and_attrs(pos.to(cuda), 5.0, bonds.to(cuda), attrs.to(cuda), None, None, False)
+    assert ea.shape == (ei.shape[1], 2) and float(ea.sum()) == 2 * float(attrs.sum())
+    data = {"coordinates": pos, "edge_index": ei.cpu(), "edge_attrs": ea.cpu(), "node_attrs": torch.nn.functional.one_hot(z, 5).float(),
+            "batch": batch, "num_graphs": torch.tensor(1)}
+    e_ref, f_ref = energy_and_forces(ref, data)
+    dd = helpers.to_device(data, cuda)
+    dd["coordinates"].requires_grad_(True)
+    e = mine(dd)["y_graph_scalars"]
+    f = compute_forces_by_gradient(e, dd["coordinates"])
+    assert (e.cpu() - e_ref).abs().max().item() <= 1e-5 * e_ref.abs().max().item()
+    assert (f.cpu() - f_ref).abs().max().item() <= 1e-4
+    # the attributes matter: zeroing them changes the energy
+    dd2 = dict(dd, edge_attrs=torch.zeros_like(dd["edge_attrs"]))
+    assert (mine(dd2)["y_graph_scalars"] - e).abs().max().item() > 1e-6

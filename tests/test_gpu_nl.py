@@ -133,3 +133,92 @@ def test_periodic_model_parity(cuda):
     d2["coordinates"].requires_grad_(True)
     e2 = mine(d2)["y_graph_scalars"]
     assert (e2.cpu() - e_ref).abs().max() <= 1e-5 * e_ref.abs().max()
+
+
+def test_bond_feature_merge_matches_reference_golden(cuda):
+    """neighbourhood_list_torch.py:98-156 (SURVEY §8f N4): supplied bond edges + attributes merged into the radius graph;
+    golden produced by the reference's own construct_edge_indices_and_attrs (tests/golden/make_golden.py §5)"""
+    from physicsml_b200.neighbour_list import construct_edge_indices_and_attrs
+
+    g = torch.load(os.path.join(GOLD, "nl_bond_merge.pt"), weights_only=False)
+    ei, ea, sh = construct_edge_indices_and_attrs(g["pos"].to(cuda), g["cutoff"], g["bonds"].to(cuda), g["attrs"].to(cuda), None, None, False)
+    assert torch.equal(ei.cpu(), g["open"]["edge_index"]) and torch.equal(ea.cpu(), g["open"]["edge_attrs"])
+    assert torch.equal(sh.cpu(), g["open"]["shift"])
+    p = g["pbc"]
+    ei, ea, sh = construct_edge_indices_and_attrs((g["pos"] + p["offset"]).to(cuda), g["cutoff"], g["bonds"].to(cuda), g["attrs"].to(cuda),
+                                                  (True, True, True), p["cell"].to(cuda), False)
+    assert torch.equal(ei.cpu(), p["edge_index"]) and torch.equal(ea.cpu(), p["edge_attrs"]) and torch.equal(sh.cpu(), p["shift"])
+    with pytest.raises(ValueError):  # a bond longer than the cut-off is not a subset of the radius graph
+        construct_edge_indices_and_attrs(g["pos"].to(cuda), 1.0, g["bonds"].to(cuda), g["attrs"].to(cuda), None, None, False)
+
+
+def test_batched_periodic_neighbour_list(cuda):
+    """a collated batch of periodic structures in ONE call == one call per structure, for a shared cell
+    (the reference's batch contract) and for one (triclinic) cell per structure with cartesian shifts"""
+    from oracle.ref_nl import ref_radius_graph, sorted_edge_set
+    from physicsml_b200.neighbour_list import collate, radius_graph
+
+    gen = torch.Generator().manual_seed(12)
+    rc = 4.0
+    cells = [torch.eye(3) * 9.0, torch.tensor([[8.0, 0, 0], [2.0, 7.5, 0], [-1.0, 1.0, 10.0]]), torch.eye(3) * 5.5]
+    ns = [30, 41, 12]
+    structs = []
+    for c, n in zip(cells, ns):
+        frac = torch.rand(n, 3, generator=gen) * 1.4 - 0.2  # some atoms outside the cell: exercises the wrap + shift fix-up
+        structs.append({"coordinates": frac @ c, "species": torch.randint(0, 3, (n,), generator=gen), "cell": c})
+    # (a) per-structure cells
+    data = collate(structs, rc, cuda, num_species=3)
+    off = 0
+    for s in structs:
+        n = s["coordinates"].shape[0]
+        ei_ref, sh_ref = ref_radius_graph(s["coordinates"], rc, (True, True, True), s["cell"])
+        m = (data["edge_index"][0] >= off) & (data["edge_index"][0] < off + n)
+        ei = (data["edge_index"][:, m] - off).cpu()
+        assert bool(((ei >= 0) & (ei < n)).all())  # no edge leaves its structure
+        cart_ref = sh_ref @ s["cell"]
+        a = sorted_edge_set(ei_ref, sh_ref)[0]
+        # same edges in the same (sender, receiver, shift) order; shifts compared in length units
+        assert ei.shape == ei_ref.shape
+        key = lambda e, c: sorted(zip(e[0].tolist(), e[1].tolist(), [tuple(round(x, 3) for x in r) for r in c.tolist()]))  # noqa: E731
+        assert key(ei, data["cell_shift_vector"][m].cpu()) == key(ei_ref, cart_ref)
+        off += n
+    assert torch.equal(data["cell"].cpu(), torch.eye(3))
+    # (b) one shared cell: integer shifts, identical to single-structure calls
+    shared = [dict(s, cell=cells[1]) for s in structs]
+    data = collate(shared, rc, cuda, num_species=3)
+    assert torch.equal(data["cell"].cpu(), cells[1])
+    off = 0
+    for s in shared:
+        n = s["coordinates"].shape[0]
+        ei1, sh1, _ = radius_graph(s["coordinates"].to(cuda), rc, pbc=(True, True, True), cell=cells[1].to(cuda))
+        m = (data["edge_index"][0] >= off) & (data["edge_index"][0] < off + n)
+        assert torch.equal(data["edge_index"][:, m] - off, ei1) and torch.equal(data["cell_shift_vector"][m], sh1)
+        off += n
+    _check_plan(data["edge_index"], data["_edge_plan"], off)
+
+
+def test_collated_batch_runs_the_model(cuda):
+    """collate() output is the reference's batch dict: the model consumes it directly (periodic, per-structure cells)"""
+    from oracle.ref_model import RefPooledMACE, energy_and_forces
+    from physicsml_b200 import workloads as wl
+    from physicsml_b200.mace import PooledMACEModule
+    from physicsml_b200.neighbour_list import collate
+
+    kw = dict(cut_off=4.0, num_bessel=8, num_polynomial_cutoff=5, max_ell=2, num_interactions=2, num_node_feats=3, num_edge_feats=0,
+              hidden_irreps="16x0e + 16x1o", avg_num_neighbours=20.0, correlation=3)
+    torch.manual_seed(0)
+    ref = RefPooledMACE(mlp_irreps="16x0e", **kw)
+    mine = PooledMACEModule(mlp_irreps="16x0e", **kw)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine = mine.to(cuda)
+    gen = torch.Generator().manual_seed(3)
+    structs = []
+    for a, n in ((7.0, 20), (8.5, 28)):
+        c = torch.eye(3) * a
+        structs.append({"coordinates": torch.rand(n, 3, generator=gen) * a, "species": torch.randint(0, 3, (n,), generator=gen), "cell": c})
+    data = collate(structs, 4.0, cuda, num_species=3)
+    e, f = wl.energy_forces(mine, data)
+    cpu = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in data.items() if k != "_edge_plan"}
+    e_ref, f_ref = energy_and_forces(ref, cpu)
+    scale = e_ref.abs().max().item()
+    assert (e.cpu() - e_ref).abs().max().item() <= 1e-5 * scale and (f.cpu() - f_ref).abs().max().item() <= 1e-4

@@ -126,3 +126,92 @@ def test_patched_reference_module_matches_its_original_forward(cuda, kind):
     assert set(g0) == set(g1)
     for k in g0:
         assert (g1[k] - g0[k]).abs().max().item() <= 2e-4 * max(g0[k].abs().max().item(), 1e-12) + 1e-7, k
+
+
+def _variant_module():
+    """a MACE variant in the manner of the reference's ssf / mean_var modules (models/mace/ssf/ssf_mace_utils.py:165-209,
+    models/mace/mean_var/mean_var_mace_module.py:96-122): the reference's own blocks with an extra per-layer module in
+    between, a second pooled head for the predicted std and a node-vector head — not the plain MACE class"""
+    from oracle import import_reference as ir
+    from oracle import reference_models as rm
+
+    if not rm.available():
+        pytest.skip("reference sources not staged")
+    mod = ir.load("physicsml.models.mace.modules.mace")
+    ir.install_shims()
+    from e3nn import o3
+
+    class Variant(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.variant_mace = mod.MACE(**MACE_KW)
+            C = 16
+            self.scale = torch.nn.ParameterList([torch.nn.Parameter(torch.ones(1) * 1.1) for _ in range(2)])  # "ssf"-like
+            self.graph_scalars_head = mod.PooledReadoutHead(self.variant_mace.out_irreps, o3.Irreps("16x0e"), o3.Irreps("1x0e"), 1.0, 0.0)
+            self.graph_scalars_head_std = mod.PooledReadoutHead(self.variant_mace.out_irreps, o3.Irreps("16x0e"), o3.Irreps("1x0e"), 1.0, 0)
+            del C
+
+        def forward(self, data):
+            m = self.variant_mace
+            from physicsml.models.utils import compute_lengths_and_vectors
+
+            lengths, vectors = compute_lengths_and_vectors(data["coordinates"], data["edge_index"], None, None)
+            h = m.node_embedding(data["node_attrs"])
+            Y, B = m.spherical_harmonics(vectors), m.radial_embedding(lengths)
+            for i, (inter, msg, upd) in enumerate(zip(m.interactions, m.messages, m.node_updates)):
+                a = inter(node_feats=h, node_attrs=data["node_attrs"], edge_attrs=Y, edge_feats=B, edge_index=data["edge_index"])
+                h = upd(m_i=msg(a_i=a, node_attrs=data["node_attrs"]), node_feats=h, node_attrs=data["node_attrs"])
+                h = h * self.scale[i]
+                data[f"node_feats_{i}"] = h
+            e = self.graph_scalars_head(data)
+            std = torch.abs(self.graph_scalars_head_std(data)) / (data["ptr"][1:] - data["ptr"][:-1]).unsqueeze(-1)
+            return {"y_graph_scalars": e, "y_graph_scalars::std": std}
+
+    torch.manual_seed(0)
+    return Variant()
+
+
+def test_block_level_patch_of_a_variant_backbone_cpu():
+    import physicsml_b200
+    from physicsml_b200 import patching as P
+
+    v = _variant_module()
+    keys = list(v.state_dict().keys())
+    physicsml_b200.patch(v)
+    swapped = [m for m in v.modules() if getattr(m, "_b200_mirror", None) is not None]
+    assert len(swapped) == 6  # 2 x (interaction, message, node update); the variant's own forward is untouched
+    assert "forward" not in v.__dict__ and list(v.state_dict().keys()) == keys
+    for m in swapped:
+        ref_params = dict(m.named_parameters())
+        for name, p in m._b200_mirror.named_parameters():
+            if p.numel():
+                assert p is ref_params[name]
+    P.unpatch(v)
+    assert not P.is_patched(v)
+
+
+@pytest.mark.gpu
+def test_block_level_patch_of_a_variant_backbone_matches(cuda):
+    import physicsml_b200
+
+    v = _variant_module()
+    pos, z, batch = helpers.random_molecules(4, 8, 14, 5, seed=21)
+    data = helpers.make_batch(pos, z, batch, 5, MACE_KW["cut_off"])
+    ptr = torch.zeros(5, dtype=torch.long)
+    ptr[1:] = torch.cumsum(torch.bincount(batch, minlength=4), 0)
+    data["ptr"] = ptr
+
+    def run(model, d):
+        d = dict(d)
+        d["coordinates"] = d["coordinates"].clone().requires_grad_(True)
+        out = model(d)
+        (g,) = torch.autograd.grad([out["y_graph_scalars"].sum() + out["y_graph_scalars::std"].sum()], [d["coordinates"]])
+        return out["y_graph_scalars"].detach().cpu(), out["y_graph_scalars::std"].detach().cpu(), g.cpu()
+
+    e0, s0, g0 = run(v, data)
+    v.to(cuda)
+    physicsml_b200.patch(v)
+    e1, s1, g1 = run(v, helpers.to_device(data, cuda))
+    assert (e1 - e0).abs().max().item() <= 1e-5 * e0.abs().max().item()
+    assert (s1 - s0).abs().max().item() <= 1e-5 * max(s0.abs().max().item(), 1e-6)
+    assert (g1 - g0).abs().max().item() <= 1e-4
