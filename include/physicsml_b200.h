@@ -255,6 +255,9 @@ int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int 
 int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse, pml_stream_t stream);
 
 int pml_scan_i32(const int* counts, int* out, int n, pml_stream_t stream);
+/* Verlet-skin test of a single-structure MD loop (plugins/openmm/openmm_graph.py:119-176 rebuilds the neighbour list on
+ * every step): *out = max_i |pos_i - ref_i|^2 over N atoms; out: device float, zero-initialised by the caller. */
+int pml_max_disp2(const float* pos, const float* ref, int N, float* out, pml_stream_t stream);
 
 /* ---- K1: radius-graph neighbour list ------------------------------------------------------------------------------
  * Replaces compute_neighborlist_n2_no_cell / construct_edge_indices_and_attrs (lightning/graph_datasets/

@@ -211,6 +211,31 @@ extern "C" int pml_pool_gather(const float* g, const long long* batch, float* ou
   return PML_OK;
 }
 
+// Verlet-skin test of the MD loop (md.py): *out = max_i |pos_i - ref_i|^2 (out zero-initialised by the caller; the
+// squared displacement is non-negative, so its IEEE bits order like an unsigned integer)
+namespace pml {
+__global__ void __launch_bounds__(256) max_disp2_kernel(const float* __restrict__ pos, const float* __restrict__ ref, int N,
+                                                        unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const float dx = pos[3 * i] - ref[3 * i], dy = pos[3 * i + 1] - ref[3 * i + 1], dz = pos[3 * i + 2] - ref[3 * i + 2];
+    m = fmaxf(m, dx * dx + dy * dy + dz * dz);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+}  // namespace pml
+
+extern "C" int pml_max_disp2(const float* pos, const float* ref, int N, float* out, cudaStream_t stream) {
+  if (N <= 0) return PML_OK;
+  int grid = pml::ceil_div(N, 256);
+  if (grid > 592) grid = 592;
+  pml::max_disp2_kernel<<<grid, 256, 0, stream>>>(pos, ref, N, reinterpret_cast<unsigned int*>(out));
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
 // perm[rowptr[n] + k] = id of the k-th edge (ascending id = stable order) whose index is n.  Step 1 fills every segment
 // in arrival order with an atomic cursor; step 2 sorts each segment by edge id in shared memory (one CTA per node), which
 // makes the grouping — and with it the summation order of the scatter kernels — deterministic.  Segments longer than

@@ -50,15 +50,34 @@ class _Captured:
         with ops.zero_arena(self._arena, self._device):
             return self._body(captured=captured)
 
-    def _capture(self, warmup: int, pre_capture: Optional[Callable] = None) -> None:
+    def release(self) -> None:
+        """drop the graph and the zero arena.  Gradients of a captured training step live in the arena: they are cleared"""
+        self.graph = None
+        self.out = None
+        model = getattr(self, "model", None)
+        if model is not None and getattr(self, "optimizer", None) is not None:
+            for p in model.parameters():
+                p.grad = None
+        arena = getattr(self, "_arena", None)
+        if arena is not None and getattr(self, "_owns_arena", True):
+            arena.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _capture(self, warmup: int, pre_capture: Optional[Callable] = None, arena=None) -> None:
         from . import ops
 
-        self._arena = ops.ZeroArena()
+        self._owns_arena = arena is None
+        self._arena = arena if arena is not None else ops.ZeroArena()
         self._device = _device_of(self.data)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):  # at least one eager pass: it sizes the zero arena
+            for _ in range(max(warmup, 2)):  # at least two eager passes: the first sizes the zero arena, the second uses it
                 self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -102,10 +121,11 @@ class GraphedStep(_Captured):
 class GraphedEval(_Captured):
     """one evaluation ``fn(model, data) -> tensor or tuple of tensors`` (e.g. energy + forces) on static buffers"""
 
-    def __init__(self, model: torch.nn.Module, data: dict, fn: Callable, warmup: int = 3) -> None:
+    def __init__(self, model: torch.nn.Module, data: dict, fn: Callable, warmup: int = 3, arena=None) -> None:
+        """arena: a caller-owned ops.ZeroArena shared by successive captures (the MD loop re-captures per neighbour list)"""
         self.model, self.fn = model, fn
         self.data = _static_copy(data)
-        self._capture(warmup)
+        self._capture(warmup, arena=arena)
 
     def _body(self, captured: bool = False):
         out = self.fn(self.model, self.data)

@@ -62,6 +62,12 @@ def _empty_like(t: Tensor) -> Tensor:
 # CUDA-graph bodies (graphs.py), where nothing but the declared outputs outlives a replay.  Outside a scope (and on
 # overflow) plain ``torch.zeros`` is used.  Process-wide, not thread-local: cotangent formulas run on the autograd
 # engine's device thread.
+# Every tensor gets its OWN (non-owning) storage object over its slice of the buffer: torch.library checks that a custom
+# op's outputs share no storage with its inputs or with each other, and slices of one tensor would all share one.  The
+# arena therefore keeps its buffers alive until ``release()``; owners (GraphedStep / GraphedEval) release it when they go.
+_FROM_PTR = getattr(torch._C, "_construct_storage_from_data_pointer", None)
+
+
 class ZeroArena:
     ALIGN = 256
 
@@ -70,14 +76,24 @@ class ZeroArena:
         self.off = 0
         self.want = 0   # bytes requested during the current / last scope (sizes the buffer of the next one)
         self.served = 0
+        self._retired: list = []
 
     def begin(self, device) -> None:
+        if _FROM_PTR is None:  # this torch cannot build aliasing-free views: the arena stays off (plain torch.zeros)
+            return
         need = int(self.want * 1.25) + (1 << 20)
         if (self.buf is None or self.buf.numel() < need or self.buf.device != device) and not torch.cuda.is_current_stream_capturing():
+            if self.buf is not None:
+                self._retired.append(self.buf)  # tensors handed out earlier may still point into it
             self.buf = torch.empty(need, dtype=torch.uint8, device=device)
         self.off, self.want = 0, 0
         if self.buf is not None:
             self.buf.zero_()
+
+    def release(self) -> None:
+        """drop the buffers; every tensor handed out must be dead by now"""
+        self.buf = None
+        self._retired.clear()
 
     def take(self, ref: Tensor, shape, dtype) -> Optional[Tensor]:
         n = 1
@@ -88,7 +104,8 @@ class ZeroArena:
         self.want += padded
         if self.buf is None or ref.device != self.buf.device or self.off + padded > self.buf.numel():
             return None
-        t = self.buf[self.off : self.off + nbytes].view(dtype).view(tuple(int(d) for d in shape))
+        storage = _FROM_PTR(self.buf.data_ptr() + self.off, self.buf.device, max(nbytes, 1))
+        t = torch.empty(0, dtype=dtype, device=self.buf.device).set_(storage, 0, tuple(int(d) for d in shape))
         self.off += padded
         self.served += 1
         return t

@@ -9,7 +9,7 @@ Only runs in the build container (needs /root/reference).  Outputs (all small, f
   nequip_*.pt        the same for the reference NequIP (models/nequip/modules/nequip.py) + PooledReadoutHead
   nl_*.pt            inputs and sorted edge sets of the reference construct_edge_indices_and_attrs
                      (lightning/graph_datasets/neighbourhood_list_torch.py:53)
-  nl_bond_merge.pt   inputs and outputs of the same function's bond-feature merge branch (:98-156), open and periodic
+  bondmerge_nl.pt   inputs and outputs of the same function's bond-feature merge branch (:98-156), open and periodic
   gdb9_edges.pt      first six molecules of the reference's tests/data/gdb9.sdf with the edge counts its tests assert
                      (tests/rdkit/core/data/test_graph_dataset.py:42,50; test_datamodule.py:28-35)
 
@@ -196,8 +196,8 @@ def bond_merge():
     cell = torch.eye(3) * 14.0
     ei, ea, sh = nl_mod.construct_edge_indices_and_attrs(pos + 6.0, 5.0, bonds, attrs, (True, True, True), cell, False)
     out["pbc"] = {"cell": cell, "offset": 6.0, "edge_index": ei, "edge_attrs": ea, "shift": sh}
-    torch.save(out, os.path.join(HERE, "nl_bond_merge.pt"))
-    print("nl_bond_merge: E", ei.shape[1], "attr sum", ea.sum(0).tolist())
+    torch.save(out, os.path.join(HERE, "bondmerge_nl.pt"))
+    print("bondmerge_nl: E", ei.shape[1], "attr sum", ea.sum(0).tolist())
 
 
 if __name__ == "__main__":

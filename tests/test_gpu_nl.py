@@ -140,7 +140,7 @@ def test_bond_feature_merge_matches_reference_golden(cuda):
     golden produced by the reference's own construct_edge_indices_and_attrs (tests/golden/make_golden.py §5)"""
     from physicsml_b200.neighbour_list import construct_edge_indices_and_attrs
 
-    g = torch.load(os.path.join(GOLD, "nl_bond_merge.pt"), weights_only=False)
+    g = torch.load(os.path.join(GOLD, "bondmerge_nl.pt"), weights_only=False)
     ei, ea, sh = construct_edge_indices_and_attrs(g["pos"].to(cuda), g["cutoff"], g["bonds"].to(cuda), g["attrs"].to(cuda), None, None, False)
     assert torch.equal(ei.cpu(), g["open"]["edge_index"]) and torch.equal(ea.cpu(), g["open"]["edge_attrs"])
     assert torch.equal(sh.cpu(), g["open"]["shift"])
@@ -222,3 +222,48 @@ def test_collated_batch_runs_the_model(cuda):
     e_ref, f_ref = energy_and_forces(ref, cpu)
     scale = e_ref.abs().max().item()
     assert (e.cpu() - e_ref).abs().max().item() <= 1e-5 * scale and (f.cpu() - f_ref).abs().max().item() <= 1e-4
+
+
+def test_md_loop_skin_list_is_exact_and_reused(cuda):
+    """MDCalculator (Verlet skin + optional CUDA-graph replay) over a short random walk of a periodic
+    box == a fresh neighbour list at the model cut-off + eager evaluation at every step; the list is rebuilt only when
+    an atom moved more than skin / 2"""
+    from physicsml_b200 import workloads as wl
+    from physicsml_b200.mace import PooledMACEModule
+    from physicsml_b200.md import MDCalculator
+    from physicsml_b200.neighbour_list import radius_graph
+
+    kw = dict(cut_off=4.0, num_bessel=8, num_polynomial_cutoff=5, max_ell=2, num_interactions=2, num_node_feats=3, num_edge_feats=0,
+              hidden_irreps="16x0e + 16x1o", avg_num_neighbours=20.0, correlation=3)
+    torch.manual_seed(0)
+    model = PooledMACEModule(mlp_irreps="16x0e", **kw).to(cuda)
+    gen = torch.Generator().manual_seed(8)
+    N, a = 96, 11.0
+    cell = torch.eye(3) * a
+    pos = torch.rand(N, 3, generator=gen) * a
+    attrs = torch.nn.functional.one_hot(torch.randint(0, 3, (N,), generator=gen), 3).float()
+    for use_graph in (False, True):
+        md = MDCalculator(model, 4.0, attrs, cell=cell, skin=0.6, use_graph=use_graph)
+        p = pos.clone()
+        for step in range(12):
+            e, f = md.energy_forces(p)
+            ei, sh, plan = radius_graph(p.to(cuda), 4.0, pbc=(True, True, True), cell=cell.to(cuda))
+            d = {"coordinates": p.to(cuda), "edge_index": ei, "cell": cell.to(cuda), "cell_shift_vector": sh, "node_attrs": attrs.to(cuda),
+                 "batch": torch.zeros(N, dtype=torch.long, device=cuda), "num_graphs": torch.tensor(1)}
+            e0, f0 = wl.energy_forces(model, d)
+            assert (e - e0.reshape(-1)).abs().max().item() <= 2e-6 * max(e0.abs().max().item(), 1e-3), (use_graph, step)
+            assert (f - f0).abs().max().item() <= 2e-6
+            assert md.n_edges >= ei.shape[1]
+            p = p + 0.04 * torch.randn(N, 3, generator=gen)  # ~0.07 A per step: a rebuild every few steps
+        assert 2 <= md.n_builds < 12, md.n_builds
+    # open boundaries + unit scaling as the OpenMM module applies it (nm in, kJ/mol out)
+    md = MDCalculator(model, 4.0, attrs, skin=0.5, position_scaling=10.0, output_scaling=96.4853)
+    e, f = md.energy_forces(pos / 10.0)
+    ei, sh, plan = radius_graph(pos.to(cuda), 4.0)
+    d = {"coordinates": pos.to(cuda), "edge_index": ei, "node_attrs": attrs.to(cuda), "batch": torch.zeros(N, dtype=torch.long, device=cuda),
+         "num_graphs": torch.tensor(1)}
+    e0, f0 = wl.energy_forces(model, d)
+    assert (e - 96.4853 * e0.reshape(-1)).abs().max().item() <= 1e-5 * 96.4853 * max(e0.abs().max().item(), 1e-3)
+    assert (f - 964.853 * f0).abs().max().item() <= 1e-3
+    r = md.ase_results((pos / 10.0).numpy())
+    assert isinstance(r["energy"], float) and r["forces"].shape == (N, 3)
