@@ -91,7 +91,39 @@ def build(verbose: bool = True, jobs: int | None = None, variant: str | None = N
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
         print(f"[physicsml_b200.build] {len(rebuilt)} object(s) rebuilt -> {LIB}", file=sys.stderr)
+    if not variant:
+        build_torch_shim(verbose)
     return LIB
+
+
+TORCH_LIB = os.path.join(CSRC, "libphysicsml_b200_torch.so")
+
+
+def build_torch_shim(verbose: bool = True) -> str:
+    """csrc/torch/torch_shim.cpp -> libphysicsml_b200_torch.so: TORCH_LIBRARY registration (TorchScript-loadable with
+    torch.ops.load_library) of the neighbour list over the C ABI; plain g++ host code linked against the kernels' .so"""
+    import torch
+    from torch.utils.cpp_extension import include_paths
+
+    src = os.path.join(CSRC, "torch", "torch_shim.cpp")
+    header = os.path.join(os.path.dirname(HERE), "include", "physicsml_b200.h")
+    stamp = TORCH_LIB + ".hash"
+    key = _hash([src, header], torch.__version__)
+    if os.path.exists(TORCH_LIB) and os.path.exists(stamp) and open(stamp).read() == key:
+        return TORCH_LIB
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = (["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+           + [f"-I{p}" for p in include_paths()] + ["-I/usr/local/cuda/include", src, "-o", TORCH_LIB, f"-L{CSRC}", "-lphysicsml_b200",
+                                                    f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+                                                    "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for torch_shim.cpp:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(key)
+    if verbose:
+        print(f"[physicsml_b200.build] TORCH_LIBRARY shim -> {TORCH_LIB}", file=sys.stderr)
+    return TORCH_LIB
 
 
 if __name__ == "__main__":

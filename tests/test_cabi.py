@@ -39,3 +39,31 @@ def test_ctypes_table_matches_header():
 
     assert sorted(_lib.SIGNATURES) == _declared()
     _lib.lib()  # sets argtypes on every function
+
+
+def test_torch_library_shim_loads_and_scripts():
+    """the neighbour list is registered with TORCH_LIBRARY in its own small .so, so a TorchScript module (the
+    reference's OpenMM graph module is scripted, plugins/openmm/physicsml_potential.py:130-140) can call it after
+    torch.ops.load_library — no Python at run time"""
+    import os
+
+    import torch
+
+    from physicsml_b200 import build
+
+    path = build.TORCH_LIB
+    assert os.path.exists(path), "run python -m physicsml_b200.build"
+    torch.ops.load_library(path)
+    op = torch.ops.physicsml_b200_ts.radius_graph
+    assert "Tensor? cell" in str(op.default._schema)
+
+    @torch.jit.script
+    def edges(pos: torch.Tensor, cell: torch.Tensor, cutoff: float):
+        ei, sh = torch.ops.physicsml_b200_ts.radius_graph(pos, cell, cutoff, False)
+        return ei, sh
+
+    assert "physicsml_b200_ts::radius_graph" in str(edges.graph)
+    import pytest
+
+    with pytest.raises((NotImplementedError, RuntimeError)):  # no CPU kernel is registered: there is no fallback
+        edges(torch.zeros(4, 3), torch.eye(3), 1.0)

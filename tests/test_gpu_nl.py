@@ -4,6 +4,7 @@ import glob
 import os
 
 import pytest
+from typing import Optional
 import torch
 
 import helpers
@@ -267,3 +268,25 @@ def test_md_loop_skin_list_is_exact_and_reused(cuda):
     assert (f - 964.853 * f0).abs().max().item() <= 1e-3
     r = md.ase_results((pos / 10.0).numpy())
     assert isinstance(r["energy"], float) and r["forces"].shape == (N, 3)
+
+
+def test_torchscript_neighbour_list_op(cuda):
+    """the TORCH_LIBRARY op, called from a scripted function, returns the same edges as the Python entry point"""
+    from physicsml_b200 import build
+    from physicsml_b200.neighbour_list import radius_graph
+
+    torch.ops.load_library(build.TORCH_LIB)
+
+    @torch.jit.script
+    def edges(pos: torch.Tensor, cell: Optional[torch.Tensor], cutoff: float):
+        return torch.ops.physicsml_b200_ts.radius_graph(pos, cell, cutoff, False)
+
+    gen = torch.Generator().manual_seed(4)
+    cell = torch.tensor([[9.0, 0, 0], [1.0, 8.0, 0], [0.5, -1.0, 10.0]])
+    pos = (torch.rand(150, 3, generator=gen) @ cell).to(cuda)
+    ei, sh = edges(pos, cell.to(cuda), 4.5)
+    ei0, sh0, _ = radius_graph(pos, 4.5, pbc=(True, True, True), cell=cell.to(cuda))
+    assert torch.equal(ei, ei0) and torch.equal(sh, sh0)
+    ei, sh = edges(pos, None, 4.5)
+    ei0, sh0, _ = radius_graph(pos, 4.5)
+    assert torch.equal(ei, ei0) and float(sh.abs().max()) == 0.0
