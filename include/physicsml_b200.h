@@ -255,6 +255,13 @@ int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int 
 int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse, pml_stream_t stream);
 
 int pml_scan_i32(const int* counts, int* out, int n, pml_stream_t stream);
+/* Fused force-matching loss (lightning/module.py:65-95, mace_module.py:159-185 with the stock MSE losses):
+ * out[0] = w_e mean((e - e_t)^2) + w_f mean((-gpos - f_t)^2)   (forces = -gpos; ne / nf element counts); deterministic.
+ * bwd: de = gl w_e 2 (e - e_t) / ne ; dgpos = gl w_f 2 (gpos + f_t) / nf   (gl: device scalar, the upstream gradient) */
+int pml_ef_mse_fwd(const float* e, const float* e_t, int ne, const float* gpos, const float* f_t, int nf, float w_e, float w_f,
+                   float* out, pml_stream_t stream);
+int pml_ef_mse_bwd(const float* e, const float* e_t, int ne, const float* gpos, const float* f_t, int nf, float w_e, float w_f,
+                   const float* gl, float* de, float* dgpos, pml_stream_t stream);
 /* Verlet-skin test of a single-structure MD loop (plugins/openmm/openmm_graph.py:119-176 rebuilds the neighbour list on
  * every step): *out = max_i |pos_i - ref_i|^2 over N atoms; out: device float, zero-initialised by the caller. */
 int pml_max_disp2(const float* pos, const float* ref, int N, float* out, pml_stream_t stream);

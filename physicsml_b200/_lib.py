@@ -130,6 +130,8 @@ SIGNATURES = {
     "pml_irreps_to_channel": [_P, _P, _LL, _I, _I, _I, _P],
     "pml_scan_i32": [_P, _P, _I, _P],
     "pml_max_disp2": [_P, _P, _I, _P, _P],
+    "pml_ef_mse_fwd": [_P, _P, _I, _P, _P, _I, _F, _F, _P, _P],
+    "pml_ef_mse_bwd": [_P, _P, _I, _P, _P, _I, _F, _F, _P, _P, _P, _P],
     "pml_nl_setup": [_P, _I, _P, _I, _F, _P, _P, _P, _P],
     "pml_nl_pbc_bin": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     "pml_nl_pbc_fill_bins": [_P, _P, _P, _P, _I, _P],

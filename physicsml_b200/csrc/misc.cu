@@ -211,6 +211,61 @@ extern "C" int pml_pool_gather(const float* g, const long long* batch, float* ou
   return PML_OK;
 }
 
+// Fused force-matching loss (reference lightning/module.py:65-95 + mace_module.py:159-185 with the stock
+// MSELoss on y_graph_scalars and y_node_vector):  loss = w_e mean((e - e_t)^2) + w_f mean((-gpos - f_t)^2), forces = -gpos.
+// One CTA, fixed summation order: deterministic (the eager chain is ~8 kernels forward and ~8 backward).
+namespace pml {
+__global__ void __launch_bounds__(1024) ef_mse_fwd_kernel(const float* __restrict__ e, const float* __restrict__ e_t, int ne,
+                                                          const float* __restrict__ gpos, const float* __restrict__ f_t, int nf,
+                                                          float w_e, float w_f, float* __restrict__ out) {
+  float se = 0.f, sf = 0.f;
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    const float d = e[i] - e_t[i];
+    se = fmaf(d, d, se);
+  }
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+    const float d = -gpos[i] - f_t[i];
+    sf = fmaf(d, d, sf);
+  }
+  __shared__ float red[2][32];
+  se = warp_sum(se), sf = warp_sum(sf);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = se, red[1][threadIdx.x >> 5] = sf;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    se = threadIdx.x < nw ? red[0][threadIdx.x] : 0.f;
+    sf = threadIdx.x < nw ? red[1][threadIdx.x] : 0.f;
+    se = warp_sum(se), sf = warp_sum(sf);
+    if (threadIdx.x == 0) out[0] = w_e * se / (float)max(ne, 1) + w_f * sf / (float)max(nf, 1);
+  }
+}
+__global__ void __launch_bounds__(256) ef_mse_bwd_kernel(const float* __restrict__ e, const float* __restrict__ e_t, int ne,
+                                                         const float* __restrict__ gpos, const float* __restrict__ f_t, int nf,
+                                                         float w_e, float w_f, const float* __restrict__ gl,
+                                                         float* __restrict__ de, float* __restrict__ dgpos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float g = gl[0];
+  if (i < ne) de[i] = g * w_e * 2.f * (e[i] - e_t[i]) / (float)ne;
+  const int j = i - ne;
+  if (j >= 0 && j < nf) dgpos[j] = g * w_f * 2.f * (gpos[j] + f_t[j]) / (float)nf;
+}
+}  // namespace pml
+
+extern "C" int pml_ef_mse_fwd(const float* e, const float* e_t, int ne, const float* gpos, const float* f_t, int nf, float w_e,
+                              float w_f, float* out, cudaStream_t stream) {
+  pml::ef_mse_fwd_kernel<<<1, 1024, 0, stream>>>(e, e_t, ne, gpos, f_t, nf, w_e, w_f, out);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_ef_mse_bwd(const float* e, const float* e_t, int ne, const float* gpos, const float* f_t, int nf, float w_e,
+                              float w_f, const float* gl, float* de, float* dgpos, cudaStream_t stream) {
+  if (ne + nf <= 0) return PML_OK;
+  pml::ef_mse_bwd_kernel<<<pml::ceil_div(ne + nf, 256), 256, 0, stream>>>(e, e_t, ne, gpos, f_t, nf, w_e, w_f, gl, de, dgpos);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
 // Verlet-skin test of the MD loop (md.py): *out = max_i |pos_i - ref_i|^2 (out zero-initialised by the caller; the
 // squared displacement is non-negative, so its IEEE bits order like an unsigned integer)
 namespace pml {

@@ -1141,6 +1141,55 @@ irreps_to_channel.register_autograd(
 
 
 # ======================================================================================================================
+# fused force-matching loss
+# ======================================================================================================================
+@torch.library.custom_op(f"{NS}::energy_force_mse", mutates_args=(), device_types="cuda")
+def energy_force_mse(e: Tensor, e_t: Tensor, gpos: Tensor, f_t: Tensor, w_e: float, w_f: float) -> Tensor:
+    """w_e * mean((e - e_t)^2) + w_f * mean((-gpos - f_t)^2) with forces = -gpos = -dE/dx (reference lightning/module.py:65-95
+    + the stock MSE losses on y_graph_scalars / y_node_vector, mace_module.py:159-185): one deterministic kernel"""
+    e, e_t, gpos, f_t = _f32c(e), _f32c(e_t), _f32c(gpos), _f32c(f_t)
+    if e.numel() != e_t.numel() or gpos.numel() != f_t.numel():
+        raise ValueError("prediction / target shapes differ")
+    out = _new_empty(e, 1)
+    _call("pml_ef_mse_fwd", _p(e), _p(e_t), e.numel(), _p(gpos), _p(f_t), gpos.numel(), float(w_e), float(w_f), _p(out), _stream())
+    return out.reshape(())
+
+
+@energy_force_mse.register_fake
+def _(e, e_t, gpos, f_t, w_e, w_f):
+    return e.new_empty(())
+
+
+@torch.library.custom_op(f"{NS}::energy_force_mse_bwd", mutates_args=(), device_types="cuda")
+def energy_force_mse_bwd(gl: Tensor, e: Tensor, e_t: Tensor, gpos: Tensor, f_t: Tensor, w_e: float, w_f: float) -> Tuple[Tensor, Tensor]:
+    e, e_t, gpos, f_t, gl = _f32c(e), _f32c(e_t), _f32c(gpos), _f32c(f_t), _f32c(gl)
+    de, dg = _empty_like(e), _empty_like(gpos)
+    _call("pml_ef_mse_bwd", _p(e), _p(e_t), e.numel(), _p(gpos), _p(f_t), gpos.numel(), float(w_e), float(w_f), _p(gl), _p(de), _p(dg),
+          _stream())
+    return de, dg
+
+
+@energy_force_mse_bwd.register_fake
+def _(gl, e, e_t, gpos, f_t, w_e, w_f):
+    return _empty_like(e), _empty_like(gpos)
+
+
+def _efm_setup(ctx, inputs, output):
+    e, e_t, gpos, f_t, w_e, w_f = inputs
+    ctx.save_for_backward(e, e_t, gpos, f_t)
+    ctx.w = (w_e, w_f)
+
+
+def _efm_bwd(ctx, gl):
+    e, e_t, gpos, f_t = ctx.saved_tensors
+    de, dg = energy_force_mse_bwd(gl, e, e_t, gpos, f_t, *ctx.w)
+    return (de if ctx.needs_input_grad[0] else None, None, dg if ctx.needs_input_grad[2] else None, None, None, None)
+
+
+energy_force_mse.register_autograd(_efm_bwd, setup_context=_efm_setup)
+
+
+# ======================================================================================================================
 # graph structure (index plumbing only — no floating-point work)
 # ======================================================================================================================
 def edge_plan_for(data: dict, num_nodes: int, scatter_row: int) -> "EdgePlan":

@@ -259,6 +259,8 @@ def training_loss(model, data: dict, targets: dict) -> torch.Tensor:
 
     with ops.input_grads_only():  # the force pass: gradients w.r.t. the coordinates only
         (g,) = torch.autograd.grad([e], [pos], grad_outputs=[torch.ones_like(e)], retain_graph=True, create_graph=True)
+    if e.is_cuda:  # MSE(E) + MSE(F) in one kernel; the CPU legs (oracle / reference arm) use the stock losses
+        return ops.energy_force_mse(e, targets["energy"], g, targets["forces"], 1.0, 1.0)
     return torch.nn.functional.mse_loss(e, targets["energy"]) + torch.nn.functional.mse_loss(-g, targets["forces"])
 
 

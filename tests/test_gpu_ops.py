@@ -581,3 +581,23 @@ def test_fused_adam_matches_torch(cuda):
     assert float(o_mine.state[p_mine[0]]["step"]) == 6.0
     for a, b in zip(p_ref, p_mine):
         assert _rel(o_mine.state[b]["max_exp_avg_sq"], o_ref.state[a]["max_exp_avg_sq"]) < 1e-6
+
+
+def test_fused_energy_force_mse(cuda):
+    """the fused loss == MSELoss(E) + MSELoss(F) with F = -dE/dx, value and gradients"""
+    from physicsml_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    e, e_t = torch.randn(32, 1, generator=g), torch.randn(32, 1, generator=g)
+    gp, f_t = torch.randn(1304, 3, generator=g), torch.randn(1304, 3, generator=g)
+    a = [t.clone().to(cuda).requires_grad_(r) for t, r in ((e, True), (e_t, False), (gp, True), (f_t, False))]
+    loss = ops.energy_force_mse(a[0], a[1], a[2], a[3], 1.0, 10.0)
+    (loss * 3.0).backward()
+    b = [t.clone().double().requires_grad_(r) for t, r in ((e, True), (e_t, False), (gp, True), (f_t, False))]
+    ref = torch.nn.functional.mse_loss(b[0], b[1]) + 10.0 * torch.nn.functional.mse_loss(-b[2], b[3])
+    (ref * 3.0).backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert (a[0].grad.cpu().double() - b[0].grad).abs().max().item() <= 1e-6 * b[0].grad.abs().max().item()
+    assert (a[2].grad.cpu().double() - b[2].grad).abs().max().item() <= 1e-6 * b[2].grad.abs().max().item()
+    again = ops.energy_force_mse(a[0], a[1], a[2], a[3], 1.0, 10.0)
+    assert again.item() == loss.item()  # one CTA, fixed order: deterministic
