@@ -151,9 +151,21 @@ def enable_kernel_timing(names) -> None:
         KERNEL_TIMING[n] = []
 
 
+# PML_NVTX=1: every C-ABI launch is wrapped in an NVTX range named after its entry point, so nsys / ncu --nvtx timelines
+# show the hot path by operator (the reference has no tracing hooks of its own)
+NVTX = [os.environ.get("PML_NVTX", "0") == "1"]
+
+
 def _call(name: str, *args, launches: int = 1, tag=None) -> None:
     """launch through the C ABI; ``tag`` (default: the first argument) labels the launch in KERNEL_TIMING records"""
     LAUNCHES[0] += launches
+    if NVTX[0]:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            _lib.check(getattr(_lib.lib(), name)(*args), name)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     rec = KERNEL_TIMING.get(name[:-3] if name.endswith("_ex") else name)  # pml_tp_fwd_ex is timed as pml_tp_fwd
     if rec is None:
         _lib.check(getattr(_lib.lib(), name)(*args), name)
