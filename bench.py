@@ -46,7 +46,8 @@ def shared_config(world: int = 1) -> dict:
     return {"workload": WORKLOAD,
             "step": "training: fwd + forces(create_graph) + MSE(E)+MSE(F) + bwd + allreduce + Adam(amsgrad)",
             "molecules_per_gpu": wl.CONFIGS[WORKLOAD]["n_mol"], "atoms_per_gpu": int(data["coordinates"].shape[0]),
-            "edges_per_gpu": int(data["edge_index"].shape[1])}
+            "edges_per_gpu": int(data["edge_index"].shape[1]),
+            "per_rank_batches": "same molecule sizes on every rank (fixed work per GPU), different coordinates and species"}
 
 
 class ClockSampler:

@@ -102,7 +102,12 @@ class InteractionBlock(torch.nn.Module):
         x = data["node_feats"]
         plan = ops.edge_plan_for(data, x.shape[0], scatter_row=0)
         gather, rowptr, perm = plan.view(0)  # gather edge_index[1], scatter to edge_index[0]
-        weight = self.fc(data["edge_feats"])
+        pre = data.get("_radial")
+        if pre is not None and id(self) in pre:  # computed on the side stream by Nequip.forward
+            weight, ready = pre.pop(id(self))
+            torch.cuda.current_stream().wait_event(ready)
+        else:
+            weight = self.fc(data["edge_feats"])
         sc = None
         if self.self_connection_layer is not None:
             sc = self.self_connection_layer(x, data["node_attrs"])
@@ -194,8 +199,14 @@ class Nequip(torch.nn.Module):
                                   1.0 / re.r_max, re.p, self.max_ell)
         data["edge_feats"] = torch.cat([B, data["edge_attrs"]], dim=-1) if "edge_attrs" in data else B
         data["edge_attrs"] = Y
+        from .mace import radial_on_side_stream, side_stream_ok
+
+        if side_stream_ok(data["edge_feats"]):  # all layers' radial MLPs next to the node-level chain (see mace.MACE.forward)
+            convs = [layer.conv for layer in self.conv_layers]
+            data["_radial"] = dict(zip((id(c) for c in convs), radial_on_side_stream([c.fc for c in convs], data["edge_feats"])))
         for layer in self.conv_layers:
             data = layer(data)
+        data.pop("_radial", None)
         if supplied is None:
             data.pop("_edge_plan", None)
         else:

@@ -96,11 +96,15 @@ def rocksalt_cells(n_cells: int, reps: int = 3, lattice: float = 4.5, sigma: flo
             torch.tensor(np.concatenate(batch), dtype=torch.long), cell)
 
 
-def random_molecules(n_mol, n_lo, n_hi, n_species, seed, min_dist=0.95, probs=None):
+def random_molecules(n_mol, n_lo, n_hi, n_species, seed, min_dist=0.95, probs=None, sizes=None):
+    """sizes: atom counts to use instead of drawing them (the size draw is still consumed, so that a batch built with its
+    own sizes is reproduced bit for bit)"""
     rng = np.random.default_rng(seed)
     pos, z, batch = [], [], []
     for m in range(n_mol):
         n = int(rng.integers(n_lo, n_hi + 1))
+        if sizes is not None:
+            n = int(sizes[m])
         rad = 0.95 * n ** (1.0 / 3.0) * 1.1
         pts = []
         while len(pts) < n:
@@ -186,7 +190,13 @@ def make_batch(name: str, rank: int = 0, n_mol: int | None = None, edges: bool =
         n_graphs = n_mol
         data["cell"] = cell
     else:
-        pos, z, batch = random_molecules(n_mol, cfg["atoms"][0], cfg["atoms"][1], cfg["Z"], seed, probs=cfg["probs"])
+        # weak scaling = fixed work per GPU: every rank gets molecules of the SAME sizes as rank 0 (its own coordinates and
+        # species), so the step time of N ranks is not the time of whichever rank drew the largest molecules
+        sizes = None
+        if rank != 0:
+            _, _, b0 = random_molecules(n_mol, cfg["atoms"][0], cfg["atoms"][1], cfg["Z"], cfg["seed"], probs=cfg["probs"])
+            sizes = torch.bincount(b0, minlength=n_mol).tolist()
+        pos, z, batch = random_molecules(n_mol, cfg["atoms"][0], cfg["atoms"][1], cfg["Z"], seed, probs=cfg["probs"], sizes=sizes)
         n_graphs = n_mol
     data.update({
         "coordinates": pos,
