@@ -32,6 +32,21 @@ def side_stream_ok(edge_feats: torch.Tensor) -> bool:
     return bool(SIDE_STREAM[0]) and edge_feats.is_cuda and SIDE_STREAM_MIN_EDGES <= edge_feats.shape[0] <= SIDE_STREAM_MAX_EDGES
 
 
+def on_side_stream(fn, *tensors):
+    """run ``fn(*tensors)`` on the side stream -> (result, event); the consumer waits for the event on its own stream
+    right before it reads the result (autograd runs the cotangent of `fn` on the side stream as well)"""
+    main = torch.cuda.current_stream()
+    side = _side_stream(tensors[0].device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        out = fn(*tensors)
+        out.record_stream(main)
+        ev = side.record_event()
+    for t in tensors:
+        t.record_stream(side)
+    return out, ev
+
+
 def radial_on_side_stream(mlps, edge_feats: torch.Tensor) -> list:
     """run the radial MLPs `mlps` (one per layer, all functions of the edge features only) on the side stream;
     -> [(R_i, event_i)]: the consumer waits for event_i on its own stream right before it reads R_i"""
@@ -282,10 +297,16 @@ class NodeUpdateBlock(torch.nn.Module):
             if residual_connection else None
         )
 
-    def forward(self, m_i, node_feats, node_attrs):
+    def forward(self, m_i, node_feats, node_attrs, residual=None):
+        """residual: (tensor, event) if the caller already ran ``residual_connection_layer`` on the side stream (it depends
+        on the layer's INPUT features only, so MACE.forward starts it before the interaction block)"""
         out = self.linear(m_i)
         if self.residual_connection_layer is not None:
-            out = out + self.residual_connection_layer(node_feats, node_attrs)
+            if residual is None:
+                out = out + self.residual_connection_layer(node_feats, node_attrs)
+            else:
+                torch.cuda.current_stream().wait_event(residual[1])
+                out = out + residual[0]
         return out
 
 
@@ -344,8 +365,11 @@ class MACE(torch.nn.Module):
             radial = radial_on_side_stream([inter.net_R_channels for inter in self.interactions], B)
         h = self.node_embedding(attrs)
         for i, (inter, msg, upd) in enumerate(zip(self.interactions, self.messages, self.node_updates)):
+            res = None
+            if radial[i] is not None and upd.residual_connection_layer is not None:
+                res = on_side_stream(upd.residual_connection_layer, h, attrs)
             a = inter(h, attrs, Y, B, edge_index, edge_plan=plan, radial=radial[i])
-            h = upd(msg(a, attrs), h, attrs)
+            h = upd(msg(a, attrs), h, attrs, residual=res)
             data[f"node_feats_{i}"] = h
         return data
 
@@ -390,8 +414,19 @@ class ReadoutHead(torch.nn.Module):
 
     def forward(self, data: dict) -> torch.Tensor:
         x = None
-        for i, ro in enumerate(self.readouts):
-            y = ro(data[f"node_feats_{i}"])
+        feats = [data[f"node_feats_{i}"] for i in range(len(self.readouts))]
+        small = bool(SIDE_STREAM[0]) and feats[0].is_cuda and 256 <= feats[0].shape[0] <= 16384
+        # the per-layer readouts are independent of each other: all but the last run on the side stream (their cotangents
+        # then overlap the backward pass of the later layers)
+        early = [on_side_stream(ro, f) if small else None for ro, f in zip(self.readouts[:-1], feats[:-1])]
+        ys = [self.readouts[-1](feats[-1])]
+        for i, ro in enumerate(self.readouts[:-1]):
+            if early[i] is None:
+                ys.append(ro(feats[i]))
+            else:
+                torch.cuda.current_stream().wait_event(early[i][1])
+                ys.append(early[i][0])
+        for y in ys[1:] + ys[:1]:  # layer order, as the reference sums them (mace.py:203-214)
             x = y if x is None else x + y
         x = self.scale_shift(x)
         if self.pooled:

@@ -103,18 +103,27 @@ class InteractionBlock(torch.nn.Module):
         plan = ops.edge_plan_for(data, x.shape[0], scatter_row=0)
         gather, rowptr, perm = plan.view(0)  # gather edge_index[1], scatter to edge_index[0]
         pre = data.get("_radial")
+        ready = None
         if pre is not None and id(self) in pre:  # computed on the side stream by Nequip.forward
             weight, ready = pre.pop(id(self))
-            torch.cuda.current_stream().wait_event(ready)
         else:
             weight = self.fc(data["edge_feats"])
-        sc = None
+        sc = sc_ready = None
         if self.self_connection_layer is not None:
-            sc = self.self_connection_layer(x, data["node_attrs"])
+            if pre is not None:  # small-graph mode: the self connection is independent of the convolution -> side stream
+                from .mace import on_side_stream
+
+                sc, sc_ready = on_side_stream(self.self_connection_layer, x, data["node_attrs"])
+            else:
+                sc = self.self_connection_layer(x, data["node_attrs"])
         h = self.linear_1(x)
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)  # join right before the first consumer of the radial weights
         a = ops.tp_scatter(h, data["edge_attrs"], weight, gather, rowptr, perm, self.tp_plan.handle)
         a = self.linear_2(a)
         if sc is not None:
+            if sc_ready is not None:
+                torch.cuda.current_stream().wait_event(sc_ready)
             a = a + sc
         data["node_feats"] = a
         return data

@@ -10,14 +10,11 @@ import torch  # noqa: E402
 
 from physicsml_b200 import ops  # noqa: E402
 from physicsml_b200 import workloads as wl  # noqa: E402
-from physicsml_b200.mace import PooledMACEModule  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "mace_medium_spice_train"
 dev = torch.device("cuda:0")
 data, targets, kw, mlp = wl.make_batch(name, 0)
-kw["avg_num_neighbours"] = wl.mean_degree(name)
-torch.manual_seed(0)
-model = PooledMACEModule(mlp_irreps=mlp, **kw).to(dev)
+model = wl.build_model(name).to(dev)
 opt = wl.make_optimizer(model)
 d = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in data.items()}
 t = {k: v.to(dev) for k, v in targets.items()}
