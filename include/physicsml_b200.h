@@ -66,8 +66,10 @@ int pml_tp_fwd(int spec, const float* h, const float* Y, const float* R, const i
 int pml_tp_bwd(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,
                const int* rowptr, const int* perm, float* dh, float* dY, float* dR, int N, int C, pml_stream_t stream);
 /* Same kernels with a choice of layout inside every block of the output row `out` / its cotangent `g`:
- * out_layout 0 = e3nn order u*(2l+1) + m (what pml_tp_fwd / pml_tp_bwd use), 1 = component-major m*C + u (packed
- * 8-byte stores; the per-irrep linear that consumes the row then reads its reduction index with unit stride). */
+ * out_layout bit 0: 0 = e3nn order u*(2l+1) + m (what pml_tp_fwd / pml_tp_bwd use), 1 = component-major m*C + u (packed
+ * 8-byte stores; the per-irrep linear that consumes the row then reads its reduction index with unit stride).
+ * out_layout bit 1 (pml_tp_bwd_ex only): dR is ADDED (L2 reductions) to the values already in the buffer instead of
+ * overwritten — the second-order pass accumulates its two dR contributions without an R-sized add kernel. */
 int pml_tp_fwd_ex(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
                   const int* perm, float* out, int N, int C, int out_layout, pml_stream_t stream);
 int pml_tp_bwd_ex(int spec, const float* h, const float* Y, const float* R, const float* g, const int* gather,

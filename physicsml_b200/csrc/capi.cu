@@ -28,26 +28,28 @@ extern "C" int pml_abi_version(void) { return 1; }
 
 // K4 kernel selection (A/B measurements, tests of the path taken when rows are not 16-byte multiples).  Bit 0: use the
 // register-streaming kernels; bit 1 / bit 2: flip the producer placement of the pipelined forward / cotangent kernel
-// (default: dedicated producer warp in the forward, warp 0 doubles as producer in the cotangent kernel).
+// (default: dedicated producer warp in the forward, warp 0 doubles as producer in the cotangent kernel); bit 3: signatures
+// with several path groups run one launch per group instead of all groups inside one CTA.
 // Initial value: env PML_TP_SIMPLE (integer).
 #include <stdlib.h>
 static int g_tp_mode = -1;
 extern "C" int pml_tp_force_simple(void) {
   if (g_tp_mode < 0) {
     const char* e = getenv("PML_TP_SIMPLE");
-    g_tp_mode = e ? atoi(e) & 7 : 0;
+    g_tp_mode = e ? atoi(e) & 15 : 0;
   }
   return g_tp_mode;
 }
 extern "C" int pml_tp_set_simple(int v) {
   const int old = pml_tp_force_simple();
-  g_tp_mode = v & 7;
+  g_tp_mode = v & 15;
   return old;
 }
 extern "C" int pml_num_tp_specs(void) { return PML_TP_NUM_SPECS; }
 extern "C" int pml_num_sym_specs(void) { return PML_SYM_NUM_SPECS; }
 
-// out_layout: 0 = e3nn order inside every output block (u*(2l+1) + m), 1 = component-major (m*C + u)
+// out_layout bit 0: 0 = e3nn order inside every output block (u*(2l+1) + m), 1 = component-major (m*C + u);
+// bit 1 (cotangent only): dR is ADDED to the values already in the buffer instead of overwritten
 extern "C" int pml_tp_fwd_ex(int spec, const float* h, const float* Y, const float* R, const int* gather, const int* rowptr,
                              const int* perm, float* out, int N, int C, int out_layout, cudaStream_t stream) {
   switch (spec) {

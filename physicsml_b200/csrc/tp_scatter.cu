@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) tp_fwd_kernel(const float* __restrict__ h
     T::fwd(h0, Y0, R0, acc);
   }
   if (active) {  // mm: component-major blocks (m*C + u) instead of the e3nn order (u*(2l+1) + m)
-    if (mm) T::template store_out<true>(out + (size_t)n * T::DOUT * C, C, u, acc);
+    if (mm & 1) T::template store_out<true>(out + (size_t)n * T::DOUT * C, C, u, acc);
     else T::template store_out<false>(out + (size_t)n * T::DOUT * C, C, u, acc);
   }
 }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) tp_bwd_kernel(const float* __restrict__ h
   const int uc = active ? u : C - 1;
 
   float gv[T::DOUT];
-  if (mm) T::template load_out<true>(g + (size_t)n * T::DOUT * C, C, uc, gv);
+  if (mm & 1) T::template load_out<true>(g + (size_t)n * T::DOUT * C, C, uc, gv);
   else T::template load_out<false>(g + (size_t)n * T::DOUT * C, C, uc, gv);
   if (!active) {
 #pragma unroll
@@ -174,7 +174,11 @@ __global__ void __launch_bounds__(128) tp_bwd_kernel(const float* __restrict__ h
 
     if (WANT_R && active) {
 #pragma unroll
-      for (int p = 0; p < T::NP; ++p) st_stream(dR + (size_t)e * rstride + (size_t)p * C + u, dRv[p]);
+      for (int p = 0; p < T::NP; ++p) {
+        float* q_ = dR + (size_t)e * rstride + (size_t)p * C + u;
+        if (mm & 2) atomicAdd(q_, dRv[p]);  // accumulate onto an existing dR (second-order pass)
+        else st_stream(q_, dRv[p]);
+      }
     }
     if (WANT_H && active) T::atomic_add_h(dh + (size_t)s * hstride, C, u, dhv);
     if (WANT_Y) {
@@ -522,7 +526,7 @@ __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __r
         T::fwd2(hv, Yv, Rv, acc);
       }
       if (active) {
-        if (mm) T::template store_out2<true>(out + (size_t)n * T::DOUT_FULL * C, C, u, acc);
+        if (mm & 1) T::template store_out2<true>(out + (size_t)n * T::DOUT_FULL * C, C, u, acc);
         else T::template store_out2<false>(out + (size_t)n * T::DOUT_FULL * C, C, u, acc);
       }
       end = end_next;
@@ -558,7 +562,7 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
       const int end_next = (n + 2 <= N) ? min(__ldg(rowptr + n + 2), q_hi) : q_hi;
       float2 gv[T::DOUT];
       if (q < end) {
-        if (mm) T::template load_out2<true>(g + (size_t)n * T::DOUT_FULL * C, C, uc, gv);
+        if (mm & 1) T::template load_out2<true>(g + (size_t)n * T::DOUT_FULL * C, C, uc, gv);
         else T::template load_out2<false>(g + (size_t)n * T::DOUT_FULL * C, C, uc, gv);
         if (!active) {
 #pragma unroll
@@ -597,7 +601,12 @@ __global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __r
         if (WANT_R && active) {
           float* drow = dR + (size_t)e * rstride + (size_t)T::P0 * C + u;
 #pragma unroll
-          for (int p = 0; p < T::NP; ++p) st_stream2_hint(drow + p * C, dRv[p], pol_stream);
+          for (int p = 0; p < T::NP; ++p) {
+            // mm bit 1: ADD into an existing dR row (the two dR contributions of the second-order pass are accumulated
+            // here by L2 reductions — no load in the SM — instead of a separate R-sized add kernel)
+            if (mm & 2) red_add_f32x2(drow + p * C, dRv[p].x, dRv[p].y, pol_stream);
+            else st_stream2_hint(drow + p * C, dRv[p], pol_stream);
+          }
         }
         if (WANT_H) {
           if (active) T::atomic_add_h2(dh + (size_t)es.y * hstride, C, u, dhv, pol_keep);
@@ -675,7 +684,7 @@ __device__ __forceinline__ void fwd_group_body(const PipeCtx& c, PROD& prod, int
         TG::fwd2(hv, Yv, Rv, acc);
       }
       if (active) {
-        if (c.mm) TG::template store_out2<true>(out + (size_t)n * TG::DOUT_FULL * C, C, u, acc);
+        if (c.mm & 1) TG::template store_out2<true>(out + (size_t)n * TG::DOUT_FULL * C, C, u, acc);
         else TG::template store_out2<false>(out + (size_t)n * TG::DOUT_FULL * C, C, u, acc);
       }
       end = end_next;
@@ -758,7 +767,7 @@ __device__ __forceinline__ void bwd_group_body(const PipeCtx& c, PROD& prod, int
     const int end_next = (n + 2 <= N) ? min(__ldg(c.rowptr + n + 2), c.q_hi) : c.q_hi;
     float2 gv[TG::DOUT];
     if (q < end) {
-      if (c.mm) TG::template load_out2<true>(g + (size_t)n * TG::DOUT_FULL * C, C, uc, gv);
+      if (c.mm & 1) TG::template load_out2<true>(g + (size_t)n * TG::DOUT_FULL * C, C, uc, gv);
       else TG::template load_out2<false>(g + (size_t)n * TG::DOUT_FULL * C, C, uc, gv);
       if (!active) {
 #pragma unroll
@@ -797,7 +806,10 @@ __device__ __forceinline__ void bwd_group_body(const PipeCtx& c, PROD& prod, int
       if (WANT_R && active) {
         float* drow = dR + (size_t)e * rstride + (size_t)TG::P0 * C + u;
 #pragma unroll
-        for (int p = 0; p < TG::NP; ++p) st_stream2_hint(drow + p * C, dRv[p], pol_stream);
+        for (int p = 0; p < TG::NP; ++p) {
+          if (c.mm & 2) red_add_f32x2(drow + p * C, dRv[p].x, dRv[p].y, pol_stream);
+          else st_stream2_hint(drow + p * C, dRv[p], pol_stream);
+        }
       }
       if (WANT_H) {
         if (active) TG::atomic_add_h2(dh + (size_t)es.y * hstride, C, u, dhv, pol_keep);
