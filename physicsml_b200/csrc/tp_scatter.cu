@@ -982,7 +982,10 @@ static int max_group_dout() {
 template <int ID>
 static bool intra_supported(int C) {
   using L = PipeLayout<TPCode<ID>>;
-  return TPGroups<ID>::N > 1 && L::rows_ok(C) && max_group_dout<ID>() <= 48 &&
+  // measured (profiles/r02_k4_path_group_experiments.log): with one consumer warp per group (C <= 64, NequIP) sharing the
+  // staged rows wins clearly (forward 129 vs 184 us); with four warps per group (C = 256, MACE large) one launch per
+  // group is faster in the forward (355 vs 420 us) and equal in the cotangent: those keep their own launches
+  return TPGroups<ID>::N > 1 && L::rows_ok(C) && max_group_dout<ID>() <= 48 && L::consumer_threads(C) == 32 &&
          TPGroups<ID>::N * L::consumer_threads(C) + 32 <= 1024;
 }
 
