@@ -154,7 +154,10 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_mol = args.ref_molecules if args.ref_molecules > 0 else None
+    # N = 1 (the line the headline ratio is computed from): the FULL 32-molecule batch, ~19 s per step on 16 cores.  In the
+    # scaling run (N > 1) the reference arm is still one CPU process on rank 0: there it runs a bounded 4-molecule sample
+    # of the same workload so that four more runs of K + W steps stay within minutes (cpu_baseline.sample says which)
+    n_mol = args.ref_molecules if args.ref_molecules > 0 else (None if args.gpus <= 1 else PARITY_MOLECULES)
     rate, cores, sample, ms, kind = cpu_reference_step_rate(n_mol, max(1, args.steps), max(1, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "atoms/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -196,7 +199,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-molecules", type=int, default=0,
-                    help="molecules of the batch the --impl reference arm runs (0 = the full 32-molecule batch)")
+                    help="molecules of the batch the --impl reference arm runs (0 = the full 32-molecule batch at --gpus 1, a "
+                         "4-molecule sample in the scaling runs)")
     ap.add_argument("--cpu-baseline-molecules", type=int, default=PARITY_MOLECULES,
                     help="bounded sample of the cpu_baseline leg inside the GPU arm's run")
     ap.add_argument("--configs", default="all", help="'all', 'headline' or a comma-separated list of other_configs to run")

@@ -253,6 +253,10 @@ int pml_csr_rowptr(const long long* idx, int* counts, int* rowptr, int E, int N,
  * grouping to scatter_add's atomics).  cursor: zeroed scratch [N]; perm [E]. */
 int pml_csr_group(const long long* idx, const int* rowptr, int* cursor, int* perm, int E, int N, pml_stream_t stream);
 int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int E, pml_stream_t stream);
+/* dst[n, j] = src[n, colmap[j]] (colmap: device int32 [dst_row]): component-major copies of o3.Linear operands
+ * (blocks.py:139-144,176-181 store them in the e3nn order) so that the GEMM's reduction index has unit stride */
+int pml_permute_columns(const float* src, long long src_row, const int* colmap, float* dst, int dst_row, long long N,
+                        pml_stream_t stream);
 /* [N, C*S] irreps layout <-> [N, C, S] (models/mace/modules/irreps_tools.py:47-67) */
 int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse, pml_stream_t stream);
 

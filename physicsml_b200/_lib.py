@@ -127,6 +127,7 @@ SIGNATURES = {
     "pml_csr_rowptr": [_P, _P, _P, _I, _I, _P],
     "pml_csr_group": [_P, _P, _P, _P, _I, _I, _P],
     "pml_split_edge_index": [_P, _P, _P, _I, _P],
+    "pml_permute_columns": [_P, _LL, _P, _P, _I, _LL, _P],
     "pml_irreps_to_channel": [_P, _P, _LL, _I, _I, _I, _P],
     "pml_scan_i32": [_P, _P, _I, _P],
     "pml_max_disp2": [_P, _P, _I, _P, _P],

@@ -211,6 +211,32 @@ extern "C" int pml_pool_gather(const float* g, const long long* batch, float* ou
   return PML_OK;
 }
 
+// dst[n, j] = src[n, colmap[j]]: re-orders the columns of a node-feature row.  Used to hand the grouped GEMM a COMPONENT-MAJOR
+// copy (m*mul + u inside every irrep block) of an operand stored in the e3nn order (u*(2l+1) + m) or the channel layout
+// ([C, S]): the reduction index of the per-irrep mixing then has unit stride, which is the difference between 16-byte
+// coalesced operand loads and one 32-byte sector per element (config 5: 254 -> ~40 us for the cotangent of a 256-channel
+// o3.Linear).  Rows are a few KB and L2-resident; the pass costs a few microseconds.
+namespace pml {
+__global__ void __launch_bounds__(256) permute_columns_kernel(const float* __restrict__ src, long long src_row,
+                                                              const int* __restrict__ colmap, float* __restrict__ dst,
+                                                              int dst_row, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / dst_row;
+  const int j = (int)(i - n * dst_row);
+  dst[i] = __ldg(src + n * src_row + __ldg(colmap + j));
+}
+}  // namespace pml
+
+extern "C" int pml_permute_columns(const float* src, long long src_row, const int* colmap, float* dst, int dst_row, long long N,
+                                   cudaStream_t stream) {
+  const long long total = N * dst_row;
+  if (total <= 0) return PML_OK;
+  pml::permute_columns_kernel<<<pml::ceil_div(total, 256), 256, 0, stream>>>(src, src_row, colmap, dst, dst_row, total);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
 // Fused force-matching loss (reference lightning/module.py:65-95 + mace_module.py:159-185 with the stock
 // MSELoss on y_graph_scalars and y_node_vector):  loss = w_e mean((e - e_t)^2) + w_f mean((-gpos - f_t)^2), forces = -gpos.
 // One CTA, fixed summation order: deterministic (the eager chain is ~8 kernels forward and ~8 backward).

@@ -535,6 +535,9 @@ def _splitk_rows(tiles: int, k_extent: int, slots: int) -> int:
     return best
 
 
+# PML_COMPONENT_COPIES=0: let the tensor-core GEMM read e3nn-ordered operands in place (strided reduction index; A/B runs)
+COMPONENT_COPIES = [os.environ.get("PML_COMPONENT_COPIES", "1") == "1"]
+
 WIDE_MIN_ROWS = [int(os.environ.get("PML_WIDE_MIN_ROWS", "4096"))]
 
 
@@ -585,6 +588,13 @@ def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
         return out
     out = _zeros(x, shape) if pl.has_unfed_output else _new_empty(x, shape)
     fwd, _, _ = pl.tables(x.device)
+    if fwd is not None and n > 0 and pl._fwd_c and _gemm_name(n).endswith("_tc") and COMPONENT_COPIES[0]:
+        # e3nn-ordered input with l > 0 blocks: the GEMM reads a component-major copy (unit-stride reduction index)
+        cmap, fwd_c = pl.tables_c(x.device)[0]
+        xc = _new_empty(x, n, pl.d_in)
+        _call("pml_permute_columns", _p(x), pl.d_in, _p(cmap), _p(xc), pl.d_in, n, _stream())
+        _gemm(_gemm_name(n), _p(xc), _p(w), _p(out), _p(fwd_c), len(pl._fwd_c), n, n, pl.max_mul_out, pl.max_d, 1, pl.max_k_fwd)
+        return out
     if fwd is not None and n > 0:
         nprob = len(pl._fwd)
         if pl.fwd_serial:
@@ -624,6 +634,14 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
         sk = _splitk_rows(tiles, pl.max_k_bwd_x, _tc_slots(bn, True))
     dx = _zeros(g, n, pl.d_in) if (pl.has_unfed_input or sk > 1) else _new_empty(g, n, pl.d_in)
     _, bx, _ = pl.tables(g.device)
+    if bx is not None and n > 0 and pl._bwd_x_c and name.endswith("_tc") and COMPONENT_COPIES[0]:
+        # cotangent stored in the e3nn order / channel layout: reduce over a component-major copy of it
+        cmap, bx_c = pl.tables_c(g.device)[1]
+        gc = _new_empty(g, n, pl.d_out)
+        _call("pml_permute_columns", _p(g), pl.d_out, _p(cmap), _p(gc), pl.d_out, n, _stream())
+        _gemm(name, _p(gc), _p(w), _p(dx), _p(bx_c), len(pl._bwd_x_c), n, n, pl.max_mul_in, pl.max_d, sk,
+              (pl.max_k_bwd_x + sk - 1) // sk + 16 if sk > 1 else pl.max_k_bwd_x)
+        return dx
     if bx is not None and n > 0:
         _gemm(name, _p(g), _p(w), _p(dx), _p(bx), len(pl._bwd_x), n, n, pl.max_mul_in, pl.max_d, sk,
               (pl.max_k_bwd_x + sk - 1) // sk + 16 if sk > 1 else pl.max_k_bwd_x)

@@ -187,8 +187,67 @@ class LinearPlan:
             p.M, p.N, p.nbatch, p.alpha, p.accumulate = mi, mo, d, self.alpha[o], 0
             bw.append(p)
         self._bwd_w = bw
+        # ---- component-major operand copies (ops.irrep_linear / irrep_linear_bwd_x on node- or edge-sized inputs): the
+        # reduction index u (forward) / w (cotangent) has stride (2l+1) in the e3nn order and S in the channel layout —
+        # one 32-byte sector per element for the GEMM's operand loads.  `colmap_in` / `colmap_out` re-order a row to
+        # m*mul + u inside every block (pml_permute_columns, a few microseconds) and `_fwd_c` / `_bwd_x_c` are the same
+        # problems addressed in that copy.
+        import copy as _copy
+
+        self.in_strided = (not mmaj) and any(l > 0 and m_ >= 16 for m_, l, _ in self.irreps_in)
+        self.out_strided = any((cs != 1) and self.irreps_out[o][0] >= 16 for o, cs in enumerate(o_cs))
+        oc_off = so3.irreps_offsets(self.irreps_out)
+        cm_in = np.zeros(self.d_in, dtype=np.int32)
+        for i, (mi, li, _) in enumerate(self.irreps_in):
+            d = 2 * li + 1
+            for m_ in range(d):
+                for u in range(mi):
+                    cm_in[in_off[i] + m_ * mi + u] = in_off[i] + u * d + m_
+        cm_out = np.zeros(self.d_out, dtype=np.int32)
+        for o, (mo, lo, _) in enumerate(self.irreps_out):
+            d = 2 * lo + 1
+            for m_ in range(d):
+                for w in range(mo):
+                    cm_out[oc_off[o] + m_ * mo + w] = o_off[o] + w * o_cs[o] + m_
+        self._colmap_in, self._colmap_out = cm_in, cm_out
+        self._fwd_c = None
+        if self.in_strided and not self.fwd_serial:
+            self._fwd_c = []
+            for p0 in fwd:
+                p = _copy.copy(p0)
+                muls_in = {int(p.kc[c]) for c in range(p.nchunks)}
+                if len(muls_in) != 1:
+                    self._fwd_c = None
+                    break
+                p.a_cs, p.a_bs = 1, muls_in.pop()
+                self._fwd_c.append(p)
+        self._bwd_x_c = None
+        if self.out_strided:
+            self._bwd_x_c = []
+            for p0 in bx:
+                p = _copy.copy(p0)
+                mo = int(p.kc[0])
+                for c in range(p.nchunks):  # chunk c = output block o fed by this input block: find it by its offset
+                    o = o_off.index(int(p.a_off[c]))
+                    p.a_off[c] = oc_off[o]
+                p.a_cs, p.a_bs = 1, mo
+                self._bwd_x_c.append(p)
         self._dev: dict = {}
+        self._dev_c: dict = {}
         self.handle = register(self)
+
+    def tables_c(self, device):
+        """(colmap_in, fwd table on the component-major x) , (colmap_out, dx table on the component-major g); None where the
+        operand already has unit stride"""
+        key = str(device)
+        if key not in self._dev_c:
+            def up(lst):
+                return None if not lst else _upload((_lib.GemmProblem * len(lst))(*lst), device)
+
+            f = (torch.tensor(self._colmap_in, device=device), up(self._fwd_c)) if self._fwd_c else None
+            b = (torch.tensor(self._colmap_out, device=device), up(self._bwd_x_c)) if self._bwd_x_c else None
+            self._dev_c[key] = (f, b)
+        return self._dev_c[key]
 
     def tables(self, device):
         key = str(device)
