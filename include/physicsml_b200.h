@@ -129,11 +129,6 @@ int pml_gemm_grouped(const float* A, const float* B, float* C, const pml_gemm_pr
  * registers every 128 k, because the tensor core truncates its running sum at every MMA. */
 int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                         int max_M, int max_N, int max_batch, int splitk, int max_k, pml_stream_t stream);
-/* Same kernel compiled for operands whose ROW index is the contiguous one (weight gradients dW[u,w] = sum_n x[n,u] g[n,w]:
- * A[u, k=n] with a_rs == 1, B[k=n, w] with b_cs == 1): 16-byte loads along the rows, four lanes per k-unit.  Accepts any
- * strides; identical results. */
-int pml_gemm_grouped_tc_mn(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
-                           int max_M, int max_N, int max_batch, int splitk, int max_k, pml_stream_t stream);
 
 /* ---- K3w: streaming kernels for the wide output layer of the radial MLP (reference blocks.py:157-160,211,
  * interaction_block.py:61-64,85: the last nn.FullyConnectedNet layer, hidden 64 -> paths x channels).

@@ -109,7 +109,6 @@ SIGNATURES = {
     "pml_sym_dbl": [_I, _P, _P, _P, C.POINTER(SymWeights), _P, _P, _P, _I, _I, _I, _P],
     "pml_gemm_grouped": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pml_gemm_grouped_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "pml_gemm_grouped_tc_mn": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pml_wide_pack_w": [_P, _LL, _LL, _I, _I, _P, _P],
     "pml_wide_fwd": [_P, _LL, _I, _P, _P, _LL, _I, _I, _F, _P],
     "pml_wide_pack_wt": [_P, _LL, _LL, _I, _I, _P, _P],

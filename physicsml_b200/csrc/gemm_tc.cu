@@ -110,50 +110,15 @@ __device__ __forceinline__ void tile_coords(int idx, bool kfast, int& r, int& kc
   }
 }
 
-// Operand access modes of a [ROWS x 16 k] tile whose element (row, k) sits at base + row*rs + k*cs:
-//   kTileK (cs == 1)  : k is the contiguous index  -> one 16-byte load = 4 k of one row = one unit of the UMMA layout
-//   kTileM (rs == 1)  : the ROW is the contiguous index (weight gradients: A[u, k = node] = x[node, u], B[k = node, w] =
-//                       g[node, w]) -> one 16-byte load = 4 consecutive rows at one k; four lanes of a quad take the 4 k
-//                       of a unit, a warp reads 4 k-rows x 128 contiguous bytes.  (Read element by element these
-//                       operands cost one 32-byte sector per value: the 64 -> 4352 radial weight gradient of config 5
-//                       ran at 0.95 TB/s.)
-//   kTileS            : neither: scalar loads
-enum { kTileS = 0, kTileK = 1, kTileM = 2 };
-
 template <int ROWS>
-__device__ __forceinline__ void tile_coords_m(int idx, int& r4, int& kc, int& t) {
-  t = idx & 3;                       // k inside the unit
-  const int g = idx >> 2;            // (row group, k-unit): consecutive quads = consecutive row groups
-  r4 = g % (ROWS / 4);
-  kc = g / (ROWS / 4);
-}
-
-template <int ROWS, bool MN>
 __device__ __forceinline__ void fetch_tile(const float* __restrict__ base, long long rs, long long cs, int row0, int nrows,
-                                           int k0, int K, bool vec_ok, int mode, TileRegs<ROWS>& t) {
-  const bool kfast = !MN && mode == kTileK;
+                                           int k0, int K, bool vec_ok, TileRegs<ROWS>& t) {
+  const bool kfast = (cs == 1);
 #pragma unroll
   for (int it = 0; it < TileRegs<ROWS>::PER_THREAD; ++it) {
     const int idx = threadIdx.x + it * TC_THREADS;
     t.v[it][0] = t.v[it][1] = t.v[it][2] = t.v[it][3] = 0.f;
     if (TileRegs<ROWS>::UNITS % TC_THREADS != 0 && idx >= TileRegs<ROWS>::UNITS) continue;
-    if (MN && mode == kTileM) {
-      int r4, kc, tt;
-      tile_coords_m<ROWS>(idx, r4, kc, tt);
-      const int gr = row0 + 4 * r4, gk = k0 + 4 * kc + tt;
-      if (gk < K && gr < nrows) {
-        const float* p = base + (long long)gr + (long long)gk * cs;
-        if (vec_ok && gr + 3 < nrows) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-          t.v[it][0] = q.x; t.v[it][1] = q.y; t.v[it][2] = q.z; t.v[it][3] = q.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (gr + j < nrows) t.v[it][j] = __ldg(p + j);
-        }
-      }
-      continue;
-    }
     int r, kc;
     tile_coords<ROWS>(idx, kfast, r, kc);
     const int gr = row0 + r, gk = k0 + kc * 4;
@@ -171,28 +136,13 @@ __device__ __forceinline__ void fetch_tile(const float* __restrict__ base, long 
   }
 }
 
-template <int ROWS, bool MN>
-__device__ __forceinline__ void commit_tile(const TileRegs<ROWS>& t, int mode, float scale, float* __restrict__ s_hi,
+template <int ROWS>
+__device__ __forceinline__ void commit_tile(const TileRegs<ROWS>& t, bool kfast, float scale, float* __restrict__ s_hi,
                                             float* __restrict__ s_lo) {
-  const bool kfast = !MN && mode == kTileK;
 #pragma unroll
   for (int it = 0; it < TileRegs<ROWS>::PER_THREAD; ++it) {
     const int idx = threadIdx.x + it * TC_THREADS;
     if (TileRegs<ROWS>::UNITS % TC_THREADS != 0 && idx >= TileRegs<ROWS>::UNITS) continue;
-    if (MN && mode == kTileM) {  // registers hold 4 ROWS at one k: four scalar stores into the K-major units of those rows
-      int r4, kc, tt;
-      tile_coords_m<ROWS>(idx, r4, kc, tt);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = 4 * r4 + j;
-        float hi, lo;
-        split_tf32(t.v[it][j] * scale, hi, lo);
-        const int word = 4 * ((r & 7) + 8 * kc + 32 * (r >> 3)) + tt;
-        s_hi[word] = hi;
-        s_lo[word] = lo;
-      }
-      continue;
-    }
     int r, kc;
     tile_coords<ROWS>(idx, kfast, r, kc);
     float4 hi, lo;
@@ -236,10 +186,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
   }
 }
 
-// MN: the row-contiguous access mode is compiled in (weight-gradient launches); the K-contiguous mode is compiled in
-// otherwise.  Two instantiations instead of one kernel with both: the extra mode costs 45 registers, which would take
-// the BN <= 64 variants from three CTAs per SM to two.
-template <int BN, bool PROMOTE, bool MN>
+template <int BN, bool PROMOTE>
 __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                      float* __restrict__ C,
                                                                      const pml_gemm_problem* __restrict__ probs,
@@ -271,13 +218,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   const long long a_rs = P.a_rs, a_cs = P.a_cs, b_rs = P.b_rs, b_cs = P.b_cs;
   const int nchunks = P.nchunks;
   const long long a_boff = (long long)zb * P.a_bs, b_boff = (long long)zb * P.b_bs;
-  // operand access mode (see fetch_tile): K-contiguous, row-contiguous (M for A, N for B: weight gradients), or scalar
-  const int a_mode = MN ? (a_rs == 1 ? kTileM : kTileS) : (a_cs == 1 ? kTileK : kTileS);
-  const int b_mode = MN ? (b_cs == 1 ? kTileM : kTileS) : (b_rs == 1 ? kTileK : kTileS);
-  const bool a_vec_base = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
-                          (a_mode == kTileK ? ((a_rs & 3) == 0) : (a_mode == kTileM && (a_cs & 3) == 0));
-  const bool b_vec_base = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) &&
-                          (b_mode == kTileK ? ((b_cs & 3) == 0) : (b_mode == kTileM && (b_rs & 3) == 0));
+  const bool a_kfast = a_cs == 1, b_kfast = b_rs == 1;
+  const bool a_vec_base = a_kfast && ((a_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool b_vec_base = b_kfast && ((b_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 
   constexpr int NBUF = PROMOTE ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (NBUF * BN) < 32 ? 32 : (NBUF * BN);
@@ -326,9 +269,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
     const long long aoff = P.a_off[q.ch] + a_boff;
     const long long boff = P.b_off[q.ch] + b_boff;
     const int K = chunk_k(q.ch);
-    fetch_tile<TC_BM, MN>(A + aoff, a_rs, a_cs, row0, M, q.k0, K, a_vec_base && ((aoff & 3) == 0), a_mode, ra);
+    fetch_tile<TC_BM>(A + aoff, a_rs, a_cs, row0, M, q.k0, K, a_vec_base && ((aoff & 3) == 0), ra);
     // B operand as an [N x K] K-major tile: element (n, k) = B[k*b_rs + n*b_cs]
-    fetch_tile<BN, MN>(B + boff, b_cs, b_rs, col0, N, q.k0, K, b_vec_base && ((boff & 3) == 0), b_mode, rb);
+    fetch_tile<BN>(B + boff, b_cs, b_rs, col0, N, q.k0, K, b_vec_base && ((boff & 3) == 0), rb);
   };
 
   // this thread's slice of the output tile: TMEM lane quadrant q (rows 32q + lane), column half `half`
@@ -370,12 +313,12 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
     if (it >= TC_STAGES) mbar_wait(smem_u32(&S.bar[s]), ((it / TC_STAGES) - 1) & 1);  // MMAs that read stage s retired
     const int rsel = it & 1;
     if (rsel == 0) {
-      commit_tile<TC_BM, MN>(ra[0], a_mode, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
-      commit_tile<BN, MN>(rb[0], b_mode, 1.f, S.b[s][0], S.b[s][1]);
+      commit_tile<TC_BM>(ra[0], a_kfast, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
+      commit_tile<BN>(rb[0], b_kfast, 1.f, S.b[s][0], S.b[s][1]);
       if (pos[2].ch < nchunks) fetch(pos[2], ra[0], rb[0]);
     } else {
-      commit_tile<TC_BM, MN>(ra[1], a_mode, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
-      commit_tile<BN, MN>(rb[1], b_mode, 1.f, S.b[s][0], S.b[s][1]);
+      commit_tile<TC_BM>(ra[1], a_kfast, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
+      commit_tile<BN>(rb[1], b_kfast, 1.f, S.b[s][0], S.b[s][1]);
       if (pos[2].ch < nchunks) fetch(pos[2], ra[1], rb[1]);
     }
     if (PROMOTE && to_promote >= 0) {  // the period closed one k-block ago: its MMAs have had an iteration to retire
@@ -516,7 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   }
 }
 
-template <int BN, bool PROMOTE, bool MN>
+template <int BN, bool PROMOTE>
 static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                      int max_M, int max_N, int max_batch, int splitk, cudaStream_t stream) {
   const int tiles_m = (max_M + TC_BM - 1) / TC_BM, tiles_n = (max_N + BN - 1) / BN;
@@ -526,12 +469,12 @@ static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_pr
   static bool configured[kMaxDevices] = {};
   const int slot = device_slot();
   if (!configured[slot]) {
-    if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN, PROMOTE, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return PML_ERR_LAUNCH;
     configured[slot] = true;
   }
   dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)nprobs, (unsigned)gz);
-  gemm_grouped_tc_kernel<BN, PROMOTE, MN><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
+  gemm_grouped_tc_kernel<BN, PROMOTE><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
   return PML_OK;
 }
 
@@ -541,38 +484,22 @@ static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_pr
 // Same contract as pml_gemm_grouped (gemm.cu) plus max_k: an upper bound of the reduction length one CTA sees (sum of
 // the chunk extents of a problem, divided by splitk); <= 0 means unknown.  Reductions longer than 128 run the kernel
 // variant that promotes the TMEM accumulators into registers every 128 k (see kPromoBlocks).
-template <bool MN>
-static int gemm_grouped_tc_entry(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
-                                 int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k,
-                                 cudaStream_t stream) {
+extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
+                                   int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k,
+                                   cudaStream_t stream) {
   if (nprobs <= 0 || max_M <= 0 || max_N <= 0 || max_batch <= 0) return PML_OK;
   if (splitk < 1) splitk = 1;
   const bool promote = max_k <= 0 || max_k > pml::kPromoBlocks * pml::TC_BK;
   int rc;
   if (promote) {
-    if (max_N <= 32) rc = pml::launch_tc<32, true, MN>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
-    else rc = pml::launch_tc<64, true, MN>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    if (max_N <= 32) rc = pml::launch_tc<32, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    else rc = pml::launch_tc<64, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
   } else {
-    if (max_N <= 32) rc = pml::launch_tc<32, false, MN>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
-    else if (max_N <= 64) rc = pml::launch_tc<64, false, MN>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
-    else rc = pml::launch_tc<128, false, MN>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    if (max_N <= 32) rc = pml::launch_tc<32, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    else if (max_N <= 64) rc = pml::launch_tc<64, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
+    else rc = pml::launch_tc<128, false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
   }
   if (rc != PML_OK) return rc;
   PML_CHECK_LAUNCH();
   return PML_OK;
-}
-
-extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
-                                   int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k,
-                                   cudaStream_t stream) {
-  return gemm_grouped_tc_entry<false>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, max_k, stream);
-}
-
-// The same kernel compiled for operands whose ROW index is the contiguous one (a_rs == 1 / b_cs == 1): weight gradients
-// dW[u, w] = sum_n x[n, u] g[n, w] of scalar layers and of component-major operands.  Any strides are accepted (the
-// scalar path covers the rest); results are identical to pml_gemm_grouped_tc.
-extern "C" int pml_gemm_grouped_tc_mn(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
-                                      int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k,
-                                      cudaStream_t stream) {
-  return gemm_grouped_tc_entry<true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, max_k, stream);
 }

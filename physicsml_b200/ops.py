@@ -486,7 +486,7 @@ def _gemm_name(n_runtime: int) -> str:
 
 def _gemm(name: str, a, b, c, table, nprob: int, m_runtime: int, max_m: int, max_n: int, max_batch: int, splitk: int,
           max_k: int) -> None:
-    if name.endswith("_tc") or name.endswith("_tc_mn"):
+    if name.endswith("_tc"):
         _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, max_k, _stream())
     else:
         _call(name, a, b, c, table, nprob, m_runtime, max_m, max_n, max_batch, splitk, _stream())
@@ -662,40 +662,18 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
     _, _, bw = pl.tables(x.device)
     if bw is not None and n > 0:
         name = _gemm_name(n)
-        A, B = x, g
-        mn = False
-        if name.endswith("_tc") and COMPONENT_COPIES[0]:
-            if pl.bwd_w_mn_direct:  # scalar layers (radial MLP): x[n, u] and g[n, w] are row-contiguous as they are
-                name, mn = "pml_gemm_grouped_tc_mn", True
-            elif pl.max_mul_in >= 16 and pl.max_mul_out >= 16:
-                # both operands through component-major copies: row-contiguous A[u, k = n] and B[k = n, w]
-                cin, cout, bw_c = pl.tables_c(x.device)[2]
-                if pl.in_layout == "component":
-                    A = x
-                else:
-                    A = _new_empty(x, n, pl.d_in)
-                    _call("pml_permute_columns", _p(x), pl.d_in, _p(cin), _p(A), pl.d_in, n, _stream())
-                g2 = g.reshape(n, -1)
-                if pl.out_strided:
-                    B = _new_empty(g, n, pl.d_out)
-                    _call("pml_permute_columns", _p(g2), pl.d_out, _p(cout), _p(B), pl.d_out, n, _stream())
-                else:
-                    B = g2
-                bw, name, mn = bw_c, "pml_gemm_grouped_tc_mn", True
-        if name.endswith("_tc") or mn:
+        if name.endswith("_tc"):
             bn = 32 if pl.max_mul_out <= 32 else (64 if pl.max_mul_out <= 64 else 128)
             ctas = ((pl.max_mul_in + 127) // 128) * ((pl.max_mul_out + bn - 1) // bn) * len(pl._bwd_w) * pl.max_d
-            per = 2 * _sms() if mn else _tc_slots(bn, False)  # the row-contiguous variants hold 125 registers: 2 CTAs per SM
-            slots = 2 * per if bn >= 128 else per
         else:
             ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
-            slots = 4 * _sms()
-        sk = _splitk_for(n, ctas, slots)
+        sk = _splitk_for(n, ctas, 2 * _tc_slots(bn, False) if name.endswith("_tc") and bn >= 128 else
+                         (_tc_slots(bn, False) if name.endswith("_tc") else 4 * _sms()))
         k_cta = (n + sk - 1) // sk + 16
         # Weight gradients are sums over nodes / edges whose fp32 evaluation order already carries ~sqrt(n) eps; up to
         # 1024 terms per CTA they run on the plain TMEM accumulator (worst-case truncation bias 2e-5 relative, measured
         # < 1e-6 on random data) instead of the promoting variant, which is 1.5x slower on these shapes.
-        _gemm(name, _p(A), _p(B), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d, sk,
+        _gemm(name, _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d, sk,
               min(k_cta, 128) if k_cta <= 1024 else k_cta)
     return dw
 

@@ -232,17 +232,6 @@ class LinearPlan:
                     p.a_off[c] = oc_off[o]
                 p.a_cs, p.a_bs = 1, mo
                 self._bwd_x_c.append(p)
-        # weight gradients on component-major copies of BOTH operands: A[u, k = n] = xc[n, in_off + m*mi + u] and
-        # B[k = n, w] = gc[n, oc_off + m*mo + w] are row-contiguous -> pml_gemm_grouped_tc_mn reads them with 16-byte loads
-        self._bwd_w_c = []
-        for p0, (i, o, w_) in zip(bw, paths):
-            p = _copy.copy(p0)
-            mi, mo = self.irreps_in[i][0], self.irreps_out[o][0]
-            p.a_off[0], p.a_rs, p.a_cs, p.a_bs = in_off[i], 1, self.d_in, mi
-            p.b_off[0], p.b_rs, p.b_cs, p.b_bs = oc_off[o], self.d_out, 1, mo
-            self._bwd_w_c.append(p)
-        # are the operands row-contiguous as they are (scalar layers such as the radial MLP; component-major inputs)?
-        self.bwd_w_mn_direct = all(p.a_rs == 1 and p.b_cs == 1 for p in bw) if bw else False
         self._dev: dict = {}
         self._dev_c: dict = {}
         self.handle = register(self)
@@ -255,10 +244,9 @@ class LinearPlan:
             def up(lst):
                 return None if not lst else _upload((_lib.GemmProblem * len(lst))(*lst), device)
 
-            cin, cout = torch.tensor(self._colmap_in, device=device), torch.tensor(self._colmap_out, device=device)
-            f = (cin, up(self._fwd_c)) if self._fwd_c else None
-            b = (cout, up(self._bwd_x_c)) if self._bwd_x_c else None
-            self._dev_c[key] = (f, b, (cin, cout, up(self._bwd_w_c)))
+            f = (torch.tensor(self._colmap_in, device=device), up(self._fwd_c)) if self._fwd_c else None
+            b = (torch.tensor(self._colmap_out, device=device), up(self._bwd_x_c)) if self._bwd_x_c else None
+            self._dev_c[key] = (f, b)
         return self._dev_c[key]
 
     def tables(self, device):
