@@ -538,6 +538,9 @@ def _splitk_rows(tiles: int, k_extent: int, slots: int) -> int:
 # PML_COMPONENT_COPIES=0: let the tensor-core GEMM read e3nn-ordered operands in place (strided reduction index; A/B runs)
 COMPONENT_COPIES = [os.environ.get("PML_COMPONENT_COPIES", "1") == "1"]
 
+# PML_TRANSPOSED_DW=0: compute the weight gradient of few-in / many-out layers as dW instead of dW^T (A/B runs)
+TRANSPOSED_DW = [os.environ.get("PML_TRANSPOSED_DW", "1") == "1"]
+
 WIDE_MIN_ROWS = [int(os.environ.get("PML_WIDE_MIN_ROWS", "4096"))]
 
 
@@ -662,18 +665,29 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
     _, _, bw = pl.tables(x.device)
     if bw is not None and n > 0:
         name = _gemm_name(n)
+        A, B, max_m, max_n = x, g, pl.max_mul_in, pl.max_mul_out
+        if name.endswith("_tc") and pl._bwd_w_t and TRANSPOSED_DW[0]:
+            # few inputs -> many outputs (radial output layer): dW^T = g^T x, the wide dimension on the 128-row tile
+            bw, A, B, max_m, max_n = pl.table_bwd_w_t(x.device), g, x, pl.max_mul_out, pl.max_mul_in
         if name.endswith("_tc"):
-            bn = 32 if pl.max_mul_out <= 32 else (64 if pl.max_mul_out <= 64 else 128)
-            ctas = ((pl.max_mul_in + 127) // 128) * ((pl.max_mul_out + bn - 1) // bn) * len(pl._bwd_w) * pl.max_d
+            bn = 32 if max_n <= 32 else (64 if max_n <= 64 else 128)
+            ctas = ((max_m + 127) // 128) * ((max_n + bn - 1) // bn) * len(pl._bwd_w) * pl.max_d
         else:
-            ctas = ((pl.max_mul_in + 63) // 64) * ((pl.max_mul_out + 63) // 64) * len(pl._bwd_w) * pl.max_d
+            ctas = ((max_m + 63) // 64) * ((max_n + 63) // 64) * len(pl._bwd_w) * pl.max_d
         sk = _splitk_for(n, ctas, 2 * _tc_slots(bn, False) if name.endswith("_tc") and bn >= 128 else
                          (_tc_slots(bn, False) if name.endswith("_tc") else 4 * _sms()))
         k_cta = (n + sk - 1) // sk + 16
+        if name.endswith("_tc") and k_cta > 1024:
+            # long reductions run the accumulator-promoting kernel (BN <= 64, 126 registers: two CTAs per SM): size the
+            # split for ITS tiles and slots, rounding down so that the grid is one full wave instead of one and a bit
+            bn_p = 32 if max_n <= 32 else 64
+            ctas_p = ((max_m + 127) // 128) * ((max_n + bn_p - 1) // bn_p) * len(pl._bwd_w) * pl.max_d
+            sk = max(1, (2 * _sms()) // max(1, ctas_p))
+            k_cta = (n + sk - 1) // sk + 16
         # Weight gradients are sums over nodes / edges whose fp32 evaluation order already carries ~sqrt(n) eps; up to
         # 1024 terms per CTA they run on the plain TMEM accumulator (worst-case truncation bias 2e-5 relative, measured
         # < 1e-6 on random data) instead of the promoting variant, which is 1.5x slower on these shapes.
-        _gemm(name, _p(x), _p(g), _p(dw), _p(bw), len(pl._bwd_w), n, pl.max_mul_in, pl.max_mul_out, pl.max_d, sk,
+        _gemm(name, _p(A), _p(B), _p(dw), _p(bw), len(pl._bwd_w), n, max_m, max_n, pl.max_d, sk,
               min(k_cta, 128) if k_cta <= 1024 else k_cta)
     return dw
 

@@ -187,6 +187,25 @@ class LinearPlan:
             p.M, p.N, p.nbatch, p.alpha, p.accumulate = mi, mo, d, self.alpha[o], 0
             bw.append(p)
         self._bwd_w = bw
+        # ---- weight gradients of "few inputs -> many outputs" layers (the radial MLP's output layer: 64 -> P*C): computed
+        # TRANSPOSED, dW^T[w, u] = sum_n g[n, w] x[n, u], so that the wide dimension fills the 128-row MMA tile and the narrow
+        # one the 32/64-column tile.  As dW[u, w] a 64-row A tile is padded to 128 rows whose staging costs the same
+        # instructions as real rows: half the k-blocks for the same work (config 5, 64 -> 4352: 68 column tiles x 4304
+        # k-blocks -> 34 x 4304).  ops.irrep_linear_bwd_w passes (g, x) as (A, B) for these tables.
+        self._bwd_w_t = None
+        if bw and all(self.irreps_in[i][0] <= 64 and self.irreps_out[o][0] >= 2 * self.irreps_in[i][0] for i, o, _ in paths):
+            self._bwd_w_t = []
+            for p0, (i, o, w_) in zip(bw, paths):
+                mi, mo = self.irreps_in[i][0], self.irreps_out[o][0]
+                p = prob()
+                p.nchunks = 1
+                p.a_off[0], p.b_off[0], p.kc[0] = p0.b_off[0], p0.a_off[0], -1
+                p.c_off = w_
+                p.a_rs, p.a_cs, p.a_bs = p0.b_cs, p0.b_rs, p0.b_bs  # A'[w, k = n] = g[n, o_off + w cs + m]
+                p.b_rs, p.b_cs, p.b_bs = p0.a_cs, p0.a_rs, p0.a_bs  # B'[k = n, u] = x[n, in_off + u d + m]
+                p.c_rs, p.c_cs, p.c_bs = 1, mo, 0                   # C'[w, u] = dW[u, w]
+                p.M, p.N, p.nbatch, p.alpha, p.accumulate = mo, mi, p0.nbatch, p0.alpha, 0
+                self._bwd_w_t.append(p)
         # ---- component-major operand copies (ops.irrep_linear / irrep_linear_bwd_x on node- or edge-sized inputs): the
         # reduction index u (forward) / w (cotangent) has stride (2l+1) in the e3nn order and S in the channel layout —
         # one 32-byte sector per element for the GEMM's operand loads.  `colmap_in` / `colmap_out` re-order a row to
@@ -258,7 +277,12 @@ class LinearPlan:
                 return _upload((_lib.GemmProblem * len(lst))(*lst), device)
 
             self._dev[key] = (up(self._fwd), up(self._bwd_x), up(self._bwd_w))
+            self._dev[key + ":t"] = up(self._bwd_w_t) if self._bwd_w_t else None
         return self._dev[key]
+
+    def table_bwd_w_t(self, device):
+        self.tables(device)
+        return self._dev[str(device) + ":t"]
 
 
 class ElementLinearPlan:
