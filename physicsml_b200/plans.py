@@ -193,7 +193,7 @@ class LinearPlan:
         # instructions as real rows: half the k-blocks for the same work (config 5, 64 -> 4352: 68 column tiles x 4304
         # k-blocks -> 34 x 4304).  ops.irrep_linear_bwd_w passes (g, x) as (A, B) for these tables.
         self._bwd_w_t = None
-        if bw and all(self.irreps_in[i][0] <= 64 and self.irreps_out[o][0] >= 2 * self.irreps_in[i][0] for i, o, _ in paths):
+        if bw and all(self.irreps_in[i][0] <= 64 and self.irreps_out[o][0] >= 128 for i, o, _ in paths):
             self._bwd_w_t = []
             for p0, (i, o, w_) in zip(bw, paths):
                 mi, mo = self.irreps_in[i][0], self.irreps_out[o][0]
