@@ -678,11 +678,22 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
                          (_tc_slots(bn, False) if name.endswith("_tc") else 4 * _sms()))
         k_cta = (n + sk - 1) // sk + 16
         if name.endswith("_tc") and k_cta > 1024:
-            # long reductions run the accumulator-promoting kernel (BN <= 64, 126 registers: two CTAs per SM): size the
-            # split for ITS tiles and slots, rounding down so that the grid is one full wave instead of one and a bit
+            # Long reductions would run the accumulator-promoting kernel (BN <= 64, 126 registers: two CTAs per SM).  Two
+            # candidates, costed in k-blocks (1.3 us promoting, 1.1 us plain) x rounds of resident CTAs, counting only the
+            # (problem, batch) pairs that exist: (a) promoting, split sized for ITS tiles and slots, rounded down to
+            # whole waves; (b) enough splits to keep every CTA's reduction <= 1008 terms on the plain kernel (config 5,
+            # the 17-block weight gradient of `linear` over 1728 nodes: 331 us promoting, one split -> two plain splits).
+            tm, nb = (max_m + 127) // 128, pl.bwd_w_batches
             bn_p = 32 if max_n <= 32 else 64
-            ctas_p = ((max_m + 127) // 128) * ((max_n + bn_p - 1) // bn_p) * len(pl._bwd_w) * pl.max_d
-            sk = max(1, (2 * _sms()) // max(1, ctas_p))
+            ctas_p = tm * ((max_n + bn_p - 1) // bn_p) * nb
+            sk_p = max(1, (2 * _sms()) // max(1, ctas_p))
+            atom = lambda ctas_, bn_: ctas_ * 128.0 * bn_ / 2.0e5  # split-K epilogue: ~2e5 fp32 atomics per microsecond
+            cost_p = -(-ctas_p * sk_p // (2 * _sms())) * ((n / sk_p) / 16.0 * 1.3 + 8.0) + atom(ctas_p * sk_p, bn_p)
+            sk_n = -(-n // 1008)
+            ctas_n = tm * ((max_n + bn - 1) // bn) * nb
+            slots_n = _tc_slots(bn, False)
+            cost_n = -(-ctas_n * sk_n // slots_n) * ((n / sk_n) / 16.0 * 1.1 + 8.0) + atom(ctas_n * sk_n, bn)
+            sk = sk_n if cost_n < cost_p else sk_p
             k_cta = (n + sk - 1) // sk + 16
         # Weight gradients are sums over nodes / edges whose fp32 evaluation order already carries ~sqrt(n) eps; up to
         # 1024 terms per CTA they run on the plain TMEM accumulator (worst-case truncation bias 2e-5 relative, measured

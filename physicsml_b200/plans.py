@@ -187,6 +187,7 @@ class LinearPlan:
             p.M, p.N, p.nbatch, p.alpha, p.accumulate = mi, mo, d, self.alpha[o], 0
             bw.append(p)
         self._bwd_w = bw
+        self.bwd_w_batches = sum(int(p.nbatch) for p in bw)  # (problem, batch) pairs that exist (the grid has max_d per problem)
         # ---- weight gradients of "few inputs -> many outputs" layers (the radial MLP's output layer: 64 -> P*C): computed
         # TRANSPOSED, dW^T[w, u] = sum_n g[n, w] x[n, u], so that the wide dimension fills the 128-row MMA tile and the narrow
         # one the 32/64-column tile.  As dW[u, w] a 64-row A tile is padded to 128 rows whose staging costs the same
