@@ -150,6 +150,46 @@ def cpu_reference_step_rate(n_mol, steps: int, warmup: int, budget_s: float | No
     return n_atoms / per, cores, sample, per * 1e3, kind
 
 
+def gpu_eager_step_rate(dev, steps: int = 5, warmup: int = 2) -> dict:
+    """the headline training step with the reference's own modules (or the oracle port) moved to the GPU: stock PyTorch
+    kernels, stock autograd (create_graph for the forces), torch.optim.Adam.  None of this repo's kernels on the path."""
+    import torch
+
+    from physicsml_b200 import workloads as wl
+
+    data, targets, _, _ = wl.make_batch(WORKLOAD, 0)
+    model, kind = _cpu_model(WORKLOAD)
+    model = model.to(dev)
+    d = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in data.items()}
+    t = {k: v.to(dev) for k, v in targets.items()}
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad and p.numel() > 0], lr=1e-2, amsgrad=True)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        dd = dict(d)
+        pos = dd["coordinates"].detach().requires_grad_(True)
+        dd["coordinates"] = pos
+        e = model(dd)["y_graph_scalars"]
+        (g,) = torch.autograd.grad([e], [pos], grad_outputs=[torch.ones_like(e)], retain_graph=True, create_graph=True)
+        loss = torch.nn.functional.mse_loss(e, t["energy"]) + torch.nn.functional.mse_loss(-g, t["forces"])
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = int(d["coordinates"].shape[0])
+    return {"value": n / (ms * 1e-3), "unit": "atoms/s", "ms_per_step": ms, "kind": kind + " modules, eager PyTorch on the same GPU",
+            "steps": steps}
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -439,9 +479,39 @@ def main() -> None:
         if nl_ms is not None:
             res["neighbour_list_ms"] = nl_ms
             res["atoms_per_s_with_neighbour_list"] = total_atoms / ((ms_dev + nl_ms) * 1e-3)
+            res["md_loop"] = md_loop_rate(model, cfg, data, dev, steps)
         if headline and rank == 0 and not args.no_cpu_baseline and world == 1:
             res["parity"] = parity_vs_oracle(name, model, data, targets, dev)
         return res
+
+    def md_loop_rate(model, cfg, data, dev, steps):
+        """the consumer of this config: an MD-style loop through md.MDCalculator — host coordinates in, energy
+        and forces back on the host EVERY step, atoms moving ~0.03 A per step, the Verlet-skin neighbour list rebuilt when
+        needed (the reference rebuilds it on every step: plugins/openmm/openmm_graph.py:148-156)"""
+        from physicsml_b200.md import MDCalculator
+
+        md = MDCalculator(model, cfg["model"]["cut_off"], data["node_attrs"], cell=data["cell"], skin=0.5)
+        n = int(data["coordinates"].shape[0])
+        gen = torch.Generator().manual_seed(5)
+        pos = data["coordinates"].clone()
+        host_pos = torch.empty(n, 3).pin_memory()
+        f_host = torch.empty(n, 3).pin_memory()
+        e_host = torch.empty(1).pin_memory()
+        times = []
+        for i in range(steps + 3):
+            pos = pos + 0.017 * torch.randn(n, 3, generator=gen)  # |dr| ~ 0.03 A per step
+            host_pos.copy_(pos)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e, f = md.energy_forces(host_pos)
+            e_host.copy_(e, non_blocking=True)
+            f_host.copy_(f, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if i >= 3:
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * sum(times) / len(times)
+        return {"ms_per_step": ms, "atoms_per_s": n / (ms * 1e-3), "steps": len(times), "neighbour_list_builds": md.n_builds,
+                "skin_A": 0.5, "edges_in_list": md.n_edges, "timing": "host wall clock per step, coordinates from / results to pinned host memory"}
 
     def parity_vs_oracle(name, model, data, targets, dev):
         """step-0 check inside the benchmark run: the GPU model vs the CPU oracle (same weights) on the first
@@ -526,6 +596,15 @@ def main() -> None:
         rate, cores, sample, _, kind = cpu_reference_step_rate(args.cpu_baseline_molecules, 2, 1)
         cpu = {"value": rate, "unit": "atoms/s", "cores": cores, "kind": kind, "sample": sample}
 
+    # informational: the same training step in plain eager PyTorch ON THE SAME GPU (the reference's own modules over the
+    # e3nn shims, stock autograd, torch.optim.Adam) — what a user of the reference gets by calling .cuda() today
+    gpu_eager = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            gpu_eager = gpu_eager_step_rate(dev)
+        except Exception as exc:
+            gpu_eager = {"error": f"{type(exc).__name__}: {exc}"}
+
     config = shared_config(world)
     line = {
         "metric": METRIC, "value": head["atoms_per_s"], "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
@@ -538,6 +617,7 @@ def main() -> None:
         "gpu_launches": head["gpu_launches"] * args.steps, "gpu_launches_per_step": head["gpu_launches"],
         "cuda_graph": head["cuda_graph"], "clocks": head.get("clocks"), "roofline": roof, "cpu_baseline": cpu,
         "parity": head.get("parity"), "per_rank": head.get("per_rank"), "allreduce": head.get("allreduce"),
+        "gpu_eager_baseline": gpu_eager,
         "other_configs": others,
     }
     print(json.dumps(line), flush=True)

@@ -84,7 +84,8 @@ for name, recs in ops.KERNEL_TIMING.items():
         tot = sum(ts) / reps
         line = f"{name:28s} spec/tag {tag!s:>14s}  launches/eval {len(ts) / reps:5.1f}  ms/eval {tot:8.3f}  avg {sum(ts) / len(ts):8.3f} ms"
         if name in ("pml_tp_fwd", "pml_tp_bwd"):
-            pl = next(p for p in plans._PLANS if getattr(p, "spec_id", None) == tag and hasattr(p, "DIN"))
+            spec = tag[0] if isinstance(tag, tuple) else tag  # cotangent launches are tagged (spec, need_h, need_y, need_r)
+            pl = next(p for p in plans._PLANS if getattr(p, "spec_id", None) == spec and hasattr(p, "DIN"))
             fwd_b = E * (4 * pl.NP * pl.C + 4 * pl.NSH + 16) + N * 4 * (pl.C * pl.DIN + pl.C * pl.DOUT)
             if name == "pml_tp_bwd":  # reads R,Y,h,g ; writes dR, dY (+ dh atomics): SURVEY §8d cotangent formulas combined
                 fwd_b = E * (8 * pl.NP * pl.C + 8 * pl.NSH + 16) + N * 4 * (2 * pl.C * pl.DIN + pl.C * pl.DOUT)
