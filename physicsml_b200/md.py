@@ -4,8 +4,9 @@ configs[3].  Mirrors what the reference's OpenMM graph module does per MD step
 neighbour list, run the module, scale the output) and what its ASE calculator returns (``plugins/ase/ase_graph.py:17-64``:
 energy and forces), with three differences that matter at 24 000 atoms:
 
-* **Verlet skin**: the neighbour list is built with ``cut_off + skin`` and reused until some atom has moved more than
-  ``skin / 2`` since the build (one tiny kernel + one 4-byte read-back per step).  Results are EXACT, not approximate: an
+* **Verlet skin** (default on when the evaluation is graph-captured, off for large eager systems, where the 0.7 ms GPU
+  list is simply rebuilt every step): the neighbour list is built with ``cut_off + skin`` and reused until some atom has
+  moved more than ``skin / 2`` since the build (one tiny kernel + one 4-byte read-back per step).  Results are EXACT, not approximate: an
   edge longer than the model's cut-off contributes exactly zero to every layer — the polynomial cut-off makes its Bessel
   features 0, the bias-free radial MLP maps 0 to 0 (SiLU(0) = 0), so its tensor-product weights vanish.
 * **No per-step host work** between rebuilds: the evaluation is captured in a CUDA graph per neighbour list (optional; on
@@ -30,7 +31,7 @@ from .ops import _call, _p, _stream
 
 class MDCalculator:
     def __init__(self, module: torch.nn.Module, cut_off: float, node_attrs: torch.Tensor, cell: Optional[torch.Tensor] = None,
-                 skin: float = 0.5, position_scaling: float = 1.0, output_scaling: float = 1.0, self_interaction: bool = False,
+                 skin: Optional[float] = None, position_scaling: float = 1.0, output_scaling: float = 1.0, self_interaction: bool = False,
                  use_graph: Optional[bool] = None, graph_max_atoms: int = 6000, y_output: str = "y_graph_scalars",
                  total_atomic_energy: Optional[float] = None) -> None:
         """module: a ``forward(data) -> {"y_graph_scalars": ...}`` module on a CUDA device (``PooledMACEModule`` /
@@ -41,7 +42,7 @@ class MDCalculator:
         self.dev = next(module.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("MDCalculator needs the module on a CUDA device (no CPU fallback)")
-        self.cut_off, self.skin = float(cut_off), float(skin)
+        self.cut_off = float(cut_off)
         self.position_scaling, self.output_scaling = float(position_scaling), float(output_scaling)
         self.self_interaction, self.y_output = self_interaction, y_output
         self.node_attrs = node_attrs.to(self.dev, torch.float32).contiguous()
@@ -49,6 +50,11 @@ class MDCalculator:
         self.cell = None if cell is None else cell.to(self.dev, torch.float32).reshape(3, 3).contiguous()
         self._cell_host = None if cell is None else cell.detach().cpu().to(torch.float32).reshape(3, 3).clone()
         self.use_graph = (self.N <= graph_max_atoms) if use_graph is None else bool(use_graph)
+        # Skin default.  A list built with cut_off + skin has (1 + skin / cut_off)^3 times the edges (+27 % at 6 + 0.5 A), all of
+        # which the edge kernels still process; the GPU neighbour list itself costs 0.7 ms at 24 000 atoms.  So the skin pays
+        # where a rebuild is expensive — a captured graph has to be re-captured (small systems) — and NOT on large eager
+        # systems, which simply rebuild the exact list every step.
+        self.skin = float(skin) if skin is not None else (0.5 if self.use_graph else 0.0)
         self.total_atomic_energy = total_atomic_energy
         self.pos = torch.zeros(self.N, 3, device=self.dev)       # static input buffer
         self.ref_pos = torch.zeros(self.N, 3, device=self.dev)   # positions the current list was built from
@@ -63,7 +69,7 @@ class MDCalculator:
 
     # ------------------------------------------------------------------------------------------------------------------
     def _needs_rebuild(self) -> bool:
-        if self._data is None:
+        if self._data is None or self.skin <= 0.0:
             return True
         self._disp.zero_()
         _call("pml_max_disp2", _p(self.pos), _p(self.ref_pos), self.N, _p(self._disp), _stream())

@@ -257,6 +257,12 @@ def test_md_loop_skin_list_is_exact_and_reused(cuda):
             assert md.n_edges >= ei.shape[1]
             p = p + 0.04 * torch.randn(N, 3, generator=gen)  # ~0.07 A per step: a rebuild every few steps
         assert 2 <= md.n_builds < 12, md.n_builds
+    # eager default (large-system mode): no skin, the exact list is rebuilt on the GPU at every step
+    md = MDCalculator(model, 4.0, attrs, cell=cell, use_graph=False)
+    assert md.skin == 0.0
+    for step in range(3):
+        md.energy_forces(pos + 0.01 * step)
+    assert md.n_builds == 3
     # open boundaries + unit scaling as the OpenMM module applies it (nm in, kJ/mol out)
     md = MDCalculator(model, 4.0, attrs, skin=0.5, position_scaling=10.0, output_scaling=96.4853)
     e, f = md.energy_forces(pos / 10.0)
