@@ -458,7 +458,15 @@ def main() -> None:
             res["clocks"] = sampler.stop()
         # a replayed graph cannot carry per-kernel events: time the fused edge kernels in an eager pass of the SAME step
         # (same inputs, same kernels), and count the kernels of one step the same way
-        _, launches = timed(eager, min(steps, 10), 2, kernel_timing=True)
+        # ... with the side stream off, so that every launch runs alone between its two events (in the timed step the radial
+        # MLPs run concurrently on a second stream; a launch bracketed there would be charged for its neighbours' SM time)
+        from physicsml_b200 import mace as _mace
+
+        side_was, _mace.SIDE_STREAM[0] = _mace.SIDE_STREAM[0], False
+        try:
+            _, launches = timed(eager, min(steps, 10), 2, kernel_timing=True)
+        finally:
+            _mace.SIDE_STREAM[0] = side_was
         table = edge_kernel_table(n_atoms, n_edges, min(steps, 10))
         ms_e2e = None
         if not args.no_e2e:
