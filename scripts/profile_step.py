@@ -43,3 +43,23 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=70, max_name_column_width=70))
+
+if os.environ.get("PML_PROFILE_SHAPES") == "1":  # which eager ATen ops (and tensor shapes) are still on the device
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
+        step()
+        torch.cuda.synchronize()
+    rows = [e for e in prof.key_averages(group_by_input_shape=True) if e.key.startswith("aten::") and e.self_device_time_total > 0]
+    rows.sort(key=lambda e: -e.self_device_time_total)
+    print("\nATen ops with device time, one step (op, input shapes, calls, device us):")
+    for e in rows[:40]:
+        print(f"{e.key:28s} {str(e.input_shapes)[:90]:90s} {e.count:4d} {e.self_device_time_total:9.1f}")
+    print(f"total ATen device time {sum(e.self_device_time_total for e in rows):.1f} us")
+    big = [e for e in prof.events() if e.name.startswith("aten::") and e.self_device_time_total > 20 and e.stack]
+    seen = set()
+    for e in big:
+        frames = [s for s in e.stack if "physicsml_b200" in s or "workloads" in s][:3]
+        key = (e.name, tuple(frames))
+        if key in seen:
+            continue
+        seen.add(key)
+        print(e.name, [list(s) for s in (e.input_shapes or [])][:3], f"{e.self_device_time_total:.0f}us", frames)
