@@ -257,6 +257,26 @@ int pml_split_edge_index(const long long* edge_index, int* row0, int* row1, int 
  * (blocks.py:139-144,176-181 store them in the e3nn order) so that the GEMM's reduction index has unit stride */
 int pml_permute_columns(const float* src, long long src_row, const int* colmap, float* dst, int dst_row, long long N,
                         pml_stream_t stream);
+/* ---- element-indexed linears on the tensor cores: nodes grouped by chemical element ------------------------------
+ * o3.FullyConnectedTensorProduct(x, one-hot node_attrs) (mix_layer blocks.py:183-188,231-232; residual_connection_layer
+ * blocks.py:72-78,88-92; NequIP self_connection_layer interaction_block.py:73-82,91-92) is one [mul_in, mul_out] matrix per
+ * element: on nodes grouped by element every (element, irrep) pair is a dense GEMM over a contiguous row range.
+ * pml_species_order: order[pos] = node ids grouped by element (ascending inside a group), seg[0..Z] = group starts,
+ *   seg[Z+1] = 1 if some attrs row is not one-hot (its node is left out); Z <= 128, else PML_ERR_UNSUPPORTED.
+ * pml_segment_problems: out[i] = tmpl[i] placed on group meta[i].v (all device pointers) - see pml_seg_meta; a batch that
+ *   is not one-hot gets alpha = NaN in every problem.
+ * pml_permute_rows_cols: scatter 0: dst[pos, j] = src[rows[pos], colmap[j]] ; scatter 1: dst[rows[pos], colmap[j]] = src[pos, j]
+ *   for pos < N, j < ncols (rows / colmap: device int32). */
+typedef struct {
+  int v;    /* group (element) index into seg[] */
+  int mode; /* 0: M = group size ; 1: kc[0] = group size (the reduction runs over the group) */
+  long long a_mult, b_mult, c_mult; /* a_off / b_off / c_off grow by seg[v] * mult */
+} pml_seg_meta;
+int pml_species_order(const float* attrs, int N, int Z, int* order, int* seg, pml_stream_t stream);
+int pml_segment_problems(const pml_gemm_problem* tmpl, const pml_seg_meta* meta, int nprob, const int* seg, int Z,
+                         pml_gemm_problem* out, pml_stream_t stream);
+int pml_permute_rows_cols(const float* src, long long src_row, const int* rows, const int* colmap, float* dst,
+                          long long dst_row, int ncols, long long N, int scatter, pml_stream_t stream);
 /* [N, C*S] irreps layout <-> [N, C, S] (models/mace/modules/irreps_tools.py:47-67) */
 int pml_irreps_to_channel(const float* x, float* y, long long N, int C, int lmax, int inverse, pml_stream_t stream);
 

@@ -42,6 +42,10 @@ class GemmProblem(C.Structure):
     ]
 
 
+class SegMeta(C.Structure):
+    _fields_ = [("v", C.c_int), ("mode", C.c_int), ("a_mult", C.c_longlong), ("b_mult", C.c_longlong), ("c_mult", C.c_longlong)]
+
+
 class ElPlan(C.Structure):
     _fields_ = [
         ("npaths", C.c_int),
@@ -128,6 +132,9 @@ SIGNATURES = {
     "pml_csr_group": [_P, _P, _P, _P, _I, _I, _P],
     "pml_split_edge_index": [_P, _P, _P, _I, _P],
     "pml_permute_columns": [_P, _LL, _P, _P, _I, _LL, _P],
+    "pml_species_order": [_P, _I, _I, _P, _P, _P],
+    "pml_segment_problems": [_P, _P, _I, _P, _I, _P, _P],
+    "pml_permute_rows_cols": [_P, _LL, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "pml_irreps_to_channel": [_P, _P, _LL, _I, _I, _I, _P],
     "pml_scan_i32": [_P, _P, _I, _P],
     "pml_max_disp2": [_P, _P, _I, _P, _P],

@@ -17,4 +17,10 @@ typedef struct {
   float alpha;
   int accumulate;  // 0: C = result ; 1: C += result (plain RMW, single writer) ; split-K always uses atomics
 } pml_gemm_problem;
+// how pml_segment_problems places a template problem on the row group of one element (mirrors include/physicsml_b200.h)
+typedef struct {
+  int v;                            // group (element) index into seg[]
+  int mode;                         // 0: M = group size ; 1: kc[0] = group size
+  long long a_mult, b_mult, c_mult; // offsets grow by seg[v] * mult (the row strides of the operands indexed by the group)
+} pml_seg_meta;
 }

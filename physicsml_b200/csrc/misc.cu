@@ -3,6 +3,7 @@
 // the per-graph pooled readout (mace.py:252-258) and the receiver-CSR build used by the fused edge kernels.
 #include <stdio.h>
 
+#include "gemm_problem.h"
 #include "pml_common.cuh"
 
 namespace pml {
@@ -233,6 +234,148 @@ extern "C" int pml_permute_columns(const float* src, long long src_row, const in
   const long long total = N * dst_row;
   if (total <= 0) return PML_OK;
   pml::permute_columns_kernel<<<pml::ceil_div(total, 256), 256, 0, stream>>>(src, src_row, colmap, dst, dst_row, total);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+// ---- species-sorted node order for the element-indexed linears (element_linear.cu's header explains the op) ----------
+// FullyConnectedTensorProduct(x, one-hot attrs) is "one [mul_in, mul_out] matrix per chemical element": with the nodes
+// GROUPED by element every (element, irrep) pair is a dense GEMM over a contiguous row range, which is what the tensor
+// cores want (the FFMA kernels of element_linear.cu reach ~6 % of the fp32 pipe on a batch of molecules).
+//   order[pos]  = node ids grouped by element, ascending inside a group (deterministic: a stable counting sort)
+//   seg[0..Z]   = start of every element's group in `order`; seg[Z + 1] = 1 when some attrs row is not one-hot
+// One CTA: N is the number of nodes of a batch (1e3 .. 1e5); Z <= 128.
+namespace pml {
+constexpr int kSpeciesMaxZ = 128;
+
+__device__ __forceinline__ int one_hot_species(const float* __restrict__ row, int Z) {
+  int nz = 0, last = -1;
+  bool unit = true;
+  for (int e = 0; e < Z; ++e) {
+    const float y = __ldg(row + e);
+    if (y != 0.f) {
+      ++nz;
+      last = e;
+      unit = unit && (y == 1.f);
+    }
+  }
+  return (nz == 1 && unit) ? last : -1;
+}
+
+__global__ void __launch_bounds__(1024) species_order_kernel(const float* __restrict__ attrs, int N, int Z,
+                                                             int* __restrict__ order, int* __restrict__ seg) {
+  // group Z collects the nodes whose row is not one-hot: they go to the tail of `order`, which stays a permutation
+  __shared__ int cnt[kSpeciesMaxZ + 1], base[kSpeciesMaxZ + 1], run[kSpeciesMaxZ + 1];
+  __shared__ int wcnt[32][kSpeciesMaxZ + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = Z + 1;
+  if (tid < G) cnt[tid] = 0, run[tid] = 0;
+  __syncthreads();
+  for (int n = tid; n < N; n += blockDim.x) {
+    const int s = one_hot_species(attrs + (size_t)n * Z, Z);
+    atomicAdd(&cnt[s < 0 ? Z : s], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int v = 0; v < G; ++v) {
+      base[v] = acc;
+      if (v <= Z) seg[v] = acc;  // seg[Z] = number of one-hot rows
+      acc += cnt[v];
+    }
+    seg[Z + 1] = cnt[Z] > 0 ? 1 : 0;
+  }
+  const int chunks = (N + (int)blockDim.x - 1) / (int)blockDim.x;
+  for (int c = 0; c < chunks; ++c) {
+    __syncthreads();  // base / run of the previous chunk are final; wcnt is free
+    for (int i = tid; i < 32 * G; i += blockDim.x) wcnt[i / G][i % G] = 0;
+    __syncthreads();
+    const int n = c * (int)blockDim.x + tid;
+    int s = -1;
+    if (n < N) {
+      s = one_hot_species(attrs + (size_t)n * Z, Z);
+      if (s < 0) s = Z;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, s);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (s >= 0 && rank == 0) wcnt[warp][s] = __popc(peers);
+    __syncthreads();
+    if (s >= 0) {
+      int off = 0;
+      for (int w = 0; w < warp; ++w) off += wcnt[w][s];
+      order[base[s] + run[s] + off + rank] = n;
+    }
+    __syncthreads();
+    if (tid < G) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += wcnt[w][tid];
+      run[tid] += tot;
+    }
+  }
+}
+
+// The per-batch GEMM problem tables of the element-indexed linears: `tmpl` holds one problem per (path, element) with the
+// element-independent fields filled in by the host plan; here the row range of the element's group is patched in
+//   mode 0: M = group size, rows start at seg[v]  ;  mode 1: the reduction (chunk 0) runs over the group
+// entirely on the device, so a captured CUDA graph stays valid when a new batch is loaded into its static buffers.
+// A batch whose attrs are not one-hot (seg[Z + 1]) poisons every problem with alpha = NaN instead of computing a wrong result.
+__global__ void segment_problems_kernel(const pml_gemm_problem* __restrict__ tmpl, const pml_seg_meta* __restrict__ meta,
+                                        int nprob, const int* __restrict__ seg, int Z, pml_gemm_problem* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nprob) return;
+  pml_gemm_problem p = tmpl[i];
+  const pml_seg_meta m = meta[i];
+  const long long start = seg[m.v];
+  const int count = seg[m.v + 1] - seg[m.v];
+  for (int c = 0; c < p.nchunks; ++c) {
+    p.a_off[c] += start * m.a_mult;
+    p.b_off[c] += start * m.b_mult;
+  }
+  p.c_off += start * m.c_mult;
+  if (m.mode == 0) p.M = count;
+  else p.kc[0] = count;
+  if (seg[Z + 1] != 0) p.alpha = __int_as_float(0x7fc00000);
+  out[i] = p;
+}
+
+// dst[pos, j] = src[rows[pos], colmap[j]]   (scatter == 0: gather rows, permute columns; dst rows are dense)
+// dst[rows[pos], colmap[j]] = src[pos, j]   (scatter == 1: the inverse; src rows are dense)
+__global__ void __launch_bounds__(256) permute_rows_cols_kernel(const float* __restrict__ src, long long src_row,
+                                                                const int* __restrict__ rows, const int* __restrict__ colmap,
+                                                                float* __restrict__ dst, long long dst_row, int ncols,
+                                                                long long total, int scatter) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long pos = i / ncols;
+  const int j = (int)(i - pos * ncols);
+  const long long r = __ldg(rows + pos);
+  const int cj = __ldg(colmap + j);
+  if (scatter) dst[r * dst_row + cj] = __ldg(src + pos * src_row + j);
+  else dst[pos * dst_row + j] = __ldg(src + r * src_row + cj);
+}
+}  // namespace pml
+
+extern "C" int pml_species_order(const float* attrs, int N, int Z, int* order, int* seg, cudaStream_t stream) {
+  if (Z <= 0 || Z > pml::kSpeciesMaxZ || N < 0) return PML_ERR_UNSUPPORTED;
+  pml::species_order_kernel<<<1, 1024, 0, stream>>>(attrs, N, Z, order, seg);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_segment_problems(const pml_gemm_problem* tmpl, const pml_seg_meta* meta, int nprob, const int* seg, int Z,
+                                    pml_gemm_problem* out, cudaStream_t stream) {
+  if (nprob <= 0) return PML_OK;
+  pml::segment_problems_kernel<<<pml::ceil_div(nprob, 128), 128, 0, stream>>>(tmpl, meta, nprob, seg, Z, out);
+  PML_CHECK_LAUNCH();
+  return PML_OK;
+}
+
+extern "C" int pml_permute_rows_cols(const float* src, long long src_row, const int* rows, const int* colmap, float* dst,
+                                     long long dst_row, int ncols, long long N, int scatter, cudaStream_t stream) {
+  const long long total = N * ncols;
+  if (total <= 0) return PML_OK;
+  pml::permute_rows_cols_kernel<<<pml::ceil_div(total, 256), 256, 0, stream>>>(src, src_row, rows, colmap, dst, dst_row, ncols,
+                                                                              total, scatter);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

@@ -107,8 +107,10 @@ class ElementLinear(torch.nn.Module):
         mask = torch.zeros(self.plan.d_out)
         self.register_buffer("output_mask", mask + 1.0 if not self.plan.has_unfed_output else mask)
 
-    def forward(self, x: torch.Tensor, node_attrs: torch.Tensor) -> torch.Tensor:
-        return ops.element_linear(x, node_attrs, self.weight, self.plan.handle)
+    def forward(self, x: torch.Tensor, node_attrs: torch.Tensor, species: Optional["ops.SpeciesPlan"] = None) -> torch.Tensor:
+        """species: the batch's nodes grouped by element (ops.species_plan_for): the contraction then runs as grouped
+        tensor-core GEMMs over contiguous row ranges instead of the per-node FFMA kernels"""
+        return ops.element_linear(x, node_attrs, self.weight, self.plan.handle, -1 if species is None else species.handle)
 
 
 class _DenseLayer(torch.nn.Module):
@@ -202,7 +204,7 @@ class InteractionBlock(torch.nn.Module):
         self._channel = channel
 
     def forward(self, node_feats, node_attrs, edge_attrs, edge_feats, edge_index, edge_plan: Optional[ops.EdgePlan] = None,
-                radial: Optional[torch.Tensor] = None):
+                radial: Optional[torch.Tensor] = None, species: Optional["ops.SpeciesPlan"] = None):
         """radial: the block's radial-MLP output if the caller already computed it (MACE.forward runs the radial MLPs of all
         layers on a side stream: they depend on the edge features only)"""
         if edge_plan is None:
@@ -216,7 +218,7 @@ class InteractionBlock(torch.nn.Module):
         A = ops.tp_scatter(wh, edge_attrs, R, edge_plan.gather, edge_plan.rowptr, edge_plan.perm, self.tp.handle)
         A = self.linear(A)
         if self.mix_layer is not None:
-            A = self.mix_layer(A, node_attrs)
+            A = self.mix_layer(A, node_attrs, species)
         if not self._channel:
             A = ops.irreps_to_channel(A, self.channels, self.lmax, False)
         return A  # [N, C, S]
@@ -297,13 +299,13 @@ class NodeUpdateBlock(torch.nn.Module):
             if residual_connection else None
         )
 
-    def forward(self, m_i, node_feats, node_attrs, residual=None):
+    def forward(self, m_i, node_feats, node_attrs, residual=None, species=None):
         """residual: (tensor, event) if the caller already ran ``residual_connection_layer`` on the side stream (it depends
         on the layer's INPUT features only, so MACE.forward starts it before the interaction block)"""
         out = self.linear(m_i)
         if self.residual_connection_layer is not None:
             if residual is None:
-                out = out + self.residual_connection_layer(node_feats, node_attrs)
+                out = out + self.residual_connection_layer(node_feats, node_attrs, species)
             else:
                 torch.cuda.current_stream().wait_event(residual[1])
                 out = out + residual[0]
@@ -341,6 +343,7 @@ class MACE(torch.nn.Module):
             self.messages.append(MessageBlock(inter, attrs, hid_out, correlation))
             self.node_updates.append(NodeUpdateBlock(attrs, node_in, hid_out, not first))
             self.out_irreps.append(so3.irreps_str(hid_out))
+        self._el_plans = None
 
     def forward(self, data: dict) -> dict:
         pos = data["coordinates"]
@@ -351,6 +354,9 @@ class MACE(torch.nn.Module):
             cell = data["cell"][:3].contiguous()  # one cell for the whole batch: only rows 0-2 are read (utils.py:88-90)
             shift = data["cell_shift_vector"].contiguous()
         plan = ops.edge_plan_for(data, pos.shape[0], scatter_row=1)
+        if self._el_plans is None:
+            self._el_plans = [m.plan for m in self.modules() if isinstance(m, ElementLinear)]
+        species = ops.species_plan_for(data, self._el_plans)  # nodes grouped by element: tensor-core element linears
         re = self.radial_embedding
         Y, B = ops.edge_featurise(pos, plan.snd, plan.rcv, shift, cell, re.bessel_fn.bessel_weights, re.r_max,
                                   re.prefactor, 1.0, re.p, self.max_ell)
@@ -367,9 +373,9 @@ class MACE(torch.nn.Module):
         for i, (inter, msg, upd) in enumerate(zip(self.interactions, self.messages, self.node_updates)):
             res = None
             if radial[i] is not None and upd.residual_connection_layer is not None:
-                res = on_side_stream(upd.residual_connection_layer, h, attrs)
-            a = inter(h, attrs, Y, B, edge_index, edge_plan=plan, radial=radial[i])
-            h = upd(msg(a, attrs), h, attrs, residual=res)
+                res = on_side_stream(lambda h_, a_, layer=upd.residual_connection_layer: layer(h_, a_, species), h, attrs)
+            a = inter(h, attrs, Y, B, edge_index, edge_plan=plan, radial=radial[i], species=species)
+            h = upd(msg(a, attrs), h, attrs, residual=res, species=species)
             data[f"node_feats_{i}"] = h
         return data
 

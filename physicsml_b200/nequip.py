@@ -113,9 +113,10 @@ class InteractionBlock(torch.nn.Module):
             if pre is not None:  # small-graph mode: the self connection is independent of the convolution -> side stream
                 from .mace import on_side_stream
 
-                sc, sc_ready = on_side_stream(self.self_connection_layer, x, data["node_attrs"])
+                sp = data.get("_species")
+                sc, sc_ready = on_side_stream(lambda x_, a_: self.self_connection_layer(x_, a_, sp), x, data["node_attrs"])
             else:
-                sc = self.self_connection_layer(x, data["node_attrs"])
+                sc = self.self_connection_layer(x, data["node_attrs"], data.get("_species"))
         h = self.linear_1(x)
         if ready is not None:
             torch.cuda.current_stream().wait_event(ready)  # join right before the first consumer of the radial weights
@@ -188,6 +189,7 @@ class Nequip(torch.nn.Module):
             present = {(l, p) for _, l, p in layer.conv_irreps_out}
             node_in = [(m, l, p) for m, l, p in hidden if (l, p) in present]
             self.out_irreps.append(so3.irreps_str(node_in))
+        self._el_plans = None
 
     def forward(self, data: dict) -> dict:
         pos = data["coordinates"]
@@ -201,6 +203,9 @@ class Nequip(torch.nn.Module):
         supplied = data.get("_edge_plan")
         plan = ops.edge_plan_for(data, pos.shape[0], scatter_row=0)
         data["_edge_plan"] = plan
+        if self._el_plans is None:
+            self._el_plans = [m.plan for m in self.modules() if isinstance(m, ElementLinear)]
+        data["_species"] = ops.species_plan_for(data, self._el_plans)  # nodes grouped by element (tensor-core self connections)
         re = self.radial_embedding
         w = re.bessel_fn.bessel_weights
         data["node_feats"] = self.node_embedding(data["node_attrs"])
@@ -216,6 +221,7 @@ class Nequip(torch.nn.Module):
         for layer in self.conv_layers:
             data = layer(data)
         data.pop("_radial", None)
+        data.pop("_species", None)
         if supplied is None:
             data.pop("_edge_plan", None)
         else:

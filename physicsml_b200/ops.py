@@ -10,6 +10,7 @@ tensors raises ``NotImplementedError`` from the dispatcher, and a missing shared
 from __future__ import annotations
 
 import contextlib
+import weakref
 import ctypes as C
 import os
 from typing import List, Optional, Tuple
@@ -798,8 +799,38 @@ irrep_linear_bwd_w.register_autograd(_lin_bw_bwd, setup_context=_lin_bw_setup)
 # ======================================================================================================================
 # element-indexed linear
 # ======================================================================================================================
+# PML_EL_SORTED=0: keep the FFMA kernels of element_linear.cu even when a SpeciesPlan is available (A/B runs)
+EL_SORTED = [os.environ.get("PML_EL_SORTED", "1") == "1"]
+
+
+def _el_species(pl, sp: int, n: int):
+    """the SpeciesPlan behind handle `sp` if this call takes the tensor-core route (nodes grouped by element), else None"""
+    if sp < 0 or not EL_SORTED[0] or not pl.seg_ok or GEMM_MODE[0] != "tc" or n < TC_MIN_ROWS[0]:
+        return None
+    s = _SPECIES.get(sp)
+    if s is None:
+        raise RuntimeError("the SpeciesPlan of this element_linear call was released before its gradient was taken")
+    if s.N != n or s.Z != pl.Z:
+        raise ValueError(f"SpeciesPlan of {s.N} nodes / {s.Z} elements used on {n} nodes / {pl.Z} elements")
+    return s
+
+
+def _el_gather(src: Tensor, src_row: int, s: "SpeciesPlan", colmap: Tensor, ncols: int) -> Tensor:
+    """dense copy of `src` with the rows grouped by element and every block component-major"""
+    dst = _new_empty(src, s.N, ncols)
+    _call("pml_permute_rows_cols", _p(src), src_row, _p(s.order), _p(colmap), _p(dst), ncols, ncols, s.N, 0, _stream())
+    return dst
+
+
+def _el_tables(pl, s: "SpeciesPlan"):
+    tabs = s.tables(pl)
+    sz = C.sizeof(_lib.GemmProblem) * pl.seg_nprob
+    _, _, cm_in, cm_out = pl.segment_tables(tabs.device)
+    return tabs.data_ptr(), tabs.data_ptr() + sz, tabs.data_ptr() + 2 * sz, cm_in, cm_out
+
+
 @torch.library.custom_op(f"{NS}::element_linear", mutates_args=(), device_types="cuda")
-def element_linear(x: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tensor:
+def element_linear(x: Tensor, attrs: Tensor, w: Tensor, plan: int, sp: int = -1) -> Tensor:
     pl = plans.get(plan)
     x, attrs, w = _f32c(x), _f32c(attrs), _f32c(w)
     n = x.shape[0]
@@ -808,12 +839,20 @@ def element_linear(x: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tensor:
         S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
         shape = (n, pl.d_out // S, S)
     out = _zeros(x, shape) if pl.has_unfed_output else _new_empty(x, shape)
+    s = _el_species(pl, sp, n)
+    if s is not None:
+        t_fwd, _, _, cm_in, cm_out = _el_tables(pl, s)
+        xs = _el_gather(x, pl.d_in, s, cm_in, pl.d_in_c)
+        ys = _new_empty(x, n, pl.d_out_c)
+        _gemm("pml_gemm_grouped_tc", _p(xs), _p(w), _p(ys), t_fwd, pl.seg_nprob, n, n, pl.seg_max_mo, pl.seg_max_d, 1, pl.seg_max_mi)
+        _call("pml_permute_rows_cols", _p(ys), pl.d_out_c, _p(s.order), _p(cm_out), _p(out), pl.d_out, pl.d_out_c, n, 1, _stream())
+        return out
     _call("pml_element_linear_fwd", _p(x), _p(attrs), _p(w), C.byref(pl.c_plan), _p(out), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return out
 
 
 @element_linear.register_fake
-def _(x, attrs, w, plan):
+def _(x, attrs, w, plan, sp=-1):
     pl = plans.get(plan)
     if pl.out_layout == "channel":
         S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
@@ -822,79 +861,103 @@ def _(x, attrs, w, plan):
 
 
 @torch.library.custom_op(f"{NS}::element_linear_bwd_x", mutates_args=(), device_types="cuda")
-def element_linear_bwd_x(g: Tensor, attrs: Tensor, w: Tensor, plan: int) -> Tensor:
+def element_linear_bwd_x(g: Tensor, attrs: Tensor, w: Tensor, plan: int, sp: int = -1) -> Tensor:
     pl = plans.get(plan)
     g, attrs, w = _f32c(g), _f32c(attrs), _f32c(w)
     n = g.shape[0]
+    s = _el_species(pl, sp, n)
+    if s is not None:
+        _, t_bx, _, cm_in, cm_out = _el_tables(pl, s)
+        gs = _el_gather(g, pl.d_out, s, cm_out, pl.d_out_c)
+        dxs = _new_empty(g, n, pl.d_in_c)
+        _gemm("pml_gemm_grouped_tc", _p(gs), _p(w), _p(dxs), t_bx, pl.seg_nprob, n, n, pl.seg_max_mi, pl.seg_max_d, 1, pl.seg_max_mo)
+        dx = _zeros(g, n, pl.d_in) if pl.has_unfed_input else _new_empty(g, n, pl.d_in)
+        _call("pml_permute_rows_cols", _p(dxs), pl.d_in_c, _p(s.order), _p(cm_in), _p(dx), pl.d_in, pl.d_in_c, n, 1, _stream())
+        return dx
     dx = _zeros(g, n, pl.d_in)  # accumulated atomically per (element, node chunk)
     _call("pml_element_linear_bwd_x", _p(g), _p(attrs), _p(w), C.byref(pl.c_plan), _p(dx), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return dx
 
 
 @element_linear_bwd_x.register_fake
-def _(g, attrs, w, plan):
+def _(g, attrs, w, plan, sp=-1):
     return _new_empty(g, g.shape[0], plans.get(plan).d_in)
 
 
 @torch.library.custom_op(f"{NS}::element_linear_bwd_w", mutates_args=(), device_types="cuda")
-def element_linear_bwd_w(x: Tensor, g: Tensor, attrs: Tensor, plan: int) -> Tensor:
+def element_linear_bwd_w(x: Tensor, g: Tensor, attrs: Tensor, plan: int, sp: int = -1) -> Tensor:
     pl = plans.get(plan)
     x, g, attrs = _f32c(x), _f32c(g), _f32c(attrs)
+    n = x.shape[0]
     dw = _zeros(x, pl.weight_numel)
+    s = _el_species(pl, sp, n)
+    if s is not None:
+        _, _, t_bw, cm_in, cm_out = _el_tables(pl, s)
+        xs = _el_gather(x, pl.d_in, s, cm_in, pl.d_in_c)
+        gs = _el_gather(g, pl.d_out, s, cm_out, pl.d_out_c)
+        # the reduction runs over one element's nodes (<= n): split so that a CTA sums <= 1008 terms on the plain TMEM
+        # accumulator (see irrep_linear_bwd_w); the (2l+1) components of a block add into the same dW slab atomically
+        sk = max(1, -(-n // 1008))
+        _gemm("pml_gemm_grouped_tc", _p(xs), _p(gs), _p(dw), t_bw, pl.seg_nprob, n, pl.seg_max_mi, pl.seg_max_mo,
+              pl.seg_max_d, sk, min((n + sk - 1) // sk + 16, 128))
+        return dw
     _call("pml_element_linear_bwd_w", _p(x), _p(g), _p(attrs), C.byref(pl.c_plan), _p(dw), x.shape[0], pl.Z, 0, _stream(),
           launches=pl.n_launch)
     return dw
 
 
 @element_linear_bwd_w.register_fake
-def _(x, g, attrs, plan):
+def _(x, g, attrs, plan, sp=-1):
     return _new_empty(x, plans.get(plan).weight_numel)
 
 
 def _el_setup(ctx, inputs, output):
-    x, attrs, w, plan = inputs
+    x, attrs, w, plan, sp = inputs
     ctx.save_for_backward(x, attrs, w)
-    ctx.plan = plan
+    ctx.plan, ctx.sp = plan, sp
+    ctx.sp_ref = _SPECIES.get(sp) if sp >= 0 else None  # keeps the plan alive as long as the autograd graph
 
 
 def _el_bwd(ctx, g):
     x, attrs, w = ctx.saved_tensors
     nx, _, nw = ctx.needs_input_grad[:3]
     nw = nw and _PARAM_GRADS[0]
-    return (element_linear_bwd_x(g, attrs, w, ctx.plan) if nx else None, None,
-            element_linear_bwd_w(x, g, attrs, ctx.plan) if nw else None, None)
+    return (element_linear_bwd_x(g, attrs, w, ctx.plan, ctx.sp) if nx else None, None,
+            element_linear_bwd_w(x, g, attrs, ctx.plan, ctx.sp) if nw else None, None, None)
 
 
 element_linear.register_autograd(_el_bwd, setup_context=_el_setup)
 
 
 def _el_bx_setup(ctx, inputs, output):
-    g, attrs, w, plan = inputs
+    g, attrs, w, plan, sp = inputs
     ctx.save_for_backward(g, attrs, w)
-    ctx.plan = plan
+    ctx.plan, ctx.sp = plan, sp
+    ctx.sp_ref = _SPECIES.get(sp) if sp >= 0 else None
 
 
 def _el_bx_bwd(ctx, v):
     g, attrs, w = ctx.saved_tensors
     ng, _, nw = ctx.needs_input_grad[:3]
-    return (element_linear(v, attrs, w, ctx.plan).reshape(g.shape) if ng else None, None,
-            element_linear_bwd_w(v, g, attrs, ctx.plan) if nw else None, None)
+    return (element_linear(v, attrs, w, ctx.plan, ctx.sp).reshape(g.shape) if ng else None, None,
+            element_linear_bwd_w(v, g, attrs, ctx.plan, ctx.sp) if nw else None, None, None)
 
 
 element_linear_bwd_x.register_autograd(_el_bx_bwd, setup_context=_el_bx_setup)
 
 
 def _el_bw_setup(ctx, inputs, output):
-    x, g, attrs, plan = inputs
+    x, g, attrs, plan, sp = inputs
     ctx.save_for_backward(x, g, attrs)
-    ctx.plan = plan
+    ctx.plan, ctx.sp = plan, sp
+    ctx.sp_ref = _SPECIES.get(sp) if sp >= 0 else None
 
 
 def _el_bw_bwd(ctx, V):
     x, g, attrs = ctx.saved_tensors
     nx, ng = ctx.needs_input_grad[:2]
-    return (element_linear_bwd_x(g, attrs, V, ctx.plan) if nx else None,
-            element_linear(x, attrs, V, ctx.plan).reshape(g.shape) if ng else None, None, None)
+    return (element_linear_bwd_x(g, attrs, V, ctx.plan, ctx.sp) if nx else None,
+            element_linear(x, attrs, V, ctx.plan, ctx.sp).reshape(g.shape) if ng else None, None, None, None)
 
 
 element_linear_bwd_w.register_autograd(_el_bw_bwd, setup_context=_el_bw_setup)
@@ -1276,6 +1339,82 @@ energy_force_mse.register_autograd(_efm_bwd, setup_context=_efm_setup)
 # ======================================================================================================================
 # graph structure (index plumbing only — no floating-point work)
 # ======================================================================================================================
+_SPECIES: "weakref.WeakValueDictionary[int, SpeciesPlan]" = weakref.WeakValueDictionary()
+_SPECIES_NEXT = [0]
+_ONE_HOT_SEEN: list = []  # (data_ptr, version, shape) of attrs tensors already validated (most recent last)
+
+
+class SpeciesPlan:
+    """The nodes of a batch grouped by chemical element (``node_attrs`` one-hot rows): ``order`` [N] node ids, element by
+    element, and ``seg`` [Z + 2] group starts (+ a not-one-hot flag), both on the device and built by ONE kernel with no
+    host round trip — so the plan can be rebuilt inside a captured CUDA graph from whatever batch sits in the static
+    buffers.  It turns the element-indexed linears (mix_layer / residual_connection_layer / self_connection_layer) into
+    grouped tensor-core GEMMs over contiguous row ranges; ``tables(plan)`` are the per-batch problem tables of one
+    ElementLinearPlan (three: forward, dx, dW), also completed on the device."""
+
+    def __init__(self, attrs: Tensor) -> None:
+        attrs = _f32c(attrs)
+        self.N, self.Z = int(attrs.shape[0]), int(attrs.shape[1])
+        dev = attrs.device
+        self.order = torch.empty(max(self.N, 1), dtype=torch.int32, device=dev)
+        self.seg = torch.empty(self.Z + 2, dtype=torch.int32, device=dev)
+        _call("pml_species_order", _p(attrs), self.N, self.Z, _p(self.order), _p(self.seg), _stream())
+        self._src = (attrs.data_ptr(), attrs._version, tuple(attrs.shape))
+        self._tables: dict = {}
+        self.handle = _SPECIES_NEXT[0]
+        _SPECIES_NEXT[0] += 1
+        _SPECIES[self.handle] = self
+
+    def matches(self, attrs: Tensor) -> bool:
+        return self._src == (attrs.data_ptr(), attrs._version, tuple(attrs.shape))
+
+    def one_hot(self) -> bool:
+        """host check (one synchronising read of the flag the kernel wrote)"""
+        return int(self.seg[self.Z + 1].item()) == 0
+
+    def tables(self, pl) -> Tensor:
+        t = self._tables.get(pl.handle)
+        if t is None:
+            tmpl, meta, _, _ = pl.segment_tables(self.order.device)
+            n = 3 * pl.seg_nprob
+            t = torch.empty(n * C.sizeof(_lib.GemmProblem), dtype=torch.uint8, device=self.order.device)
+            _call("pml_segment_problems", _p(tmpl), _p(meta), n, _p(self.seg), self.Z, _p(t), _stream())
+            self._tables[pl.handle] = t
+        return t
+
+
+def species_plan_for(data: dict, el_plans=()) -> Optional["SpeciesPlan"]:
+    """SpeciesPlan of ``data["node_attrs"]`` (the caller-supplied ``data["_species_plan"]`` if it still describes that
+    tensor), or None when the FFMA kernels should run: attrs not one-hot, more than 128 elements, too few nodes to fill
+    128-row MMA tiles, or no element-indexed linear large enough to profit.  ``el_plans``: the ElementLinearPlans whose
+    problem tables are built right away (on the caller's stream, before any side-stream work uses them).
+
+    One-hot rows are validated with one synchronising read the first time an attrs tensor is seen; inside a CUDA-graph
+    capture the validation of the warm-up passes stands, and a later batch that is not one-hot turns the outputs into
+    NaN (pml_segment_problems) instead of silently using the wrong weights."""
+    attrs = data["node_attrs"]
+    if not (EL_SORTED[0] and GEMM_MODE[0] == "tc" and attrs.is_cuda and attrs.dim() == 2):
+        return None
+    n, z = attrs.shape
+    el_plans = [pl for pl in el_plans if pl.seg_ok]
+    if n < TC_MIN_ROWS[0] or z > 128 or not el_plans:
+        return None
+    sp = data.get("_species_plan")
+    if sp is None or not sp.matches(attrs):
+        sp = SpeciesPlan(attrs)
+        if not torch.cuda.is_current_stream_capturing():
+            key = sp._src
+            if key in _ONE_HOT_SEEN:
+                _ONE_HOT_SEEN.remove(key)
+            elif not sp.one_hot():
+                return None
+            _ONE_HOT_SEEN.append(key)
+            del _ONE_HOT_SEEN[:-16]
+    for pl in el_plans:
+        sp.tables(pl)
+    return sp
+
+
 def edge_plan_for(data: dict, num_nodes: int, scatter_row: int) -> "EdgePlan":
     """the caller-supplied ``data["_edge_plan"]`` (e.g. from ``neighbour_list.radius_graph``) if it still describes
     ``data["edge_index"]``, else a fresh plan; never written back into the caller's dict"""

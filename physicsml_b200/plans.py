@@ -334,7 +334,108 @@ class ElementLinearPlan:
         p.x_rs, p.o_rs = self.d_in, self.d_out
         self.c_plan = p
         self.n_launch = len({2 * self.irreps_in[i][1] + 1 for i, _, _ in paths})
+        self._build_segment_templates(paths, in_off, o_off, o_ws)
+        self._seg_dev: dict = {}
         self.handle = register(self)
+
+    def _build_segment_templates(self, paths, in_off, o_off, o_ws) -> None:
+        """Tensor-core route (ops.element_linear with a SpeciesPlan): on nodes GROUPED by element the op is one dense GEMM
+        per (path, element) over a contiguous row range.  Operands are compact component-major copies
+            xs[pos, cin_i + m*mul_in + u] = x[order[pos], in_off_i + u*d + m]      (fed input blocks only)
+            ys[pos, cout_o + m*mul_out + w] <-> out[order[pos], o_off_o + w*o_ws + m]  (fed output blocks only)
+        so that the reduction index and the output columns have unit stride.  The templates below are completed on the
+        device by pml_segment_problems (group start / size of every element): problem p*Z + v of each table."""
+        Z = self.Z
+        fed_in = sorted({i for i, _, _ in paths})
+        fed_out = sorted({o for _, o, _ in paths})
+        cin, cout, acc = {}, {}, 0
+        for i in fed_in:
+            cin[i] = acc
+            acc += self.irreps_in[i][0] * (2 * self.irreps_in[i][1] + 1)
+        self.d_in_c = acc
+        acc = 0
+        for o in fed_out:
+            cout[o] = acc
+            acc += self.irreps_out[o][0] * (2 * self.irreps_out[o][1] + 1)
+        self.d_out_c = acc
+        cm_in = np.zeros(max(self.d_in_c, 1), dtype=np.int32)
+        for i in fed_in:
+            mi, li, _ = self.irreps_in[i]
+            d = 2 * li + 1
+            for m_ in range(d):
+                for u in range(mi):
+                    cm_in[cin[i] + m_ * mi + u] = in_off[i] + u * d + m_
+        cm_out = np.zeros(max(self.d_out_c, 1), dtype=np.int32)
+        for o in fed_out:
+            mo, lo, _ = self.irreps_out[o]
+            d = 2 * lo + 1
+            for m_ in range(d):
+                for w in range(mo):
+                    cm_out[cout[o] + m_ * mo + w] = o_off[o] + w * o_ws[o] + m_
+        self._cm_in, self._cm_out = cm_in, cm_out
+
+        def prob():
+            q = _lib.GemmProblem()
+            for c in range(_lib.GEMM_MAX_CHUNKS):
+                q.cscale[c] = 1.0
+            q.nchunks, q.accumulate = 1, 0
+            return q
+
+        fwd, bx, bw, mf, mx, mw = [], [], [], [], [], []
+        for k, (i, o, w_off) in enumerate(paths):
+            mi, li, _ = self.irreps_in[i]
+            mo = self.irreps_out[o][0]
+            d = 2 * li + 1
+            alpha = float(self.c_plan.alpha[k])
+            for v in range(Z):
+                wv = w_off + v * mo  # W[u, v, w] at w_off + (u*Z + v)*mo + w
+                q = prob()  # ys = alpha * xs W_v over the rows of element v
+                q.a_off[0], q.b_off[0], q.kc[0], q.c_off = cin[i], wv, mi, cout[o]
+                q.a_rs, q.a_cs, q.a_bs = self.d_in_c, 1, mi
+                q.b_rs, q.b_cs, q.b_bs = Z * mo, 1, 0
+                q.c_rs, q.c_cs, q.c_bs = self.d_out_c, 1, mo
+                q.M, q.N, q.nbatch, q.alpha = 0, mo, d, alpha
+                fwd.append(q)
+                mf.append(_lib.SegMeta(v, 0, self.d_in_c, 0, self.d_out_c))
+                q = prob()  # dxs = alpha * gs W_v^T
+                q.a_off[0], q.b_off[0], q.kc[0], q.c_off = cout[o], wv, mo, cin[i]
+                q.a_rs, q.a_cs, q.a_bs = self.d_out_c, 1, mo
+                q.b_rs, q.b_cs, q.b_bs = 1, Z * mo, 0  # B[k = w, col = u] = W[u, v, w]
+                q.c_rs, q.c_cs, q.c_bs = self.d_in_c, 1, mi
+                q.M, q.N, q.nbatch, q.alpha = 0, mi, d, alpha
+                bx.append(q)
+                mx.append(_lib.SegMeta(v, 0, self.d_out_c, 0, self.d_in_c))
+                q = prob()  # dW[:, v, :] = alpha * sum over the element's rows and the 2l+1 components of xs^T gs
+                q.a_off[0], q.b_off[0], q.kc[0], q.c_off = cin[i], cout[o], 0, wv
+                q.a_rs, q.a_cs, q.a_bs = 1, self.d_in_c, mi     # A[u, k = pos]
+                q.b_rs, q.b_cs, q.b_bs = self.d_out_c, 1, mo    # B[k = pos, w]
+                q.c_rs, q.c_cs, q.c_bs = Z * mo, 1, 0
+                q.M, q.N, q.nbatch, q.alpha = mi, mo, d, alpha
+                bw.append(q)
+                mw.append(_lib.SegMeta(v, 1, self.d_in_c, self.d_out_c, 0))
+        self._seg_tmpl = fwd + bx + bw
+        self._seg_meta = mf + mx + mw
+        self.seg_nprob = len(fwd)
+        self.seg_max_mi = max([self.irreps_in[i][0] for i, _, _ in paths] + [1])
+        self.seg_max_mo = max([self.irreps_out[o][0] for _, o, _ in paths] + [1])
+        self.seg_max_d = max([2 * self.irreps_in[i][1] + 1 for i, _, _ in paths] + [1])
+        # worth three extra launches (two permutes + the table kernel) only when the contraction is sizeable: the scalar
+        # residual layers (one 128 -> 128 block) stay on the FFMA kernels
+        work = sum(self.irreps_in[i][0] * self.irreps_out[o][0] * (2 * self.irreps_in[i][1] + 1) for i, o, _ in paths)
+        self.seg_ok = bool(paths) and work >= 4 * 64 * 64 and self.seg_max_mi >= 16 and self.seg_max_mo >= 16
+
+    def segment_tables(self, device):
+        """(templates [3 * seg_nprob problems: forward, dx, dW], metas, colmap_in, colmap_out) on `device`"""
+        key = str(device)
+        if key not in self._seg_dev:
+            n = len(self._seg_tmpl)
+            self._seg_dev[key] = (
+                _upload((_lib.GemmProblem * n)(*self._seg_tmpl), device),
+                _upload((_lib.SegMeta * n)(*self._seg_meta), device),
+                torch.tensor(self._cm_in, device=device),
+                torch.tensor(self._cm_out, device=device),
+            )
+        return self._seg_dev[key]
 
 
 class TPPlan:

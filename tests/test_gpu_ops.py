@@ -440,6 +440,86 @@ def test_element_linear(cuda, irr_in, irr_out, layout, onehot):
         assert _rel(a, b) < 2e-5
 
 
+def test_species_plan_orders_nodes_by_element(cuda):
+    """pml_species_order: node ids grouped by element, ascending inside a group; group starts; the not-one-hot flag"""
+    from physicsml_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    for N, Z in ((1, 3), (700, 7), (5000, 4), (2049, 128)):
+        z = torch.randint(0, Z, (N,), generator=g)
+        if Z == 7:
+            z[z == 2] = 3  # an element that does not occur
+        attrs = torch.nn.functional.one_hot(z, Z).float().to(cuda)
+        sp = ops.SpeciesPlan(attrs)
+        assert sp.one_hot()
+        want = torch.sort(z, stable=True).indices
+        assert torch.equal(sp.order.cpu().long(), want)
+        counts = torch.bincount(z, minlength=Z)
+        assert sp.seg[: Z + 1].cpu().tolist() == [0] + torch.cumsum(counts, 0).tolist()
+    attrs[5, :] = 0.5
+    sp = ops.SpeciesPlan(attrs)
+    assert not sp.one_hot()
+    assert sorted(sp.order.cpu().tolist()) == list(range(attrs.shape[0]))  # still a permutation (rejected rows at the tail)
+    assert sp.order[-1].item() == 5
+
+
+@pytest.mark.parametrize("irr_in,irr_out,layout,Z", [
+    ("128x0e+128x1o+128x2e+128x3o", "128x0e+128x1o+128x2e+128x3o", "channel", 10),
+    ("64x0e+64x1o+64x2e", "64x0e+64x1e+64x1o+64x2e", "irreps", 5),   # an output block nobody feeds
+    ("32x0e+32x1o+32x1e", "32x0e+32x1o", "irreps", 3),               # an input block that feeds nothing
+    ("256x0e+256x1o+256x2e", "256x0e+256x1o+256x2e", "channel", 4),  # reductions longer than 128: promoting kernel
+])
+def test_element_linear_grouped_by_element(cuda, irr_in, irr_out, layout, Z):
+    """the tensor-core route of element_linear (nodes grouped by element, ops.SpeciesPlan) against e3nn's
+    FullyConnectedTensorProduct and against the FFMA kernels: values, first and second order"""
+    from e3nn import o3
+    from oracle.ref_model import to_channel_major
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import ElementLinearPlan
+
+    g = torch.Generator().manual_seed(7)
+    N = 777
+    ref = o3.FullyConnectedTensorProduct(o3.Irreps(irr_in), o3.Irreps(f"{Z}x0e"), o3.Irreps(irr_out)).to(cuda)
+    plan = ElementLinearPlan(irr_in, Z, irr_out, out_layout=layout)
+    assert plan.seg_ok
+    z = torch.randint(0, Z, (N,), generator=g)
+    z[z == 1] = 0  # element 1 does not occur in the batch
+    attrs = torch.nn.functional.one_hot(z, Z).float().to(cuda)
+    sp = ops.species_plan_for({"node_attrs": attrs}, [plan])
+    assert sp is not None
+    x = torch.randn(N, ref.irreps_in1.dim, generator=g).to(cuda).requires_grad_(True)
+    w = ref.weight.detach().clone().requires_grad_(True)
+    gemms, real_gemm = [], ops._gemm
+    ops._gemm = lambda name, *a: (gemms.append(name), real_gemm(name, *a))[1]
+    try:
+        y = ops.element_linear(x, attrs, w, plan.handle, sp.handle)
+    finally:
+        ops._gemm = real_gemm
+    assert gemms == ["pml_gemm_grouped_tc"]  # the grouped tensor-core route ran, not the FFMA kernels
+    y0 = ops.element_linear(x, attrs, w, plan.handle)
+    yr = ref(x, attrs)
+    if layout == "channel":
+        yr = to_channel_major(yr, ref.irreps_out)
+    assert _rel(y, yr) < 1e-5 and _rel(y0, yr) < 1e-5
+    gy = torch.randn(y.shape, generator=g).to(cuda).requires_grad_(True)
+    gs = torch.autograd.grad([y], [x, w], [gy], create_graph=True)
+    gr = torch.autograd.grad([yr], [x, ref.weight], [gy], create_graph=True)
+    for a, b in zip(gs, gr):
+        assert _rel(a, b) < 2e-5
+    vs = [torch.randn(a.shape, generator=g).to(cuda) for a in gs]
+    g2 = torch.autograd.grad(sum((a * v).sum() for a, v in zip(gs, vs)), [x, w, gy])
+    g2r = torch.autograd.grad(sum((a * v).sum() for a, v in zip(gr, vs)), [x, ref.weight, gy])
+    for a, b in zip(g2, g2r):
+        assert _rel(a, b) < 2e-5
+    # a batch that is not one-hot must not silently use the wrong weights: no plan from the host check ...
+    bad = attrs.clone()
+    bad[3] = 0.25
+    assert ops.species_plan_for({"node_attrs": bad}, [plan]) is None
+    # ... and NaN from a plan built without it (what a replayed CUDA graph would do)
+    spb = ops.SpeciesPlan(bad)
+    assert torch.isnan(ops.element_linear(x, bad, w, plan.handle, spb.handle)).any()
+
+
 # --------------------------------------------------------------------------------------------------------------------
 SYM_CASES = [(2, "4x0e+4x1o", 2, 4), (2, "4x0e", 2, 4), (2, "32x0e+32x1o", 3, 32), (3, "16x0e+16x1o", 3, 16),
              (3, "128x0e", 3, 128), (3, "8x0e+8x1o+8x2e", 3, 8)]
