@@ -9,7 +9,8 @@
 // Structure per CTA (one 128 x BN output tile, 256 threads):
 //   * all threads stage A/B k-blocks: global (arbitrary strides) -> registers -> hi/lo split -> shared memory in the
 //     canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), 2-stage ring;
-//   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 3 products per k-step, accumulating in TMEM;
+//   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 3 products per k-step, accumulating in TMEM — the
+//     hi*hi products into one accumulator, the two small cross terms into a second one (see TcSmem / kPromoBlocks);
 //     tcgen05.commit arrives on the stage's mbarrier to hand the stage back to the loaders;
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> scale -> global (plain / accumulate / atomic).
 // No TMA: operands must pass through registers anyway for the hi/lo split.
@@ -81,6 +82,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// v[0..31] += 32 TMEM columns, eight at a time (a second 32-register staging array would cost the kernels a resident CTA)
+__device__ __forceinline__ void tmem_add32(uint32_t taddr, float* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr + 8 * c));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[8 * c + j] += __uint_as_float(r[j]);
+  }
 }
 
 // Operand staging is split in two so the global loads of k-block i+1 are in flight while k-block i is converted,
@@ -173,6 +188,11 @@ struct __align__(128) TcSmem {
 // k-blocks (K = 128): each period accumulates into one of two TMEM buffers from zero and is then added, with ordinary
 // round-to-nearest fp32 adds, into per-thread register accumulators while the next period's MMAs run into the other
 // buffer.  The result is deterministic and keeps ~1e-6 relative accuracy at any K.
+//
+// The two cross terms A_lo*B_hi + A_hi*B_lo are ~2^-11 of the hi*hi sum.  Added into the SAME accumulator they cost two of
+// the three truncations per k-step; they go to a second TMEM accumulator instead (their own truncation is relative to
+// their small magnitude, i.e. negligible) and the two are added in registers at the end: one truncation per k-step
+// instead of three (K = 128: 16 instead of 48, ~1e-6 instead of ~3e-6 relative bias) for no extra MMA.
 constexpr int kPromoBlocks = 8;
 
 template <int N32>
@@ -223,7 +243,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   const bool b_vec_base = b_kfast && ((b_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 
   constexpr int NBUF = PROMOTE ? 2 : 1;
-  constexpr uint32_t TMEM_COLS = (NBUF * BN) < 32 ? 32 : (NBUF * BN);
+  constexpr uint32_t CORR = NBUF * BN;  // column offset of the cross-term accumulators (one per main buffer)
+  constexpr uint32_t TMEM_COLS = (2 * NBUF * BN) < 32 ? 32 : (2 * NBUF * BN);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
                  "r"(TMEM_COLS)
@@ -288,10 +309,14 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
     mbar_wait(smem_u32(&S.accbar[buf]), (period >> 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (half < NHALF) {
-      float v[COLS_PER_WARP];
-      tmem_ld_cols<COLS_PER_WARP / 32>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * COLS_PER_WARP), v);
+      const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * COLS_PER_WARP);
+      if (PROMOTE) {
 #pragma unroll
-      for (int j = 0; j < COLS_PER_WARP; ++j) acc[PROMOTE ? j : 0] += v[j];
+        for (int c32 = 0; c32 < COLS_PER_WARP / 32; ++c32) {
+          tmem_add32(t0 + CORR + 32 * c32, acc + (PROMOTE ? 32 * c32 : 0));  // the small cross terms first
+          tmem_add32(t0 + 32 * c32, acc + (PROMOTE ? 32 * c32 : 0));
+        }
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
@@ -338,9 +363,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
 #pragma unroll
       for (int kk = 0; kk < TC_BK / 8; ++kk) {
         const uint32_t o = kk * 256;  // two 16-byte k-units = two core matrices of 128 B
-        umma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, (!opens || kk > 0) ? 1u : 0u);
-        umma_tf32(d, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
-        umma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
+        const uint32_t first = (!opens || kk > 0) ? 1u : 0u;
+        umma_tf32(d + CORR, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, first);
+        umma_tf32(d + CORR, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
+        umma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, first);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[s]))
                    : "memory");
@@ -388,7 +414,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = acc[PROMOTE ? (c0 + j) : 0];
           } else {
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
+            const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0);
+            tmem_ld32(t0, v);
+            tmem_add32(t0 + CORR, v);
           }
           float* srow = stg + (q * 32 + lane) * SP + half * COLS_PER_WARP + c0;
 #pragma unroll
@@ -427,7 +455,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = acc[PROMOTE ? (c0 + j) : 0];
           } else {
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0), v);
+            const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP + c0);
+            tmem_ld32(t0, v);
+            tmem_add32(t0 + CORR, v);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) stg[(q * 32 + lane) * PITCH + half * 32 + j] = v[j];

@@ -466,7 +466,7 @@ def test_species_plan_orders_nodes_by_element(cuda):
 @pytest.mark.parametrize("irr_in,irr_out,layout,Z", [
     ("128x0e+128x1o+128x2e+128x3o", "128x0e+128x1o+128x2e+128x3o", "channel", 10),
     ("64x0e+64x1o+64x2e", "64x0e+64x1e+64x1o+64x2e", "irreps", 5),   # an output block nobody feeds
-    ("32x0e+32x1o+32x1e", "32x0e+32x1o", "irreps", 3),               # an input block that feeds nothing
+    ("64x0e+64x1o+64x1e", "64x0e+64x1o", "irreps", 3),               # an input block that feeds nothing
     ("256x0e+256x1o+256x2e", "256x0e+256x1o+256x2e", "channel", 4),  # reductions longer than 128: promoting kernel
 ])
 def test_element_linear_grouped_by_element(cuda, irr_in, irr_out, layout, Z):
