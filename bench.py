@@ -507,20 +507,30 @@ def main() -> None:
         f_host = torch.empty(n, 3).pin_memory()
         e_host = torch.empty(1).pin_memory()
         times = []
-        for i in range(steps + 3):
-            pos = pos + 0.017 * torch.randn(n, 3, generator=gen)  # |dr| ~ 0.03 A per step
-            host_pos.copy_(pos)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            e, f = md.energy_forces(host_pos)
-            e_host.copy_(e, non_blocking=True)
-            f_host.copy_(f, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            if i >= 3:
-                times.append(time.perf_counter() - t0)
+        mallocs = 0
+        try:
+            for i in range(steps + 3):
+                pos = pos + 0.017 * torch.randn(n, 3, generator=gen)  # |dr| ~ 0.03 A per step
+                host_pos.copy_(pos)
+                torch.cuda.synchronize()
+                if i == 3:
+                    mallocs = torch.cuda.memory_stats()["num_device_alloc"]
+                t0 = time.perf_counter()
+                e, f = md.energy_forces(host_pos)
+                e_host.copy_(e, non_blocking=True)
+                f_host.copy_(f, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                if i >= 3:
+                    times.append(time.perf_counter() - t0)
+            mallocs = torch.cuda.memory_stats()["num_device_alloc"] - mallocs
+        finally:
+            # MDCalculator switched the caching allocator to expandable segments (a list of a different length every
+            # step; see md.py): back to the default for the configs that follow
+            torch.cuda.memory._set_allocator_settings("expandable_segments:False")
         ms = 1e3 * sum(times) / len(times)
-        return {"ms_per_step": ms, "atoms_per_s": n / (ms * 1e-3), "steps": len(times), "neighbour_list_builds": md.n_builds,
-                "skin_A": md.skin, "edges_in_list": md.n_edges, "timing": "host wall clock per step, coordinates from / results to pinned host memory"}
+        return {"ms_per_step": ms, "ms_per_step_max": 1e3 * max(times), "atoms_per_s": n / (ms * 1e-3), "steps": len(times),
+                "neighbour_list_builds": md.n_builds, "skin_A": md.skin, "edges_in_list": md.n_edges, "cuda_mallocs_in_timed_steps": mallocs,
+                "timing": "host wall clock per step, coordinates from / results to pinned host memory"}
 
     def parity_vs_oracle(name, model, data, targets, dev):
         """step-0 check inside the benchmark run: the GPU model vs the CPU oracle (same weights) on the first

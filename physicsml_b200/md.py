@@ -11,6 +11,12 @@ energy and forces), with three differences that matter at 24 000 atoms:
   features 0, the bias-free radial MLP maps 0 to 0 (SiLU(0) = 0), so its tensor-product weights vanish.
 * **No per-step host work** between rebuilds: the evaluation is captured in a CUDA graph per neighbour list (optional; on
   by default below ``graph_max_atoms``) and replayed; positions are copied into the static buffer.
+* **Allocator**: an eagerly evaluated list has a slightly different length every step, so every edge-sized tensor (up
+  to 10 GB at 2 M edges) changes size every step.  PyTorch's default caching allocator cannot reuse a cached block for
+  a larger request: measured on the 24 k-atom box, two fresh ~10 GB cudaMallocs per step (+19 GiB reserved per step)
+  until the device is full, then an 870 ms stall while everything is freed (scripts/md_probe.py).  The calculator
+  therefore switches the allocator to expandable segments (``expandable_segments=True``; a process-wide PyTorch
+  allocator setting), with which the same loop holds 31.5 GiB and 32.3-33.0 ms per step, flat.
 * **Analytic forces**: -dE/dx comes from the fused cotangent kernels in the same call (the OpenMM route differentiates
   the TorchScript module from outside).
 
@@ -33,11 +39,12 @@ class MDCalculator:
     def __init__(self, module: torch.nn.Module, cut_off: float, node_attrs: torch.Tensor, cell: Optional[torch.Tensor] = None,
                  skin: Optional[float] = None, position_scaling: float = 1.0, output_scaling: float = 1.0, self_interaction: bool = False,
                  use_graph: Optional[bool] = None, graph_max_atoms: int = 6000, y_output: str = "y_graph_scalars",
-                 total_atomic_energy: Optional[float] = None) -> None:
+                 total_atomic_energy: Optional[float] = None, expandable_segments: Optional[bool] = None) -> None:
         """module: a ``forward(data) -> {"y_graph_scalars": ...}`` module on a CUDA device (``PooledMACEModule`` /
         ``PooledNequipModule`` or a patched reference module); node_attrs [N, Z] one-hot species (+ features);
         cell [3,3] or None (open boundaries); position_scaling / output_scaling as in the reference's OpenMM module
-        (nm -> Angstrom, eV -> kJ/mol)."""
+        (nm -> Angstrom, eV -> kJ/mol).  expandable_segments: let the CUDA caching allocator grow its segments in place
+        (default: on for eagerly evaluated systems, see the module docstring; False leaves the allocator alone)."""
         self.module = module.eval()
         self.dev = next(module.parameters()).device
         if self.dev.type != "cuda":
@@ -56,6 +63,10 @@ class MDCalculator:
         # systems, which simply rebuild the exact list every step.
         self.skin = float(skin) if skin is not None else (0.5 if self.use_graph else 0.0)
         self.total_atomic_energy = total_atomic_energy
+        if expandable_segments is None:
+            expandable_segments = not self.use_graph
+        if expandable_segments:
+            torch.cuda.memory._set_allocator_settings("expandable_segments:True")
         self.pos = torch.zeros(self.N, 3, device=self.dev)       # static input buffer
         self.ref_pos = torch.zeros(self.N, 3, device=self.dev)   # positions the current list was built from
         self._disp = torch.zeros(1, device=self.dev)

@@ -829,24 +829,64 @@ def _el_tables(pl, s: "SpeciesPlan"):
     return tabs.data_ptr(), tabs.data_ptr() + sz, tabs.data_ptr() + 2 * sz, cm_in, cm_out
 
 
+def _el_fwd_sorted(pl, s, x: Tensor, w: Tensor, xs: Optional[Tensor] = None) -> Tensor:
+    """y = L(x; w) on nodes grouped by element: gather -> grouped tensor-core GEMM -> scatter"""
+    n = x.shape[0]
+    t_fwd, _, _, cm_in, cm_out = _el_tables(pl, s)
+    if xs is None:
+        xs = _el_gather(x, pl.d_in, s, cm_in, pl.d_in_c)
+    ys = _new_empty(x, n, pl.d_out_c)
+    _gemm("pml_gemm_grouped_tc", _p(xs), _p(w), _p(ys), t_fwd, pl.seg_nprob, n, n, pl.seg_max_mo, pl.seg_max_d, 1, pl.seg_max_mi)
+    out = _zeros(x, _el_out_shape(pl, n)) if pl.has_unfed_output else _new_empty(x, _el_out_shape(pl, n))
+    _call("pml_permute_rows_cols", _p(ys), pl.d_out_c, _p(s.order), _p(cm_out), _p(out), pl.d_out, pl.d_out_c, n, 1, _stream())
+    return out
+
+
+def _el_bx_sorted(pl, s, g: Tensor, w: Tensor, gs: Optional[Tensor] = None) -> Tensor:
+    n = g.shape[0]
+    _, t_bx, _, cm_in, cm_out = _el_tables(pl, s)
+    if gs is None:
+        gs = _el_gather(g, pl.d_out, s, cm_out, pl.d_out_c)
+    dxs = _new_empty(g, n, pl.d_in_c)
+    _gemm("pml_gemm_grouped_tc", _p(gs), _p(w), _p(dxs), t_bx, pl.seg_nprob, n, n, pl.seg_max_mi, pl.seg_max_d, 1, pl.seg_max_mo)
+    dx = _zeros(g, n, pl.d_in) if pl.has_unfed_input else _new_empty(g, n, pl.d_in)
+    _call("pml_permute_rows_cols", _p(dxs), pl.d_in_c, _p(s.order), _p(cm_in), _p(dx), pl.d_in, pl.d_in_c, n, 1, _stream())
+    return dx
+
+
+def _el_bw_sorted(pl, s, x: Tensor, g: Tensor, xs: Optional[Tensor] = None, gs: Optional[Tensor] = None) -> Tensor:
+    n = x.shape[0]
+    _, _, t_bw, cm_in, cm_out = _el_tables(pl, s)
+    if xs is None:
+        xs = _el_gather(x, pl.d_in, s, cm_in, pl.d_in_c)
+    if gs is None:
+        gs = _el_gather(g, pl.d_out, s, cm_out, pl.d_out_c)
+    dw = _zeros(x, pl.weight_numel)
+    # the reduction runs over one element's nodes (<= n): split so that a CTA sums <= 1008 terms on the plain TMEM
+    # accumulator (see irrep_linear_bwd_w); the (2l+1) components of a block add into the same dW slab atomically
+    sk = max(1, -(-n // 1008))
+    _gemm("pml_gemm_grouped_tc", _p(xs), _p(gs), _p(dw), t_bw, pl.seg_nprob, n, pl.seg_max_mi, pl.seg_max_mo, pl.seg_max_d, sk,
+          min((n + sk - 1) // sk + 16, 128))
+    return dw
+
+
+def _el_out_shape(pl, n: int):
+    if pl.out_layout == "channel":
+        S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
+        return (n, pl.d_out // S, S)
+    return (n, pl.d_out)
+
+
 @torch.library.custom_op(f"{NS}::element_linear", mutates_args=(), device_types="cuda")
 def element_linear(x: Tensor, attrs: Tensor, w: Tensor, plan: int, sp: int = -1) -> Tensor:
     pl = plans.get(plan)
     x, attrs, w = _f32c(x), _f32c(attrs), _f32c(w)
     n = x.shape[0]
-    shape = (n, pl.d_out)
-    if pl.out_layout == "channel":
-        S = sum(2 * l + 1 for _, l, _ in pl.irreps_out)
-        shape = (n, pl.d_out // S, S)
-    out = _zeros(x, shape) if pl.has_unfed_output else _new_empty(x, shape)
     s = _el_species(pl, sp, n)
     if s is not None:
-        t_fwd, _, _, cm_in, cm_out = _el_tables(pl, s)
-        xs = _el_gather(x, pl.d_in, s, cm_in, pl.d_in_c)
-        ys = _new_empty(x, n, pl.d_out_c)
-        _gemm("pml_gemm_grouped_tc", _p(xs), _p(w), _p(ys), t_fwd, pl.seg_nprob, n, n, pl.seg_max_mo, pl.seg_max_d, 1, pl.seg_max_mi)
-        _call("pml_permute_rows_cols", _p(ys), pl.d_out_c, _p(s.order), _p(cm_out), _p(out), pl.d_out, pl.d_out_c, n, 1, _stream())
-        return out
+        return _el_fwd_sorted(pl, s, x, w)
+    shape = _el_out_shape(pl, n)
+    out = _zeros(x, shape) if pl.has_unfed_output else _new_empty(x, shape)
     _call("pml_element_linear_fwd", _p(x), _p(attrs), _p(w), C.byref(pl.c_plan), _p(out), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return out
 
@@ -867,13 +907,7 @@ def element_linear_bwd_x(g: Tensor, attrs: Tensor, w: Tensor, plan: int, sp: int
     n = g.shape[0]
     s = _el_species(pl, sp, n)
     if s is not None:
-        _, t_bx, _, cm_in, cm_out = _el_tables(pl, s)
-        gs = _el_gather(g, pl.d_out, s, cm_out, pl.d_out_c)
-        dxs = _new_empty(g, n, pl.d_in_c)
-        _gemm("pml_gemm_grouped_tc", _p(gs), _p(w), _p(dxs), t_bx, pl.seg_nprob, n, n, pl.seg_max_mi, pl.seg_max_d, 1, pl.seg_max_mo)
-        dx = _zeros(g, n, pl.d_in) if pl.has_unfed_input else _new_empty(g, n, pl.d_in)
-        _call("pml_permute_rows_cols", _p(dxs), pl.d_in_c, _p(s.order), _p(cm_in), _p(dx), pl.d_in, pl.d_in_c, n, 1, _stream())
-        return dx
+        return _el_bx_sorted(pl, s, g, w)
     dx = _zeros(g, n, pl.d_in)  # accumulated atomically per (element, node chunk)
     _call("pml_element_linear_bwd_x", _p(g), _p(attrs), _p(w), C.byref(pl.c_plan), _p(dx), n, pl.Z, 0, _stream(), launches=pl.n_launch)
     return dx
@@ -888,19 +922,10 @@ def _(g, attrs, w, plan, sp=-1):
 def element_linear_bwd_w(x: Tensor, g: Tensor, attrs: Tensor, plan: int, sp: int = -1) -> Tensor:
     pl = plans.get(plan)
     x, g, attrs = _f32c(x), _f32c(g), _f32c(attrs)
-    n = x.shape[0]
-    dw = _zeros(x, pl.weight_numel)
-    s = _el_species(pl, sp, n)
+    s = _el_species(pl, sp, x.shape[0])
     if s is not None:
-        _, _, t_bw, cm_in, cm_out = _el_tables(pl, s)
-        xs = _el_gather(x, pl.d_in, s, cm_in, pl.d_in_c)
-        gs = _el_gather(g, pl.d_out, s, cm_out, pl.d_out_c)
-        # the reduction runs over one element's nodes (<= n): split so that a CTA sums <= 1008 terms on the plain TMEM
-        # accumulator (see irrep_linear_bwd_w); the (2l+1) components of a block add into the same dW slab atomically
-        sk = max(1, -(-n // 1008))
-        _gemm("pml_gemm_grouped_tc", _p(xs), _p(gs), _p(dw), t_bw, pl.seg_nprob, n, pl.seg_max_mi, pl.seg_max_mo,
-              pl.seg_max_d, sk, min((n + sk - 1) // sk + 16, 128))
-        return dw
+        return _el_bw_sorted(pl, s, x, g)
+    dw = _zeros(x, pl.weight_numel)
     _call("pml_element_linear_bwd_w", _p(x), _p(g), _p(attrs), C.byref(pl.c_plan), _p(dw), x.shape[0], pl.Z, 0, _stream(),
           launches=pl.n_launch)
     return dw
@@ -918,10 +943,24 @@ def _el_setup(ctx, inputs, output):
     ctx.sp_ref = _SPECIES.get(sp) if sp >= 0 else None  # keeps the plan alive as long as the autograd graph
 
 
+def _el_shared(ctx, n: int):
+    """SpeciesPlan for a cotangent formula that may gather an operand ONCE for the two results that read it (only when no
+    graph is being recorded: the results then need no autograd node of their own)"""
+    if torch.is_grad_enabled():
+        return None, None
+    pl = plans.get(ctx.plan)
+    return pl, _el_species(pl, ctx.sp, n)
+
+
 def _el_bwd(ctx, g):
     x, attrs, w = ctx.saved_tensors
     nx, _, nw = ctx.needs_input_grad[:3]
     nw = nw and _PARAM_GRADS[0]
+    pl, s = _el_shared(ctx, x.shape[0]) if (nx and nw) else (None, None)
+    if s is not None:  # dx and dW both read the gathered cotangent
+        g_, x_, w_ = _f32c(g), _f32c(x), _f32c(w)
+        gs = _el_gather(g_, pl.d_out, s, _el_tables(pl, s)[4], pl.d_out_c)
+        return _el_bx_sorted(pl, s, g_, w_, gs), None, _el_bw_sorted(pl, s, x_, g_, None, gs), None, None
     return (element_linear_bwd_x(g, attrs, w, ctx.plan, ctx.sp) if nx else None, None,
             element_linear_bwd_w(x, g, attrs, ctx.plan, ctx.sp) if nw else None, None, None)
 
@@ -939,6 +978,11 @@ def _el_bx_setup(ctx, inputs, output):
 def _el_bx_bwd(ctx, v):
     g, attrs, w = ctx.saved_tensors
     ng, _, nw = ctx.needs_input_grad[:3]
+    pl, s = _el_shared(ctx, g.shape[0]) if (ng and nw) else (None, None)
+    if s is not None:  # L(v; w) and dW(v, g) both read the gathered tangent
+        v_, g_, w_ = _f32c(v), _f32c(g), _f32c(w)
+        vs = _el_gather(v_, pl.d_in, s, _el_tables(pl, s)[3], pl.d_in_c)
+        return _el_fwd_sorted(pl, s, v_, w_, vs).reshape(g.shape), None, _el_bw_sorted(pl, s, v_, g_, vs, None), None, None
     return (element_linear(v, attrs, w, ctx.plan, ctx.sp).reshape(g.shape) if ng else None, None,
             element_linear_bwd_w(v, g, attrs, ctx.plan, ctx.sp) if nw else None, None, None)
 
