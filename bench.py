@@ -526,7 +526,9 @@ def main() -> None:
         finally:
             # MDCalculator switched the caching allocator to expandable segments (a list of a different length every
             # step; see md.py): back to the default for the configs that follow
-            torch.cuda.memory._set_allocator_settings("expandable_segments:False")
+            from physicsml_b200.md import set_expandable_segments
+
+            set_expandable_segments(False)
         ms = 1e3 * sum(times) / len(times)
         return {"ms_per_step": ms, "ms_per_step_max": 1e3 * max(times), "atoms_per_s": n / (ms * 1e-3), "steps": len(times),
                 "neighbour_list_builds": md.n_builds, "skin_A": md.skin, "edges_in_list": md.n_edges, "cuda_mallocs_in_timed_steps": mallocs,

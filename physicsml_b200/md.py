@@ -35,6 +35,16 @@ from .neighbour_list import radius_graph
 from .ops import _call, _p, _stream
 
 
+def set_expandable_segments(on: bool) -> None:
+    """process-wide CUDA caching-allocator setting (the runtime form of PYTORCH_CUDA_ALLOC_CONF=expandable_segments:...)"""
+    setting = f"expandable_segments:{'True' if on else 'False'}"
+    fn = getattr(torch._C, "_accelerator_setAllocatorSettings", None)
+    if fn is not None:
+        fn(setting)
+    else:
+        torch.cuda.memory._set_allocator_settings(setting)
+
+
 class MDCalculator:
     def __init__(self, module: torch.nn.Module, cut_off: float, node_attrs: torch.Tensor, cell: Optional[torch.Tensor] = None,
                  skin: Optional[float] = None, position_scaling: float = 1.0, output_scaling: float = 1.0, self_interaction: bool = False,
@@ -66,7 +76,7 @@ class MDCalculator:
         if expandable_segments is None:
             expandable_segments = not self.use_graph
         if expandable_segments:
-            torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+            set_expandable_segments(True)
         self.pos = torch.zeros(self.N, 3, device=self.dev)       # static input buffer
         self.ref_pos = torch.zeros(self.N, 3, device=self.dev)   # positions the current list was built from
         self._disp = torch.zeros(1, device=self.dev)
