@@ -10,7 +10,7 @@
 //   * all threads stage A/B k-blocks: global (arbitrary strides) -> registers -> hi/lo split -> shared memory in the
 //     canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), 2-stage ring;
 //   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 3 products per k-step, accumulating in TMEM — the
-//     hi*hi products into one accumulator, the two small cross terms into a second one (see TcSmem / kPromoBlocks);
+//     hi*hi products into one accumulator, the two small cross terms into a second one (see TcSmem / kPromoK);
 //     tcgen05.commit arrives on the stage's mbarrier to hand the stage back to the loaders;
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> scale -> global (plain / accumulate / atomic).
 // No TMA: operands must pass through registers anyway for the hi/lo split.
@@ -19,7 +19,7 @@
 
 namespace pml {
 
-constexpr int TC_BM = 128, TC_BK = 16, TC_STAGES = 2, TC_THREADS = 256;
+constexpr int TC_BM = 128, TC_THREADS = 256;  // the k-block BK (16 or 32) is a template parameter
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -48,13 +48,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-// K-major, no swizzle: 16-byte unit (r, kc) of a [ROWS x 16] tile lives at  (r % 8) + 8 * kc + 32 * (r / 8)
-//   => leading (K) byte offset = 128, stride (M/N) byte offset = 512
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+// K-major, no swizzle: 16-byte unit (r, kc) of a [ROWS x BK] tile lives at  (r % 8) + 8 * kc + 2 BK * (r / 8)
+//   => leading (K) byte offset = 128, stride (M/N) byte offset = 32 BK (512 at BK = 16, 1024 at BK = 32)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)(128 >> 4) << 16;  // leading_byte_offset
-  d |= (uint64_t)(512 >> 4) << 32;  // stride_byte_offset
+  d |= (uint64_t)(128 >> 4) << 16;        // leading_byte_offset
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;  // stride_byte_offset
   d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
   return d;                         // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
@@ -102,80 +102,116 @@ __device__ __forceinline__ void tmem_add32(uint32_t taddr, float* v) {
 // stored and multiplied (register double buffering):
 //   fetch : element (row, k) at base + row*rs + k*cs -> registers ; rows >= nrows and k >= K read as 0
 //   commit: registers -> hi/lo split -> canonical UMMA shared-memory layout
-template <int ROWS>
+template <int ROWS, int BK>
 struct TileRegs {
-  static constexpr int UNITS = ROWS * (TC_BK / 4);
+  static constexpr int UNITS = ROWS * (BK / 4);
   static constexpr int PER_THREAD = (UNITS + TC_THREADS - 1) / TC_THREADS;
   float v[PER_THREAD][4];
 };
 
-template <int ROWS>
+template <int ROWS, int BK>
 __device__ __forceinline__ void tile_coords(int idx, bool kfast, int& r, int& kc) {
+  constexpr int KU = BK / 4;  // 16-byte k-units per row
   if (kfast) {
     // 8 consecutive lanes = 8 consecutive rows of one 16-byte k-unit = 8 consecutive units (128 contiguous bytes) of the
     // canonical layout: conflict-free 128-bit shared-memory accesses.  (Lanes along k hit units 8 apart = the same 4
     // banks: ncu counted 73 % of the kernel's shared-memory wavefronts as bank conflicts, which serialised the CTAs of
     // an SM on the shared-memory pipe.)  A warp still covers 8 rows x 64 contiguous bytes in global memory.
-    static_assert(TC_BK / 4 == 4, "unit mapping assumes 4 k-units per row");
-    r = (idx & 7) + 8 * (idx >> 5);
-    kc = (idx >> 3) & 3;
+    static_assert(KU == 4 || KU == 8, "k-units per row");
+    r = (idx & 7) + 8 * (idx / (8 * KU));
+    kc = (idx >> 3) & (KU - 1);
   } else {
     r = idx % ROWS;
     kc = idx / ROWS;
   }
 }
 
-template <int ROWS>
-__device__ __forceinline__ void fetch_tile(const float* __restrict__ base, long long rs, long long cs, int row0, int nrows,
-                                           int k0, int K, bool vec_ok, TileRegs<ROWS>& t) {
-  const bool kfast = (cs == 1);
+// What a thread stages of a [ROWS x 16] operand tile never changes during the kernel: which 16-byte units (row, kc), where
+// they sit in the shared-memory image and where their row starts in global memory.  Computed once; a k-block then costs
+// one 64-bit add and one load per unit.  (Recomputing coordinates, strides and bounds per element and k-block made the
+// kernel instruction-bound: 3 500 instructions per warp for a 128 x 128 x 128 tile, 29 % issue utilisation with two
+// warps per scheduler - profiles/r02_ncu_small_gemm.txt.)
+template <int ROWS, int BK>
+struct Lanes {
+  static constexpr int UNITS = ROWS * (BK / 4);
+  static constexpr int PER_THREAD = (UNITS + TC_THREADS - 1) / TC_THREADS;
+  long long off[PER_THREAD];  // row * row_stride + 4 kc * k_stride (elements, from the chunk's base)
+  int unit[PER_THREAD];       // float4 index inside the stage image; -1: this thread has no such unit
+  unsigned ok;                // bit i: unit i exists and its row is inside the matrix
+};
+
+template <int ROWS, int BK>
+__device__ __forceinline__ void setup_lanes(bool kfast, int row0, int nrows, long long rs, long long cs, Lanes<ROWS, BK>& L) {
+  L.ok = 0u;
 #pragma unroll
-  for (int it = 0; it < TileRegs<ROWS>::PER_THREAD; ++it) {
+  for (int it = 0; it < Lanes<ROWS, BK>::PER_THREAD; ++it) {
     const int idx = threadIdx.x + it * TC_THREADS;
-    t.v[it][0] = t.v[it][1] = t.v[it][2] = t.v[it][3] = 0.f;
-    if (TileRegs<ROWS>::UNITS % TC_THREADS != 0 && idx >= TileRegs<ROWS>::UNITS) continue;
+    L.unit[it] = -1;
+    L.off[it] = 0;
+    if (Lanes<ROWS, BK>::UNITS % TC_THREADS != 0 && idx >= Lanes<ROWS, BK>::UNITS) continue;
     int r, kc;
-    tile_coords<ROWS>(idx, kfast, r, kc);
-    const int gr = row0 + r, gk = k0 + kc * 4;
-    if (gr < nrows) {
-      const float* p = base + (long long)gr * rs + (long long)gk * cs;
-      if (vec_ok && gk + 3 < K) {
+    tile_coords<ROWS, BK>(idx, kfast, r, kc);
+    L.unit[it] = (r & 7) + 8 * kc + 2 * BK * (r >> 3);
+    const int gr = row0 + r;
+    L.off[it] = (long long)gr * rs + (long long)(4 * kc) * cs;
+    if (gr < nrows) L.ok |= 1u << it;
+  }
+}
+
+// element (row, k) of the chunk at base + row*rs + k*cs ; rows >= nrows and k >= K read as 0
+template <int ROWS, int BK>
+__device__ __forceinline__ void fetch_tile(const float* __restrict__ base, long long cs, int k0, int K, bool vec,
+                                           const Lanes<ROWS, BK>& L, TileRegs<ROWS, BK>& t) {
+  const bool full = k0 + BK <= K;  // uniform: only the last k-block of a chunk checks k per element
+  const float* b0 = base + (long long)k0 * cs;
+#pragma unroll
+  for (int it = 0; it < Lanes<ROWS, BK>::PER_THREAD; ++it) {
+    t.v[it][0] = t.v[it][1] = t.v[it][2] = t.v[it][3] = 0.f;
+    if (!((L.ok >> it) & 1u)) continue;
+    const float* p = b0 + L.off[it];
+    if (full) {
+      if (vec) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(p));
         t.v[it][0] = q.x; t.v[it][1] = q.y; t.v[it][2] = q.z; t.v[it][3] = q.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (gk + j < K) t.v[it][j] = __ldg(p + (long long)j * cs);
+        for (int j = 0; j < 4; ++j) t.v[it][j] = __ldg(p + (long long)j * cs);
       }
+    } else {
+      const int gk = k0 + 4 * ((L.unit[it] >> 3) & (BK / 4 - 1));
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gk + j < K) t.v[it][j] = __ldg(p + (long long)j * cs);
     }
   }
 }
 
-template <int ROWS>
-__device__ __forceinline__ void commit_tile(const TileRegs<ROWS>& t, bool kfast, float scale, float* __restrict__ s_hi,
-                                            float* __restrict__ s_lo) {
+template <int ROWS, int BK>
+__device__ __forceinline__ void commit_tile(const TileRegs<ROWS, BK>& t, const Lanes<ROWS, BK>& L, float scale,
+                                            float* __restrict__ s_hi, float* __restrict__ s_lo) {
+  const bool scaled = scale != 1.f;  // uniform
 #pragma unroll
-  for (int it = 0; it < TileRegs<ROWS>::PER_THREAD; ++it) {
-    const int idx = threadIdx.x + it * TC_THREADS;
-    if (TileRegs<ROWS>::UNITS % TC_THREADS != 0 && idx >= TileRegs<ROWS>::UNITS) continue;
-    int r, kc;
-    tile_coords<ROWS>(idx, kfast, r, kc);
+  for (int it = 0; it < Lanes<ROWS, BK>::PER_THREAD; ++it) {
+    if (Lanes<ROWS, BK>::UNITS % TC_THREADS != 0 && L.unit[it] < 0) continue;
+    float x0 = t.v[it][0], x1 = t.v[it][1], x2 = t.v[it][2], x3 = t.v[it][3];
+    if (scaled) x0 *= scale, x1 *= scale, x2 *= scale, x3 *= scale;
     float4 hi, lo;
-    split_tf32(t.v[it][0] * scale, hi.x, lo.x);
-    split_tf32(t.v[it][1] * scale, hi.y, lo.y);
-    split_tf32(t.v[it][2] * scale, hi.z, lo.z);
-    split_tf32(t.v[it][3] * scale, hi.w, lo.w);
-    const int unit = (r & 7) + 8 * kc + 32 * (r >> 3);
-    reinterpret_cast<float4*>(s_hi)[unit] = hi;
-    reinterpret_cast<float4*>(s_lo)[unit] = lo;
+    split_tf32(x0, hi.x, lo.x);
+    split_tf32(x1, hi.y, lo.y);
+    split_tf32(x2, hi.z, lo.z);
+    split_tf32(x3, hi.w, lo.w);
+    reinterpret_cast<float4*>(s_hi)[L.unit[it]] = hi;
+    reinterpret_cast<float4*>(s_lo)[L.unit[it]] = lo;
   }
 }
 
-template <int BN>
+constexpr int TC_STAGES = 2;
+
+template <int BN, int BK>
 struct __align__(128) TcSmem {
-  float a[TC_STAGES][2][TC_BM * TC_BK];
-  float b[TC_STAGES][2][BN * TC_BK];
-  float stage_pad[(TC_BM * (BN + 4) > 2 * 2 * (TC_BM + BN) * TC_BK) ? (TC_BM * (BN + 4) - 2 * 2 * (TC_BM + BN) * TC_BK) : 4];
+  float a[TC_STAGES][2][TC_BM * BK];
+  float b[TC_STAGES][2][BN * BK];
+  float stage_pad[(TC_BM * (BN + 4) > TC_STAGES * 2 * (TC_BM + BN) * BK) ? (TC_BM * (BN + 4) - TC_STAGES * 2 * (TC_BM + BN) * BK) : 4];
   unsigned long long bar[TC_STAGES];  // ring: the MMAs that read a stage have retired
   unsigned long long accbar[2];       // an accumulation period has retired into TMEM buffer 0 / 1
   uint32_t tmem_base;
@@ -184,7 +220,7 @@ struct __align__(128) TcSmem {
 };
 
 // tcgen05 accumulates in fp32 but aligns and TRUNCATES every partial sum, a bias of ~2^-24 of the running sum per MMA
-// (1e-5 relative after the 480 MMAs of K = 1280).  With PROMOTE the K loop is cut into periods of kPromoBlocks
+// (1e-5 relative after the 480 MMAs of K = 1280).  With PROMOTE the K loop is cut into periods of kPromoK / BK
 // k-blocks (K = 128): each period accumulates into one of two TMEM buffers from zero and is then added, with ordinary
 // round-to-nearest fp32 adds, into per-thread register accumulators while the next period's MMAs run into the other
 // buffer.  The result is deterministic and keeps ~1e-6 relative accuracy at any K.
@@ -193,7 +229,7 @@ struct __align__(128) TcSmem {
 // the three truncations per k-step; they go to a second TMEM accumulator instead (their own truncation is relative to
 // their small magnitude, i.e. negligible) and the two are added in registers at the end: one truncation per k-step
 // instead of three (K = 128: 16 instead of 48, ~1e-6 instead of ~3e-6 relative bias) for no extra MMA.
-constexpr int kPromoBlocks = 8;
+constexpr int kPromoK = 128;  // reduction length of one accumulation period
 
 template <int N32>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
@@ -206,13 +242,20 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
   }
 }
 
-template <int BN, bool PROMOTE>
-__global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
+// BK: reduction elements per pipeline step (shared-memory stage, barrier round trip, MMA issue).  Every step costs the same
+// ~1 us of dependent instructions, fences and barriers whatever it multiplies (scripts/bench_small_gemm.py: 0.95 us per
+// 16-wide k-block at N = 32 and at N = 128, unchanged by deeper prefetch or more stages), so grids of a few CTAs per
+// SM - the node-level problems of a molecule batch - run BK = 32: half the steps.  Grids that fill the GPU keep BK = 16:
+// 48 KB of shared memory and 80 registers let three CTAs share an SM and overlap each other's steps.
+template <int BN, bool PROMOTE, int BK>
+__global__ void __launch_bounds__(TC_THREADS, (BK == 16 && !PROMOTE && BN <= 64) ? 3 : ((BK == 16 || (!PROMOTE && BN <= 64)) ? 2 : 1))
+gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                      float* __restrict__ C,
                                                                      const pml_gemm_problem* __restrict__ probs,
                                                                      int M_runtime, int splitk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  TcSmem<BN>& S = *reinterpret_cast<TcSmem<BN>*>(smem_raw);
+  constexpr int kPromoBlocks = kPromoK / BK;
+  TcSmem<BN, BK>& S = *reinterpret_cast<TcSmem<BN, BK>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const pml_gemm_problem& Pg = probs[blockIdx.y];
@@ -274,25 +317,29 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   };
   auto chunk_k = [&](int ch) { return P.kc[ch] < 0 ? M_runtime : P.kc[ch]; };
   auto first_pos = [&](int ch_from) {
-    KPos q{ch_from, ks * TC_BK};
+    KPos q{ch_from, ks * BK};
     while (q.ch < nchunks && q.k0 >= chunk_k(q.ch)) ++q.ch;
     return q;
   };
   auto next_pos = [&](KPos q) {
-    q.k0 += TC_BK * splitk;
+    q.k0 += BK * splitk;
     if (q.k0 >= chunk_k(q.ch)) {
       KPos n = first_pos(q.ch + 1);
       return n;
     }
     return q;
   };
-  auto fetch = [&](const KPos& q, TileRegs<TC_BM>& ra, TileRegs<BN>& rb) {
+  Lanes<TC_BM, BK> LA;
+  Lanes<BN, BK> LB;
+  setup_lanes<TC_BM, BK>(a_kfast, row0, M, a_rs, a_cs, LA);
+  // B operand as an [N x K] K-major tile: element (n, k) = B[k*b_rs + n*b_cs]
+  setup_lanes<BN, BK>(b_kfast, col0, N, b_cs, b_rs, LB);
+  auto fetch = [&](const KPos& q, TileRegs<TC_BM, BK>& ra, TileRegs<BN, BK>& rb) {
     const long long aoff = P.a_off[q.ch] + a_boff;
     const long long boff = P.b_off[q.ch] + b_boff;
     const int K = chunk_k(q.ch);
-    fetch_tile<TC_BM>(A + aoff, a_rs, a_cs, row0, M, q.k0, K, a_vec_base && ((aoff & 3) == 0), ra);
-    // B operand as an [N x K] K-major tile: element (n, k) = B[k*b_rs + n*b_cs]
-    fetch_tile<BN>(B + boff, b_cs, b_rs, col0, N, q.k0, K, b_vec_base && ((boff & 3) == 0), rb);
+    fetch_tile<TC_BM, BK>(A + aoff, a_cs, q.k0, K, a_vec_base && ((aoff & 3) == 0), LA, ra);
+    fetch_tile<BN, BK>(B + boff, b_rs, q.k0, K, b_vec_base && ((boff & 3) == 0), LB, rb);
   };
 
   // this thread's slice of the output tile: TMEM lane quadrant q (rows 32q + lane), column half `half`
@@ -322,8 +369,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   };
 
   // two k-blocks of register prefetch: the loads of k-block i+2 are issued while block i is converted and multiplied
-  TileRegs<TC_BM> ra[2];
-  TileRegs<BN> rb[2];
+  TileRegs<TC_BM, BK> ra[2];
+  TileRegs<BN, BK> rb[2];
   KPos pos[3];
   pos[0] = first_pos(0);
   pos[1] = pos[0].ch < nchunks ? next_pos(pos[0]) : pos[0];
@@ -336,14 +383,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
     pos[2] = pos[1].ch < nchunks ? next_pos(pos[1]) : pos[1];
     const int s = it % TC_STAGES;
     if (it >= TC_STAGES) mbar_wait(smem_u32(&S.bar[s]), ((it / TC_STAGES) - 1) & 1);  // MMAs that read stage s retired
-    const int rsel = it & 1;
-    if (rsel == 0) {
-      commit_tile<TC_BM>(ra[0], a_kfast, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
-      commit_tile<BN>(rb[0], b_kfast, 1.f, S.b[s][0], S.b[s][1]);
+    if ((it & 1) == 0) {  // statically indexed register sets
+      commit_tile<TC_BM, BK>(ra[0], LA, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
+      commit_tile<BN, BK>(rb[0], LB, 1.f, S.b[s][0], S.b[s][1]);
       if (pos[2].ch < nchunks) fetch(pos[2], ra[0], rb[0]);
     } else {
-      commit_tile<TC_BM>(ra[1], a_kfast, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
-      commit_tile<BN>(rb[1], b_kfast, 1.f, S.b[s][0], S.b[s][1]);
+      commit_tile<TC_BM, BK>(ra[1], LA, P.cscale[pos[0].ch], S.a[s][0], S.a[s][1]);
+      commit_tile<BN, BK>(rb[1], LB, 1.f, S.b[s][0], S.b[s][1]);
       if (pos[2].ch < nchunks) fetch(pos[2], ra[1], rb[1]);
     }
     if (PROMOTE && to_promote >= 0) {  // the period closed one k-block ago: its MMAs have had an iteration to retire
@@ -361,12 +407,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
       const uint32_t b_hi = smem_u32(S.b[s][0]), b_lo = smem_u32(S.b[s][1]);
       const uint32_t d = tmem + (uint32_t)((period & 1) * BN);
 #pragma unroll
-      for (int kk = 0; kk < TC_BK / 8; ++kk) {
+      for (int kk = 0; kk < BK / 8; ++kk) {
         const uint32_t o = kk * 256;  // two 16-byte k-units = two core matrices of 128 B
         const uint32_t first = (!opens || kk > 0) ? 1u : 0u;
-        umma_tf32(d + CORR, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, first);
-        umma_tf32(d + CORR, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
-        umma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, first);
+        constexpr uint32_t SBO = 32 * BK;
+        umma_tf32(d + CORR, make_desc(a_lo + o, SBO), make_desc(b_hi + o, SBO), IDESC, first);
+        umma_tf32(d + CORR, make_desc(a_hi + o, SBO), make_desc(b_lo + o, SBO), IDESC, 1u);
+        umma_tf32(d, make_desc(a_hi + o, SBO), make_desc(b_hi + o, SBO), IDESC, first);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[s]))
                    : "memory");
@@ -489,37 +536,53 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_grouped_tc_kernel(const float
   }
 }
 
+template <int BN, bool PROMOTE, int BK>
+static int launch_tc_bk(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
+                           dim3 grid, int splitk, cudaStream_t stream) {
+  const size_t smem = sizeof(TcSmem<BN, BK>) + 128;
+  static bool configured[kMaxDevices] = {};
+  const int slot = device_slot();
+  if (!configured[slot]) {
+    if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN, PROMOTE, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return PML_ERR_LAUNCH;
+    configured[slot] = true;
+  }
+  gemm_grouped_tc_kernel<BN, PROMOTE, BK><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
+  return PML_OK;
+}
+
 template <int BN, bool PROMOTE>
 static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                      int max_M, int max_N, int max_batch, int splitk, cudaStream_t stream) {
   const int tiles_m = (max_M + TC_BM - 1) / TC_BM, tiles_n = (max_N + BN - 1) / BN;
   const long long gz = (long long)max_batch * splitk;
   if (gz > 65535 || nprobs > 65535) return PML_ERR_BAD_ARG;
-  const size_t smem = sizeof(TcSmem<BN>) + 128;
-  static bool configured[kMaxDevices] = {};
-  const int slot = device_slot();
-  if (!configured[slot]) {
-    if (cudaFuncSetAttribute(gemm_grouped_tc_kernel<BN, PROMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return PML_ERR_LAUNCH;
-    configured[slot] = true;
-  }
   dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)nprobs, (unsigned)gz);
-  gemm_grouped_tc_kernel<BN, PROMOTE><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
-  return PML_OK;
+  static int sms[kMaxDevices] = {};
+  const int slot = device_slot();
+  if (sms[slot] == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms[slot], cudaDevAttrMultiProcessorCount, dev);
+  }
+  // BK = 32 holds 64 (BN + 128) bytes x 16 of shared memory per CTA (128 KB at BN = 128): used where the whole grid fits in
+  // one wave of one (BN = 128) or two CTAs per SM
+  if ((long long)grid.x * grid.y * grid.z <= ((BN >= 128 || PROMOTE) ? 1ll : 2ll) * sms[slot])
+    return launch_tc_bk<BN, PROMOTE, 32>(A, B, C, probs, nprobs, M_runtime, grid, splitk, stream);
+  return launch_tc_bk<BN, PROMOTE, 16>(A, B, C, probs, nprobs, M_runtime, grid, splitk, stream);
 }
-
 
 }  // namespace pml
 
 // Same contract as pml_gemm_grouped (gemm.cu) plus max_k: an upper bound of the reduction length one CTA sees (sum of
 // the chunk extents of a problem, divided by splitk); <= 0 means unknown.  Reductions longer than 128 run the kernel
-// variant that promotes the TMEM accumulators into registers every 128 k (see kPromoBlocks).
+// variant that promotes the TMEM accumulators into registers every 128 k (see kPromoK).
 extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
                                    int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k,
                                    cudaStream_t stream) {
   if (nprobs <= 0 || max_M <= 0 || max_N <= 0 || max_batch <= 0) return PML_OK;
   if (splitk < 1) splitk = 1;
-  const bool promote = max_k <= 0 || max_k > pml::kPromoBlocks * pml::TC_BK;
+  const bool promote = max_k <= 0 || max_k > pml::kPromoK;
   int rc;
   if (promote) {
     if (max_N <= 32) rc = pml::launch_tc<32, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);

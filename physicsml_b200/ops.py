@@ -536,6 +536,20 @@ def _splitk_rows(tiles: int, k_extent: int, slots: int) -> int:
     return best
 
 
+# Node-sized problems (a batch of molecules: ~10 row tiles) occupy a handful of SMs and are latency chains: ~1 us per
+# 16-wide k-block whatever the tile multiplies (scripts/bench_small_gemm.py).  Long reductions (K >= 256) are split over
+# otherwise idle SMs, with an atomic epilogue into a zeroed output: 1 304 x 256 x 128: 17.1 -> 11.4 us, x 512: 30.4 ->
+# 12.9 us.  Below that the zero-fill and the atomic epilogue cost what the shorter chain saves (K = 64: 8.5 -> 11.3 us).
+# PML_SMALL_SPLITK=0 switches it off (A/B runs).
+SMALL_SPLITK = [os.environ.get("PML_SMALL_SPLITK", "1") == "1"]
+
+
+def _splitk_small(tiles: int, k_extent: int) -> int:
+    if not SMALL_SPLITK[0] or k_extent < 256 or tiles * 4 > _sms():
+        return 1
+    return max(1, min(k_extent // 64, _sms() // tiles, 8))
+
+
 # PML_COMPONENT_COPIES=0: let the tensor-core GEMM read e3nn-ordered operands in place (strided reduction index; A/B runs)
 COMPONENT_COPIES = [os.environ.get("PML_COMPONENT_COPIES", "1") == "1"]
 
@@ -590,14 +604,22 @@ def irrep_linear(x: Tensor, w: Tensor, plan: int) -> Tensor:
         image = _wide_image(w, k, nn, nn, 1)
         _call("pml_wide_fwd", _p(x), k, k, _p(image), _p(out), nn, n, nn, alpha, _stream())
         return out
-    out = _zeros(x, shape) if pl.has_unfed_output else _new_empty(x, shape)
+    sk = 1
+    if _gemm_name(n).endswith("_tc") and not pl.fwd_serial:
+        bn = 32 if pl.max_mul_out <= 32 else (64 if pl.max_mul_out <= 64 else 128)
+        sk = _splitk_small(((n + 127) // 128) * ((pl.max_mul_out + bn - 1) // bn) * len(pl._fwd) * pl.max_d, pl.max_k_fwd)
+    max_k = pl.max_k_fwd if sk == 1 else (pl.max_k_fwd + sk - 1) // sk + 32
+    out = _zeros(x, shape) if (pl.has_unfed_output or sk > 1) else _new_empty(x, shape)
     fwd, _, _ = pl.tables(x.device)
     if fwd is not None and n > 0 and pl._fwd_c and _gemm_name(n).endswith("_tc") and COMPONENT_COPIES[0]:
         # e3nn-ordered input with l > 0 blocks: the GEMM reads a component-major copy (unit-stride reduction index)
         cmap, fwd_c = pl.tables_c(x.device)[0]
         xc = _new_empty(x, n, pl.d_in)
         _call("pml_permute_columns", _p(x), pl.d_in, _p(cmap), _p(xc), pl.d_in, n, _stream())
-        _gemm(_gemm_name(n), _p(xc), _p(w), _p(out), _p(fwd_c), len(pl._fwd_c), n, n, pl.max_mul_out, pl.max_d, 1, pl.max_k_fwd)
+        _gemm(_gemm_name(n), _p(xc), _p(w), _p(out), _p(fwd_c), len(pl._fwd_c), n, n, pl.max_mul_out, pl.max_d, sk, max_k)
+        return out
+    if fwd is not None and n > 0 and not pl.fwd_serial:
+        _gemm(_gemm_name(n), _p(x), _p(w), _p(out), _p(fwd), len(pl._fwd), n, n, pl.max_mul_out, pl.max_d, sk, max_k)
         return out
     if fwd is not None and n > 0:
         nprob = len(pl._fwd)
@@ -636,6 +658,9 @@ def irrep_linear_bwd_x(g: Tensor, w: Tensor, plan: int) -> Tensor:
         bn = 32 if pl.max_mul_in <= 32 else 64
         tiles = ((n + 127) // 128) * ((pl.max_mul_in + bn - 1) // bn) * len(pl._bwd_x) * pl.max_d
         sk = _splitk_rows(tiles, pl.max_k_bwd_x, _tc_slots(bn, True))
+    if name.endswith("_tc") and sk == 1:
+        bn = 32 if pl.max_mul_in <= 32 else (64 if pl.max_mul_in <= 64 else 128)
+        sk = _splitk_small(((n + 127) // 128) * ((pl.max_mul_in + bn - 1) // bn) * len(pl._bwd_x) * pl.max_d, pl.max_k_bwd_x)
     dx = _zeros(g, n, pl.d_in) if (pl.has_unfed_input or sk > 1) else _new_empty(g, n, pl.d_in)
     _, bx, _ = pl.tables(g.device)
     if bx is not None and n > 0 and pl._bwd_x_c and name.endswith("_tc") and COMPONENT_COPIES[0]:
