@@ -534,8 +534,13 @@ __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __r
   }
 }
 
+#ifdef PML_TP_BWD_MAXREG  // tuning builds: cap the cotangent kernel's registers (one more CTA per SM, at the price of spills)
+#define PML_BWD_REGS __maxnreg__(PML_TP_BWD_MAXREG)
+#else
+#define PML_BWD_REGS
+#endif
 template <class T, bool DEDICATED, bool WANT_H, bool WANT_Y, bool WANT_R>
-__global__ void tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
+__global__ void PML_BWD_REGS tp_bwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                    const float* __restrict__ g, const int* __restrict__ gather,
                                    const int* __restrict__ rowptr, const int* __restrict__ perm, float* __restrict__ dh,
                                    float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage, int mm) {
