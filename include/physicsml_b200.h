@@ -125,7 +125,7 @@ int pml_gemm_grouped(const float* A, const float* B, float* C, const pml_gemm_pr
 /* Same contract, executed on the 5th-gen tensor cores: tcgen05.mma kind::tf32 with TMEM accumulators and 3xTF32
  * error compensation (fp32-accurate).  This is the radial-MLP path (K3) and, above PML_TC_MIN_ROWS rows, every other
  * dense contraction.  max_k: upper bound of the reduction length one CTA sees (sum of a problem's chunk extents /
- * splitk; <= 0 unknown): reductions longer than 128 use the variant that promotes the TMEM accumulators into fp32
+ * splitk; <= 0 unknown): reductions longer than 256 use the variant that promotes the TMEM accumulators into fp32
  * registers every 128 k, because the tensor core truncates its running sum at every MMA. */
 int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs, int M_runtime,
                         int max_M, int max_N, int max_batch, int splitk, int max_k, pml_stream_t stream);

@@ -229,7 +229,8 @@ struct __align__(128) TcSmem {
 // the three truncations per k-step; they go to a second TMEM accumulator instead (their own truncation is relative to
 // their small magnitude, i.e. negligible) and the two are added in registers at the end: one truncation per k-step
 // instead of three (K = 128: 16 instead of 48, ~1e-6 instead of ~3e-6 relative bias) for no extra MMA.
-constexpr int kPromoK = 128;  // reduction length of one accumulation period
+constexpr int kPromoK = 128;     // reduction length of one accumulation period
+constexpr int kPlainMaxK = 256;  // longest reduction the non-promoting kernels take
 
 template <int N32>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
@@ -575,14 +576,17 @@ static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_pr
 }  // namespace pml
 
 // Same contract as pml_gemm_grouped (gemm.cu) plus max_k: an upper bound of the reduction length one CTA sees (sum of
-// the chunk extents of a problem, divided by splitk); <= 0 means unknown.  Reductions longer than 128 run the kernel
+// the chunk extents of a problem, divided by splitk); <= 0 means unknown.  Reductions longer than 256 run the kernel
 // variant that promotes the TMEM accumulators into registers every 128 k (see kPromoK).
 extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, const pml_gemm_problem* probs, int nprobs,
                                    int M_runtime, int max_M, int max_N, int max_batch, int splitk, int max_k,
                                    cudaStream_t stream) {
   if (nprobs <= 0 || max_M <= 0 || max_N <= 0 || max_batch <= 0) return PML_OK;
   if (splitk < 1) splitk = 1;
-  const bool promote = max_k <= 0 || max_k > pml::kPromoK;
+  // With the cross terms in their own accumulator a plain reduction of 256 truncates the running sum 32 times - fewer than
+  // the 48 of a 128-long reduction before that change - so up to 256 the faster plain kernels run (BN up to 128, three /
+  // two CTAs per SM); beyond, the promoting variant.
+  const bool promote = max_k <= 0 || max_k > pml::kPlainMaxK;
   int rc;
   if (promote) {
     if (max_N <= 32) rc = pml::launch_tc<32, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);

@@ -474,7 +474,7 @@ tp_scatter_bwd.register_autograd(_tp_bwd_bwd, setup_context=_tp_bwd_setup)
 # per-irrep linear (grouped GEMM)
 # ======================================================================================================================
 # "tc": tcgen05 3xTF32 kernel for every problem with >= TC_MIN_ROWS[0] runtime rows (the edge-sized radial-MLP GEMMs,
-# their weight gradients and the node-sized per-irrep mixing of a batch; reductions longer than 128 promote the TMEM
+# their weight gradients and the node-sized per-irrep mixing of a batch; reductions longer than 256 promote the TMEM
 # accumulators into fp32 registers so the tensor core's truncating accumulation stays below 1e-6 relative), FFMA
 # kernel below that (a handful of rows cannot fill a 128-row MMA tile); "ffma": FFMA only
 GEMM_MODE = [os.environ.get("PML_GEMM", "tc")]
@@ -725,7 +725,7 @@ def irrep_linear_bwd_w(x: Tensor, g: Tensor, plan: int) -> Tensor:
         # 1024 terms per CTA they run on the plain TMEM accumulator (worst-case truncation bias 2e-5 relative, measured
         # < 1e-6 on random data) instead of the promoting variant, which is 1.5x slower on these shapes.
         _gemm(name, _p(A), _p(B), _p(dw), _p(bw), len(pl._bwd_w), n, max_m, max_n, pl.max_d, sk,
-              min(k_cta, 128) if k_cta <= 1024 else k_cta)
+              min(k_cta, 256) if k_cta <= 1024 else k_cta)
     return dw
 
 
@@ -891,7 +891,7 @@ def _el_bw_sorted(pl, s, x: Tensor, g: Tensor, xs: Optional[Tensor] = None, gs: 
     # accumulator (see irrep_linear_bwd_w); the (2l+1) components of a block add into the same dW slab atomically
     sk = max(1, -(-n // 1008))
     _gemm("pml_gemm_grouped_tc", _p(xs), _p(gs), _p(dw), t_bw, pl.seg_nprob, n, pl.seg_max_mi, pl.seg_max_mo, pl.seg_max_d, sk,
-          min((n + sk - 1) // sk + 16, 128))
+          min((n + sk - 1) // sk + 16, 256))
     return dw
 
 
