@@ -422,6 +422,7 @@ def main() -> None:
                 return graphed() if graphed is not None else wl.energy_forces(model, d_plain)
 
             G = int(data["num_graphs"])
+            md_box: list = []
             e_host = torch.zeros(G, 1).pin_memory()
             f_host = torch.zeros(n_atoms, 3).pin_memory()
 
@@ -429,14 +430,14 @@ def main() -> None:
                 if graphed is not None:
                     graphed.load(host)
                     e, f = graphed()
-                elif nl_ms is not None:  # single structure from host coordinates: copy, neighbour list, evaluate
-                    from physicsml_b200.neighbour_list import radius_graph
+                elif nl_ms is not None:
+                    # single structure from host coordinates through the public per-step API (md.MDCalculator: copy the
+                    # coordinates in, rebuild the neighbour list on the device, evaluate energy and forces)
+                    if not md_box:
+                        from physicsml_b200.md import MDCalculator
 
-                    d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()
-                         if k not in ("edge_index", "cell_shift_vector")}
-                    ei2, sh2, plan2 = radius_graph(d["coordinates"], cfg["model"]["cut_off"], pbc=(True, True, True), cell=d["cell"])
-                    d.update(edge_index=ei2, cell_shift_vector=sh2, _edge_plan=plan2)
-                    e, f = wl.energy_forces(model, d)
+                        md_box.append(MDCalculator(model, cfg["model"]["cut_off"], data["node_attrs"], cell=data["cell"]))
+                    e, f = md_box[0].energy_forces(host["coordinates"])
                 else:
                     d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in host.items()}
                     e, f = wl.energy_forces(model, d)
@@ -446,8 +447,8 @@ def main() -> None:
                 return e_host
 
             d2h = 4 * G + 12 * n_atoms
-            if nl_ms is not None:  # the e2e leg of the box ships coordinates, species, cell; edges are built on the device
-                h2d -= sum(host[k].numel() * host[k].element_size() for k in ("edge_index", "cell_shift_vector"))
+            if nl_ms is not None:  # the e2e leg of the box ships the coordinates; species and cell live in the calculator, edges are built on the device
+                h2d = host["coordinates"].numel() * host["coordinates"].element_size()
 
             def eager():
                 return wl.energy_forces(model, d_plain)

@@ -230,6 +230,32 @@ def test_small_qm9_full_batch_parity(cuda):
     assert (eg - e).abs().max().item() <= 1e-6 * scale and (fg - f).abs().max().item() <= 1e-5
 
 
+def test_graph_replay_with_other_species(cuda):
+    """the element-grouped node order and the per-batch GEMM tables of the element-indexed linears are built ON THE DEVICE
+    inside the captured evaluation: after load() of a batch with the same shapes but other species per atom the replay must
+    equal an eager evaluation of that batch (host-built tables would silently keep the captured batch's groups)"""
+    from physicsml_b200 import ops, workloads as wl
+    from physicsml_b200.graphs import GraphedEval
+
+    name = "mace_medium_spice_train"
+    data, _, _, _ = wl.make_batch(name, 0)
+    model = wl.build_model(name).to(cuda)
+    d = helpers.to_device(data, cuda)
+    plans = [m.plan for m in model.modules() if hasattr(m, "plan") and hasattr(m.plan, "seg_ok")]
+    assert any(pl.seg_ok for pl in plans) and ops.species_plan_for(d, plans) is not None  # the tensor-core route is in use
+    g = GraphedEval(model, d, wl.energy_forces)
+    e0, f0 = (t.clone() for t in g())
+    perm = torch.randperm(d["node_attrs"].shape[0], generator=torch.Generator().manual_seed(11)).to(cuda)
+    other = dict(d, node_attrs=d["node_attrs"][perm].contiguous())
+    assert not torch.equal(other["node_attrs"], d["node_attrs"])
+    g.load(other)
+    e1, f1 = (t.clone() for t in g())
+    e_ref, f_ref = wl.energy_forces(model, other)
+    scale = e_ref.abs().max().item()
+    assert (e1 - e_ref).abs().max().item() <= 1e-6 * scale and (f1 - f_ref).abs().max().item() <= 1e-5
+    assert (e1 - e0).abs().max().item() > 1e-3 * scale  # and it really is another batch
+
+
 def test_edge_plan_grouping_matches_stable_argsort(cuda):
     """pml_csr_group (own stable counting sort) == torch.argsort(stable=True), incl. a segment longer than 2048"""
     from physicsml_b200 import ops
