@@ -121,6 +121,77 @@ def test_tp_scatter(cuda, node_irreps, lmax, C):
         assert _rel(a, b) < 2e-5
 
 
+def test_tp_second_order_fused_r_cotangent(cuda):
+    """force-matching shape of the graph: a loss of the forward's output AND of its cotangents.  R then gets one cotangent
+    from the second-order node and one from the forward's node; the second is accumulated onto the first inside the kernel
+    (ops._PENDING_DR).  Same gradients as with the sum left to the engine (PML_FUSE_DR=0 semantics) and as e3nn; a pass
+    restricted to inputs that need neither leaves nothing parked for the next one."""
+    from physicsml_b200 import ops
+    from physicsml_b200.plans import TPPlan
+
+    g = torch.Generator().manual_seed(17)
+    node_irreps, lmax, C, N, deg = "32x0e+32x1o", 2, 32, 41, 7
+    ei = _edges(N, deg, g, cuda)
+    E = ei.shape[1]
+    tp_ref, target = _ref_tp(node_irreps, lmax, C)
+    tp_ref = tp_ref.to(cuda)
+    plan = TPPlan(node_irreps, lmax, str(target))
+    h = torch.randn(N, tp_ref.irreps_in1.dim, generator=g).to(cuda).requires_grad_(True)
+    Y = torch.randn(E, (lmax + 1) ** 2, generator=g).to(cuda).requires_grad_(True)
+    R = torch.randn(E, tp_ref.weight_numel, generator=g).to(cuda).requires_grad_(True)
+    ep = ops.EdgePlan(ei, N)
+    vs = None
+
+    def loss_of(fn):
+        nonlocal vs
+        out = fn(h, Y, R)
+        w = torch.tanh(out)  # the cotangent depends on the output, as dE/d(out) does in the models
+        gs = torch.autograd.grad([out], [h, Y, R], [w], create_graph=True)
+        if vs is None:
+            vs = [torch.randn(a.shape, generator=g).to(cuda) for a in gs]
+        return (out ** 2).sum() + sum((a * v).sum() for a, v in zip(gs, vs)), w
+
+    def mine(h, Y, R):
+        return ops.tp_scatter(h, Y, R, ep.gather, ep.rowptr, ep.perm, plan.handle)
+
+    def ref(h, Y, R):
+        m = tp_ref(h[ei[0]], Y, R)
+        return torch.zeros(N, m.shape[1], device=cuda, dtype=m.dtype).index_add_(0, ei[1], m)
+
+    l_ref, _ = loss_of(ref)
+    want = torch.autograd.grad(l_ref, [h, Y, R])
+    results = {}
+    for fuse in (True, False):
+        ops.FUSE_DR[0] = fuse
+        try:
+            l, w = loss_of(mine)
+            results[fuse] = torch.autograd.grad(l, [h, Y, R], retain_graph=True)
+            assert not ops._PENDING_DR
+            again = torch.autograd.grad(l, [h, Y, R])
+            for a, b in zip(results[fuse], again):
+                assert torch.equal(a, b) or _rel(a, b) < 1e-6  # atomics: not bit-identical
+        finally:
+            ops.FUSE_DR[0] = True
+    for a, b, c in zip(results[True], results[False], want):
+        assert _rel(a, c) < 2e-5 and _rel(b, c) < 2e-5 and _rel(a, b) < 1e-5
+    # a restricted pass: only the seed of the first-order cotangent is asked for, so the forward's node is not executed
+    out = mine(h, Y, R)
+    w = torch.randn(out.shape, generator=g).to(cuda).requires_grad_(True)
+    gs = torch.autograd.grad([out], [h, Y, R], [w], create_graph=True)
+    s = sum((a * v).sum() for a, v in zip(gs, vs))
+    (gw,) = torch.autograd.grad(s, [w], retain_graph=True)
+    assert not ops._PENDING_DR  # dropped at the end of the pass, nothing leaks into the next one
+    out_r = ref(h, Y, R)
+    gr = torch.autograd.grad([out_r], [h, Y, R], [w], create_graph=True)
+    (gw_r,) = torch.autograd.grad(sum((a * v).sum() for a, v in zip(gr, vs)), [w])
+    assert _rel(gw, gw_r) < 2e-5
+    full = torch.autograd.grad(s, [h, Y, R, w])
+    full_r = torch.autograd.grad(sum((a * v).sum() for a, v in zip(torch.autograd.grad([ref(h, Y, R)], [h, Y, R], [w], create_graph=True), vs)),
+                                 [h, Y, R, w])
+    for a, b in zip(full, full_r):
+        assert _rel(a, b) < 2e-5
+
+
 @pytest.mark.parametrize("node_irreps,lmax,C,N,deg", [("128x0e+128x1o", 3, 128, 300, 33), ("40x0e", 3, 40, 1000, 5),
                                                       ("32x0e+32x1o", 2, 32, 513, 17), ("16x0e+16x1o+16x2e", 3, 16, 64, 100)])
 def test_tp_pipelined_matches_streaming(cuda, node_irreps, lmax, C, N, deg):
