@@ -44,6 +44,7 @@ template <int D>
 __global__ void __launch_bounds__(128) el_fwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
                                                      const float* __restrict__ W, pml_el_plan P, float* __restrict__ out,
                                                      int N, int Z, int accumulate) {
+  pdl_enter();
   const int n = blockIdx.x, p = blockIdx.y;
   if (P.d[p] != D) return;
   extern __shared__ float xs[];  // [mul_in * D]
@@ -90,6 +91,7 @@ template <int D>
 __global__ void __launch_bounds__(256) el_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ attrs,
                                                        const float* __restrict__ W, pml_el_plan P, float* __restrict__ dx,
                                                        int N, int Z, int WC, int chunk) {
+  pdl_enter();
   constexpr int NB = D >= 5 ? 4 : 8;  // nodes per thread and pass
   constexpr int DP = D == 1 ? 1 : (D == 3 ? 4 : 8);  // staged row width: 128-bit shared-memory loads of the g rows
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
@@ -202,6 +204,7 @@ template <int D>
 __global__ void __launch_bounds__(256) el_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                        const float* __restrict__ attrs, pml_el_plan P,
                                                        float* __restrict__ dW, int N, int Z) {
+  pdl_enter();
   const int p = blockIdx.z / Z, v = blockIdx.z - p * Z;
   if (P.d[p] != D) return;
   const int MI = P.mul_in[p], MO = P.mul_out[p];
@@ -293,7 +296,7 @@ extern "C" int pml_element_linear_fwd(const float* x, const float* attrs, const 
   dim3 grid(N, plan->npaths);
   int max_mi = 0;
   for (int p = 0; p < plan->npaths; ++p) max_mi = plan->mul_in[p] > max_mi ? plan->mul_in[p] : max_mi;
-#define CALL(D) pml::el_fwd_kernel<D><<<grid, 128, (size_t)max_mi * D * sizeof(float), stream>>>(x, attrs, W, *plan, out, N, Z, accumulate);
+#define CALL(D) pml::launch_plain(pml::el_fwd_kernel<D>, dim3(grid), dim3(128), (size_t)max_mi * D * sizeof(float), stream, x, attrs, W, *plan, out, N, Z, accumulate);
   PML_EL_FOR_D(CALL)
 #undef CALL
   PML_CHECK_LAUNCH();
@@ -349,7 +352,7 @@ extern "C" int pml_element_linear_bwd_x(const float* g, const float* attrs, cons
         return PML_ERR_LAUNCH;                                                                                           \
       configured = smem[D];                                                                                              \
     }                                                                                                                    \
-    pml::el_bwd_x_kernel<D><<<grid, 256, smem[D], stream>>>(g, attrs, W, *plan, dx, N, Z, wcs[D], chunk);                        \
+    pml::launch_plain(pml::el_bwd_x_kernel<D>, dim3(grid), dim3(256), smem[D], stream, g, attrs, W, *plan, dx, N, Z, wcs[D], chunk);                        \
   }
   PML_EL_FOR_D(CALL)
 #undef CALL
@@ -368,7 +371,7 @@ extern "C" int pml_element_linear_bwd_w(const float* x, const float* g, const fl
     max_t = t > max_t ? t : max_t;
   }
   dim3 grid(max_t, (N + pml::EL_CHUNK - 1) / pml::EL_CHUNK, plan->npaths * Z);
-#define CALL(D) pml::el_bwd_w_kernel<D><<<grid, 256, 0, stream>>>(x, g, attrs, *plan, dW, N, Z);
+#define CALL(D) pml::launch_plain(pml::el_bwd_w_kernel<D>, dim3(grid), dim3(256), 0, stream, x, g, attrs, *plan, dW, N, Z);
   PML_EL_FOR_D(CALL)
 #undef CALL
   PML_CHECK_LAUNCH();

@@ -79,6 +79,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) gate_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                    const float* __restrict__ v, float* __restrict__ o0,
                                                    float* __restrict__ o1, const pml_gate_plan P, long long total) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long n = i / P.items;
@@ -137,9 +138,9 @@ extern "C" int pml_gate(const float* x, const float* dy, const float* v, const p
   if (!plan || plan->n_scal > PML_GATE_MAX_SEG || plan->n_gated > PML_GATE_MAX_SEG) return PML_ERR_BAD_ARG;
   const long long total = (long long)N * plan->items;
   const int grid = pml::ceil_div(total, 256);
-  if (mode == 0) pml::gate_kernel<0><<<grid, 256, 0, stream>>>(x, dy, v, out0, out1, *plan, total);
-  else if (mode == 1) pml::gate_kernel<1><<<grid, 256, 0, stream>>>(x, dy, v, out0, out1, *plan, total);
-  else if (mode == 2) pml::gate_kernel<2><<<grid, 256, 0, stream>>>(x, dy, v, out0, out1, *plan, total);
+  if (mode == 0) pml::launch_plain(pml::gate_kernel<0>, dim3(grid), dim3(256), 0, stream, x, dy, v, out0, out1, *plan, total);
+  else if (mode == 1) pml::launch_plain(pml::gate_kernel<1>, dim3(grid), dim3(256), 0, stream, x, dy, v, out0, out1, *plan, total);
+  else if (mode == 2) pml::launch_plain(pml::gate_kernel<2>, dim3(grid), dim3(256), 0, stream, x, dy, v, out0, out1, *plan, total);
   else return PML_ERR_BAD_ARG;
   PML_CHECK_LAUNCH();
   return PML_OK;

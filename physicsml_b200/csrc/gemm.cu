@@ -22,6 +22,7 @@ constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
 __global__ void __launch_bounds__(256) gemm_grouped_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                            float* __restrict__ C, const pml_gemm_problem* __restrict__ probs,
                                                            int M_runtime, int splitk, int tiles_m_max) {
+  pdl_enter();
   const pml_gemm_problem& P = probs[blockIdx.y];
   const int M = P.M < 0 ? M_runtime : P.M;
   const int N = P.N;
@@ -140,7 +141,7 @@ extern "C" int pml_gemm_grouped(const float* A, const float* B, float* C, const 
   const long long gz = (long long)max_batch * splitk;
   if (gz > 65535 || nprobs > 65535) return PML_ERR_BAD_ARG;
   dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)nprobs, (unsigned)gz);
-  pml::gemm_grouped_kernel<<<grid, 256, 0, stream>>>(A, B, C, probs, M_runtime, splitk, tiles_m);
+  pml::launch_plain(pml::gemm_grouped_kernel, dim3(grid), dim3(256), 0, stream, A, B, C, probs, M_runtime, splitk, tiles_m);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

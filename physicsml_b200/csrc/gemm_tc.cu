@@ -254,6 +254,7 @@ gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                      float* __restrict__ C,
                                                                      const pml_gemm_problem* __restrict__ probs,
                                                                      int M_runtime, int splitk) {
+  pdl_enter();  // before anything is read: the problem table itself may have been written by the previous kernel
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kPromoBlocks = kPromoK / BK;
   TcSmem<BN, BK>& S = *reinterpret_cast<TcSmem<BN, BK>*>(smem_raw);
@@ -548,7 +549,7 @@ static int launch_tc_bk(const float* A, const float* B, float* C, const pml_gemm
       return PML_ERR_LAUNCH;
     configured[slot] = true;
   }
-  gemm_grouped_tc_kernel<BN, PROMOTE, BK><<<grid, TC_THREADS, smem, stream>>>(A, B, C, probs, M_runtime, splitk);
+  launch_pdl(gemm_grouped_tc_kernel<BN, PROMOTE, BK>, grid, dim3(TC_THREADS), smem, stream, A, B, C, probs, M_runtime, splitk);
   return PML_OK;
 }
 

@@ -130,6 +130,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void pack_w_kernel(const float* __restrict__ W, long long w_rs, long long w_cs, int K, int N,
                               float* __restrict__ image) {
+  pdl_enter();
   // one thread per 16-byte unit of one tile: 64 rows x 16 k-units
   const int t = blockIdx.x;
   for (int idx = threadIdx.x; idx < BN * (KP / 4); idx += blockDim.x) {
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) wide_fwd_kernel(const float* __res
                                                               const float* __restrict__ image, float* __restrict__ C,
                                                               long long ldc, int M, int ntiles_n, int nsplit,
                                                               float alpha) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -351,6 +353,7 @@ __device__ __forceinline__ uint64_t make_desc32(uint32_t saddr) {  // [rows x 32
 // image[c][0 = hi, 1 = lo][unit32_of(k_out, kc)] = W[k_out, 32 c + 4 kc .. + 3] split; k_out >= K zero-filled
 __global__ void pack_wt_kernel(const float* __restrict__ W, long long w_rs, long long w_cs, int K, int N,
                                float* __restrict__ image) {
+  pdl_enter();
   const int c = blockIdx.x;
   for (int idx = threadIdx.x; idx < KP * (XC / 4); idx += blockDim.x) {
     const int kc = idx & 7, r = idx >> 3;
@@ -381,6 +384,7 @@ struct __align__(128) BwdXSmem {
 __global__ void __launch_bounds__(X_THREADS, 1) wide_bwd_x_kernel(const float* __restrict__ G, long long ldg, int N,
                                                                   const float* __restrict__ image, float* __restrict__ dA,
                                                                   long long lda, int K, int M, float alpha) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdXSmem& S = *reinterpret_cast<BwdXSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -596,6 +600,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) wide_bwd_x_tmem_kernel(const flo
                                                                        const float* __restrict__ image,
                                                                        float* __restrict__ dA, long long lda, int K, int M,
                                                                        float alpha) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdXTSmem& S = *reinterpret_cast<BwdXTSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -769,7 +774,7 @@ extern "C" long long pml_wide_image_floats(int N) { return (long long)((N + 63) 
 extern "C" int pml_wide_pack_w(const float* W, long long w_rs, long long w_cs, int K, int N, float* image,
                                cudaStream_t stream) {
   if (K <= 0 || K > pml::wide::KP || N <= 0) return PML_ERR_BAD_ARG;
-  pml::wide::pack_w_kernel<<<(N + 63) / 64, 256, 0, stream>>>(W, w_rs, w_cs, K, N, image);
+  pml::launch_plain(pml::wide::pack_w_kernel, dim3((N + 63) / 64), dim3(256), 0, stream, W, w_rs, w_cs, K, N, image);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -805,7 +810,7 @@ extern "C" int pml_wide_fwd(const float* A, long long lda, int K, const float* i
     if (cost < best * 0.97) best = cost, nsplit = s;
   }
   const int grid = min(sms, tiles_m * nsplit);
-  wide_fwd_kernel<<<grid, THREADS, smem, stream>>>(A, lda, K, image, C, ldc, M, ntiles_n, nsplit, alpha);
+  pml::launch_plain(wide_fwd_kernel, dim3(grid), dim3(THREADS), smem, stream, A, lda, K, image, C, ldc, M, ntiles_n, nsplit, alpha);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -815,7 +820,7 @@ extern "C" int pml_wide_fwd(const float* A, long long lda, int K, const float* i
 extern "C" int pml_wide_pack_wt(const float* W, long long w_rs, long long w_cs, int K, int N, float* image,
                                 cudaStream_t stream) {
   if (K <= 0 || K > pml::wide::KP || N <= 0 || (N % pml::wide::XC)) return PML_ERR_BAD_ARG;
-  pml::wide::pack_wt_kernel<<<N / pml::wide::XC, 256, 0, stream>>>(W, w_rs, w_cs, K, N, image);
+  pml::launch_plain(pml::wide::pack_wt_kernel, dim3(N / pml::wide::XC), dim3(256), 0, stream, W, w_rs, w_cs, K, N, image);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -851,11 +856,11 @@ extern "C" int pml_wide_bwd_x(const float* G, long long ldg, int N, const float*
         return PML_ERR_LAUNCH;
       configured_t[slot] = true;
     }
-    wide_bwd_x_tmem_kernel<<<min(sms, nitems), X_THREADS, smem_t, stream>>>(G, ldg, N, image, dA, lda, K, M, alpha);
+    pml::launch_plain(wide_bwd_x_tmem_kernel, dim3(min(sms, nitems)), dim3(X_THREADS), smem_t, stream, G, ldg, N, image, dA, lda, K, M, alpha);
     PML_CHECK_LAUNCH();
     return PML_OK;
   }
-  wide_bwd_x_kernel<<<min(sms, nitems), X_THREADS, smem, stream>>>(G, ldg, N, image, dA, lda, K, M, alpha);
+  pml::launch_plain(wide_bwd_x_kernel, dim3(min(sms, nitems)), dim3(X_THREADS), smem, stream, G, ldg, N, image, dA, lda, K, M, alpha);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

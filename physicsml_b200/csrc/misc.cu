@@ -33,6 +33,7 @@ template <int KIND, int ORDER>
 __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                   const float* __restrict__ v, float c, float* __restrict__ y,
                                                   long long n) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   y[i] = act_value<KIND, ORDER>(x[i], c, ORDER >= 1 ? g[i] : 0.f, ORDER >= 2 ? v[i] : 0.f);
@@ -44,6 +45,7 @@ template <int KIND, int ORDER>
 __global__ void __launch_bounds__(256) act_kernel_v4(const float4* __restrict__ x, const float4* __restrict__ g,
                                                      const float4* __restrict__ v, float c, float4* __restrict__ y,
                                                      long long n4) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 t = __ldcs(x + i);
@@ -183,12 +185,11 @@ extern "C" int pml_act(const float* x, const float* g, const float* v, float c, 
 #define PML_ACT_CASE(K, O)                                                                                          \
   if (kind == K && order == O) {                                                                                    \
     if (vec)                                                                                                        \
-      pml::act_kernel_v4<K, O><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x),                        \
-                                                         reinterpret_cast<const float4*>(g),                        \
-                                                         reinterpret_cast<const float4*>(v), c,                     \
-                                                         reinterpret_cast<float4*>(y), n / 4);                      \
+      pml::launch_pdl(pml::act_kernel_v4<K, O>, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const float4*>(x), \
+                      reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(v), c,                    \
+                      reinterpret_cast<float4*>(y), n / 4);                                                         \
     else                                                                                                            \
-      pml::act_kernel<K, O><<<grid, 256, 0, stream>>>(x, g, v, c, y, n);                                            \
+      pml::launch_pdl(pml::act_kernel<K, O>, dim3(grid), dim3(256), 0, stream, x, g, v, c, y, n);                   \
   }
   PML_ACT_CASE(0, 0) PML_ACT_CASE(0, 1) PML_ACT_CASE(0, 2) PML_ACT_CASE(1, 0) PML_ACT_CASE(1, 1) PML_ACT_CASE(1, 2)
 #undef PML_ACT_CASE
@@ -221,6 +222,7 @@ namespace pml {
 __global__ void __launch_bounds__(256) permute_columns_kernel(const float* __restrict__ src, long long src_row,
                                                               const int* __restrict__ colmap, float* __restrict__ dst,
                                                               int dst_row, long long total) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long n = i / dst_row;
@@ -233,7 +235,7 @@ extern "C" int pml_permute_columns(const float* src, long long src_row, const in
                                    cudaStream_t stream) {
   const long long total = N * dst_row;
   if (total <= 0) return PML_OK;
-  pml::permute_columns_kernel<<<pml::ceil_div(total, 256), 256, 0, stream>>>(src, src_row, colmap, dst, dst_row, total);
+  pml::launch_pdl(pml::permute_columns_kernel, dim3(pml::ceil_div(total, 256)), dim3(256), 0, stream, src, src_row, colmap, dst, dst_row, total);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -344,6 +346,7 @@ __global__ void __launch_bounds__(256) permute_rows_cols_kernel(const float* __r
                                                                 const int* __restrict__ rows, const int* __restrict__ colmap,
                                                                 float* __restrict__ dst, long long dst_row, int ncols,
                                                                 long long total, int scatter) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long pos = i / ncols;
@@ -374,8 +377,8 @@ extern "C" int pml_permute_rows_cols(const float* src, long long src_row, const 
                                      long long dst_row, int ncols, long long N, int scatter, cudaStream_t stream) {
   const long long total = N * ncols;
   if (total <= 0) return PML_OK;
-  pml::permute_rows_cols_kernel<<<pml::ceil_div(total, 256), 256, 0, stream>>>(src, src_row, rows, colmap, dst, dst_row, ncols,
-                                                                              total, scatter);
+  pml::launch_pdl(pml::permute_rows_cols_kernel, dim3(pml::ceil_div(total, 256)), dim3(256), 0, stream, src, src_row, rows, colmap,
+                  dst, dst_row, ncols, total, scatter);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

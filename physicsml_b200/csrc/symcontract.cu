@@ -101,6 +101,7 @@ struct WGrad {
 template <int ID>
 __global__ void __launch_bounds__(PML_SYM_BLOCK) sym_fwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
                                                       pml_sym_weights W, float* __restrict__ out, int N, int C, int Z) {
+  pdl_enter();
   using T = SymCode<ID>;
   // no early exit: every thread of the CTA takes part in the barriers of the generated body
   const long long tot = (long long)N * C, idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,6 +123,7 @@ template <int ID, bool WANT_W>
 __global__ void __launch_bounds__(PML_SYM_BLOCK, 3) sym_bwd_kernel(const float* __restrict__ x, const float* __restrict__ attrs,
                                                       pml_sym_weights W, const float* __restrict__ g,
                                                       float* __restrict__ dx, int N, int C, int Z) {
+  pdl_enter();
   using T = SymCode<ID>;
   // no early exit: every thread of the CTA takes part in the barriers of the generated body
   const long long tot = (long long)N * C, idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(PML_SYM_BLOCK, 3) sym_dbl_kernel(const float* 
                                                       const float* __restrict__ attrs, pml_sym_weights W,
                                                       const float* __restrict__ g, float* __restrict__ dg,
                                                       float* __restrict__ ddx, int N, int C, int Z) {
+  pdl_enter();
   using T = SymCode<ID>;
   // no early exit: every thread of the CTA takes part in the barriers of the generated body
   const long long tot = (long long)N * C, idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,7 +199,7 @@ extern "C" int PML_CAT(pml_sym_fwd_launch_, PML_SYM_ID)(const float* x, const fl
                                                          float* out, int N, int C, int Z, cudaStream_t stream) {
   if (N <= 0) return PML_OK;
   const long long tot = (long long)N * C;
-  pml::sym_fwd_kernel<PML_SYM_ID><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, attrs, *W, out, N, C, Z);
+  pml::launch_plain(pml::sym_fwd_kernel<PML_SYM_ID>, dim3(pml::ceil_div(tot, PML_SYM_BLOCK)), dim3(PML_SYM_BLOCK), 0, stream, x, attrs, *W, out, N, C, Z);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -208,9 +211,9 @@ extern "C" int PML_CAT(pml_sym_bwd_launch_, PML_SYM_ID)(const float* x, const fl
   if (N <= 0) return PML_OK;
   const long long tot = (long long)N * C;
   if (pml_sym_has_gw(*W))
-    pml::sym_bwd_kernel<PML_SYM_ID, true><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, attrs, *W, g, dx, N, C, Z);
+    pml::launch_plain(pml::sym_bwd_kernel<PML_SYM_ID, true>, dim3(pml::ceil_div(tot, PML_SYM_BLOCK)), dim3(PML_SYM_BLOCK), 0, stream, x, attrs, *W, g, dx, N, C, Z);
   else
-    pml::sym_bwd_kernel<PML_SYM_ID, false><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, attrs, *W, g, dx, N, C, Z);
+    pml::launch_plain(pml::sym_bwd_kernel<PML_SYM_ID, false>, dim3(pml::ceil_div(tot, PML_SYM_BLOCK)), dim3(PML_SYM_BLOCK), 0, stream, x, attrs, *W, g, dx, N, C, Z);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -221,9 +224,9 @@ extern "C" int PML_CAT(pml_sym_dbl_launch_, PML_SYM_ID)(const float* x, const fl
   if (N <= 0) return PML_OK;
   const long long tot = (long long)N * C;
   if (pml_sym_has_gw(*W))
-    pml::sym_dbl_kernel<PML_SYM_ID, true><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, v, attrs, *W, g, dg, ddx, N, C, Z);
+    pml::launch_plain(pml::sym_dbl_kernel<PML_SYM_ID, true>, dim3(pml::ceil_div(tot, PML_SYM_BLOCK)), dim3(PML_SYM_BLOCK), 0, stream, x, v, attrs, *W, g, dg, ddx, N, C, Z);
   else
-    pml::sym_dbl_kernel<PML_SYM_ID, false><<<pml::ceil_div(tot, PML_SYM_BLOCK), PML_SYM_BLOCK, 0, stream>>>(x, v, attrs, *W, g, dg, ddx, N, C, Z);
+    pml::launch_plain(pml::sym_dbl_kernel<PML_SYM_ID, false>, dim3(pml::ceil_div(tot, PML_SYM_BLOCK)), dim3(PML_SYM_BLOCK), 0, stream, x, v, attrs, *W, g, dg, ddx, N, C, Z);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(128) tp_fwd_kernel(const float* __restrict__ h
                                                      const float* __restrict__ R, const int* __restrict__ gather,
                                                      const int* __restrict__ rowptr, const int* __restrict__ perm,
                                                      float* __restrict__ out, int N, int C, int nslab, int mm) {
+  pdl_enter();
   using T = TPCode<ID>;
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(128) tp_bwd_kernel(const float* __restrict__ h
                                                      const int* __restrict__ perm, float* __restrict__ dh,
                                                      float* __restrict__ dY, float* __restrict__ dR, int N, int C,
                                                      int nslab, int mm) {
+  pdl_enter();
   using T = TPCode<ID>;
   constexpr int NV = next_pow2(T::NSH);
   const int lane = threadIdx.x & 31;
@@ -495,6 +497,7 @@ template <class T, bool DEDICATED>
 __global__ void tp_fwd_pipe_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                    const int* __restrict__ gather, const int* __restrict__ rowptr,
                                    const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage, int mm) {
+  pdl_enter();
   using L = PipeLayout<T>;
   PML_PIPE_PROLOGUE(true, false)
   for (int tile = blockIdx.x; tile < ts.ntiles; tile += ts.G) {
@@ -544,6 +547,7 @@ __global__ void PML_BWD_REGS tp_bwd_pipe_kernel(const float* __restrict__ h, con
                                    const float* __restrict__ g, const int* __restrict__ gather,
                                    const int* __restrict__ rowptr, const int* __restrict__ perm, float* __restrict__ dh,
                                    float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage, int mm) {
+  pdl_enter();
   using L = PipeLayout<T>;
   constexpr int NV = next_pow2(T::NSH);
   PML_PIPE_PROLOGUE((WANT_H || WANT_Y), true)
@@ -709,6 +713,7 @@ template <int ID, bool DEDICATED>
 __global__ void tp_fwd_pipe_g_kernel(const float* __restrict__ h, const float* __restrict__ Y, const float* __restrict__ R,
                                      const int* __restrict__ gather, const int* __restrict__ rowptr,
                                      const int* __restrict__ perm, float* __restrict__ out, int N, int C, int nstage, int mm) {
+  pdl_enter();
   using TF = TPCode<ID>;
   using L = PipeLayout<TF>;
   constexpr int NG = TPGroups<ID>::N;
@@ -850,6 +855,7 @@ __global__ void tp_bwd_pipe_g_kernel(const float* __restrict__ h, const float* _
                                      const float* __restrict__ g, const int* __restrict__ gather,
                                      const int* __restrict__ rowptr, const int* __restrict__ perm, float* __restrict__ dh,
                                      float* __restrict__ dY, float* __restrict__ dR, int N, int C, int nstage, int mm) {
+  pdl_enter();
   using TF = TPCode<ID>;
   using L = PipeLayout<TF>;
   constexpr int NG = TPGroups<ID>::N;
@@ -969,7 +975,7 @@ static bool launch_fwd_pipe(const float* h, const float* Y, const float* R, cons
   // nodes of different degree balance themselves instead of being paired statically
   // (config 2, 1304 nodes on 740 slots: 65.6 -> 57.3 us, 57.5 -> 65.8 % of HBM peak)
   if (DEDICATED && N < kSmallGraphNodes) cfg.grid = N < 4 * cfg.grid ? N : 4 * cfg.grid;
-  tp_fwd_pipe_kernel<T, DEDICATED><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
+  pml::launch_plain(tp_fwd_pipe_kernel<T, DEDICATED>, dim3(cfg.grid), dim3(threads), cfg.smem, stream, h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
   return true;
 }
 
@@ -1004,7 +1010,7 @@ static bool launch_fwd_intra(const float* h, const float* Y, const float* R, con
     const int sbytes = L::stage_floats(C) * 4;
     if (!pipe_config<tp_fwd_pipe_g_kernel<ID, true>>(threads, sbytes, C, N < kSmallGraphNodes, &cfg)) return false;
     if (N < kSmallGraphNodes) cfg.grid = N < 4 * cfg.grid ? N : 4 * cfg.grid;
-    tp_fwd_pipe_g_kernel<ID, true><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
+    pml::launch_plain(tp_fwd_pipe_g_kernel<ID, true>, dim3(cfg.grid), dim3(threads), cfg.smem, stream, h, Y, R, gather, rowptr, perm, out, N, C, cfg.nstage, mm);
     return true;
   } else {
     return false;
@@ -1021,7 +1027,7 @@ static bool launch_bwd_intra_one(const float* h, const float* Y, const float* R,
     const int threads = TPGroups<ID>::N * L::consumer_threads(C);
     const int sbytes = L::stage_floats(C) * 4;
     if (!pipe_config<tp_bwd_pipe_g_kernel<ID, false, H_, Y_, R_>>(threads, sbytes, C, N < kSmallGraphNodes, &cfg)) return false;
-    tp_bwd_pipe_g_kernel<ID, false, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, g, gather, rowptr, perm, dh, dY,
+    pml::launch_plain(tp_bwd_pipe_g_kernel<ID, false, H_, Y_, R_>, dim3(cfg.grid), dim3(threads), cfg.smem, stream, h, Y, R, g, gather, rowptr, perm, dh, dY,
                                                                                          dR, N, C, cfg.nstage, mm);
     return true;
   } else {
@@ -1076,7 +1082,7 @@ static bool launch_bwd_pipe_one(const float* h, const float* Y, const float* R, 
   const int threads = PL::consumer_threads(C) + (D ? 32 : 0);
   const int sbytes = PL::stage_floats(C) * 4;
   if (!pipe_config<tp_bwd_pipe_kernel<T, D, H_, Y_, R_>>(threads, sbytes, C, N < kSmallGraphNodes, &cfg)) return false;
-  tp_bwd_pipe_kernel<T, D, H_, Y_, R_><<<cfg.grid, threads, cfg.smem, stream>>>(h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N,
+  pml::launch_plain(tp_bwd_pipe_kernel<T, D, H_, Y_, R_>, dim3(cfg.grid), dim3(threads), cfg.smem, stream, h, Y, R, g, gather, rowptr, perm, dh, dY, dR, N,
                                                                                  C, cfg.nstage, mm);
   return true;
 }
@@ -1147,7 +1153,7 @@ extern "C" int PML_CAT(pml_tp_fwd_launch_, PML_TP_ID)(const float* h, const floa
   const int nslab = (C + 31) / 32;
   const int wpb = 4;
   const long long items = (long long)N * nslab;
-  pml::tp_fwd_kernel<PML_TP_ID><<<pml::ceil_div(items, wpb), wpb * 32, 0, stream>>>(h, Y, R, gather, rowptr, perm, out, N, C, nslab, mm);
+  pml::launch_plain(pml::tp_fwd_kernel<PML_TP_ID>, dim3(pml::ceil_div(items, wpb)), dim3(wpb * 32), 0, stream, h, Y, R, gather, rowptr, perm, out, N, C, nslab, mm);
   PML_CHECK_LAUNCH();
   return PML_OK;
 }
@@ -1180,7 +1186,7 @@ extern "C" int PML_CAT(pml_tp_bwd_launch_, PML_TP_ID)(const float* h, const floa
   const int grid = pml::ceil_div(items, wpb);
 #define PML_TP_BWD_CASE(M, H_, Y_, R_)                                                                              \
   case M:                                                                                                           \
-    pml::tp_bwd_kernel<PML_TP_ID, H_, Y_, R_><<<grid, wpb * 32, 0, stream>>>(h, Y, R, g, gather, rowptr, perm, dh, dY, \
+    pml::launch_plain(pml::tp_bwd_kernel<PML_TP_ID, H_, Y_, R_>, dim3(grid), dim3(wpb * 32), 0, stream, h, Y, R, g, gather, rowptr, perm, dh, dY, \
                                                                             dR, N, C, nslab, mm);                   \
     break;
   switch (mask) {

@@ -290,3 +290,41 @@ def test_gate_plan_matches_oracle_gate_layout():
             y[:, st.g_out[i]:st.g_out[i] + m * d] = blk.reshape(5, m * d)
         assert (y - y_ref).abs().max() < 1e-6
         assert abs(SILU_2MOM - 1.6791767923989418) < 1e-12 and abs(TANH_2MOM - 1.5937334472592692) < 1e-12
+
+
+def test_every_pdl_launched_kernel_waits_for_its_predecessors():
+    """a kernel launched with the programmatic-dependent-launch attribute (pml::launch_pdl) may become resident while the
+    previous kernel of the stream still runs: it MUST start with pdl_enter() (griddepcontrol.wait) or it reads stale data"""
+    import glob
+    import os
+    import re
+
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "physicsml_b200", "csrc")
+    launched, guarded = set(), set()
+    for path in glob.glob(os.path.join(csrc, "*.cu")):
+        src = open(path).read()
+        for m in re.finditer(r"launch_pdl\(\s*(?:pml::)?(?:wide::)?([A-Za-z_0-9]+)", src):
+            launched.add(m.group(1))
+        for m in re.finditer(r"__global__", src):
+            # declaration text up to the body's '{' at parenthesis depth 0; the kernel's name is the last identifier that
+            # opens a parenthesis at depth 0 (attributes such as __launch_bounds__(...) come before it)
+            i, depth, name, j = m.end(), 0, None, -1
+            while i < len(src):
+                c = src[i]
+                if c == "(":
+                    if depth == 0:
+                        ident = re.search(r"([A-Za-z_0-9]+)\s*$", src[m.end():i])
+                        name = ident.group(1) if ident else name
+                    depth += 1
+                elif c == ")":
+                    depth -= 1
+                elif c == ";" and depth == 0:
+                    break
+                elif c == "{" and depth == 0:
+                    j = i
+                    break
+                i += 1
+            if j >= 0 and name and src[j + 1 : j + 80].lstrip().startswith("pdl_enter();"):
+                guarded.add(name)
+    assert launched, "no launch_pdl call sites found"
+    assert launched <= guarded, f"launched with the PDL attribute but without pdl_enter(): {sorted(launched - guarded)}"
