@@ -455,8 +455,16 @@ def main() -> None:
 
         sampler = ClockSampler(local) if (rank == 0 and headline) else None
         ms_dev, launches = timed(resident, steps, warmup)
+        if headline:
+            # nvidia-smi delivers its first line ~100 ms after it starts and the timed region is ~100 ms long: keep the
+            # SAME step running, untimed, for another 0.6 s so that the clock / throttle samples are taken under its load
+            # (every rank runs the same number of extra steps: the step holds a collective)
+            for _ in range(int(600.0 / max(ms_dev, 0.05)) + 1):
+                resident()
+            torch.cuda.synchronize()
         if sampler is not None:
             res["clocks"] = sampler.stop()
+            res["clocks"]["window"] = "timed steps + 0.6 s of the same step, untimed"
         # a replayed graph cannot carry per-kernel events: time the fused edge kernels in an eager pass of the SAME step
         # (same inputs, same kernels), and count the kernels of one step the same way
         # ... with the side stream off, so that every launch runs alone between its two events (in the timed step the radial
