@@ -19,7 +19,11 @@
 
 namespace pml {
 
-constexpr int TC_BM = 128, TC_THREADS = 256;  // the k-block BK (16 or 32) is a template parameter
+constexpr int TC_BM = 128;  // the k-block BK (16 or 32) is a template parameter
+// Threads per CTA.  The 32-wide k-block variant runs where a CTA has an SM to itself (grids of one wave) and takes 512
+// threads: half the units per thread, four warps per scheduler instead of two.  Measured (scripts/bench_small_gemm.py,
+// 1 304 x K x 128): K = 64 8.45 -> 8.16 us, K = 128 11.8 -> 11.3 us - a step still costs ~1.6 us per 32 k.
+template <int BK> __host__ __device__ constexpr int tc_threads() { return BK == 32 ? 512 : 256; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -105,7 +109,8 @@ __device__ __forceinline__ void tmem_add32(uint32_t taddr, float* v) {
 template <int ROWS, int BK>
 struct TileRegs {
   static constexpr int UNITS = ROWS * (BK / 4);
-  static constexpr int PER_THREAD = (UNITS + TC_THREADS - 1) / TC_THREADS;
+  static constexpr int NT = tc_threads<BK>();
+  static constexpr int PER_THREAD = (UNITS + NT - 1) / NT;
   float v[PER_THREAD][4];
 };
 
@@ -134,7 +139,8 @@ __device__ __forceinline__ void tile_coords(int idx, bool kfast, int& r, int& kc
 template <int ROWS, int BK>
 struct Lanes {
   static constexpr int UNITS = ROWS * (BK / 4);
-  static constexpr int PER_THREAD = (UNITS + TC_THREADS - 1) / TC_THREADS;
+  static constexpr int NT = tc_threads<BK>();
+  static constexpr int PER_THREAD = (UNITS + NT - 1) / NT;
   long long off[PER_THREAD];  // row * row_stride + 4 kc * k_stride (elements, from the chunk's base)
   int unit[PER_THREAD];       // float4 index inside the stage image; -1: this thread has no such unit
   unsigned ok;                // bit i: unit i exists and its row is inside the matrix
@@ -145,10 +151,10 @@ __device__ __forceinline__ void setup_lanes(bool kfast, int row0, int nrows, lon
   L.ok = 0u;
 #pragma unroll
   for (int it = 0; it < Lanes<ROWS, BK>::PER_THREAD; ++it) {
-    const int idx = threadIdx.x + it * TC_THREADS;
+    const int idx = threadIdx.x + it * Lanes<ROWS, BK>::NT;
     L.unit[it] = -1;
     L.off[it] = 0;
-    if (Lanes<ROWS, BK>::UNITS % TC_THREADS != 0 && idx >= Lanes<ROWS, BK>::UNITS) continue;
+    if (Lanes<ROWS, BK>::UNITS % Lanes<ROWS, BK>::NT != 0 && idx >= Lanes<ROWS, BK>::UNITS) continue;
     int r, kc;
     tile_coords<ROWS, BK>(idx, kfast, r, kc);
     L.unit[it] = (r & 7) + 8 * kc + 2 * BK * (r >> 3);
@@ -192,7 +198,7 @@ __device__ __forceinline__ void commit_tile(const TileRegs<ROWS, BK>& t, const L
   const bool scaled = scale != 1.f;  // uniform
 #pragma unroll
   for (int it = 0; it < Lanes<ROWS, BK>::PER_THREAD; ++it) {
-    if (Lanes<ROWS, BK>::UNITS % TC_THREADS != 0 && L.unit[it] < 0) continue;
+    if (Lanes<ROWS, BK>::UNITS % Lanes<ROWS, BK>::NT != 0 && L.unit[it] < 0) continue;
     float x0 = t.v[it][0], x1 = t.v[it][1], x2 = t.v[it][2], x3 = t.v[it][3];
     if (scaled) x0 *= scale, x1 *= scale, x2 *= scale, x3 *= scale;
     float4 hi, lo;
@@ -249,12 +255,13 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
 // SM - the node-level problems of a molecule batch - run BK = 32: half the steps.  Grids that fill the GPU keep BK = 16:
 // 48 KB of shared memory and 80 registers let three CTAs share an SM and overlap each other's steps.
 template <int BN, bool PROMOTE, int BK>
-__global__ void __launch_bounds__(TC_THREADS, (BK == 16 && !PROMOTE && BN <= 64) ? 3 : ((BK == 16 || (!PROMOTE && BN <= 64)) ? 2 : 1))
+__global__ void __launch_bounds__(tc_threads<BK>(), (BK == 16 && !PROMOTE && BN <= 64) ? 3 : (BK == 16 ? 2 : 1))
 gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                      float* __restrict__ C,
                                                                      const pml_gemm_problem* __restrict__ probs,
                                                                      int M_runtime, int splitk) {
   pdl_enter();  // before anything is read: the problem table itself may have been written by the previous kernel
+  constexpr int NT = tc_threads<BK>();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kPromoBlocks = kPromoK / BK;
   TcSmem<BN, BK>& S = *reinterpret_cast<TcSmem<BN, BK>*>(smem_raw);
@@ -268,7 +275,7 @@ gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
     static_assert(sizeof(pml_gemm_problem) % 4 == 0, "descriptor is copied word by word");
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&Pg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&S.prob);
-    for (int i = tid; i < (int)(sizeof(pml_gemm_problem) / 4); i += TC_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < (int)(sizeof(pml_gemm_problem) / 4); i += NT) dst[i] = __ldg(src + i);
   }
   __syncthreads();
   const pml_gemm_problem& P = S.prob;
@@ -345,7 +352,8 @@ gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
   };
 
   // this thread's slice of the output tile: TMEM lane quadrant q (rows 32q + lane), column half `half`
-  constexpr int NHALF = BN >= 64 ? 2 : 1;
+  // warp w reads TMEM lane quadrant w % 4 (hardware rule); the warps of a quadrant split the columns between them
+  constexpr int NHALF = (NT / 128) < (BN / 32) ? (NT / 128) : (BN / 32);
   constexpr int COLS_PER_WARP = BN / NHALF;
   const int q = warp & 3, half = warp >> 2;
   float acc[PROMOTE ? COLS_PER_WARP : 1];
@@ -477,7 +485,7 @@ gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
       constexpr int VPR = BN / 4;              // 16-byte vectors per row
       constexpr int RPI = 32 / VPR > 0 ? 32 / VPR : 1;  // rows per warp instruction (BN = 128: 1, 64: 2, 32: 4)
       const int vr = lane / VPR, vc = lane % VPR;
-      for (int rr = warp * RPI + vr; rr < TC_BM; rr += (TC_THREADS / 32) * RPI) {
+      for (int rr = warp * RPI + vr; rr < TC_BM; rr += (NT / 32) * RPI) {
         const int gr = row0 + rr, gc = col0 + vc * 4;
         if (gr < M && gc < N) {
           float4 o = *reinterpret_cast<const float4*>(stg + rr * SP + vc * 4);
@@ -512,7 +520,7 @@ gemm_grouped_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
           for (int j = 0; j < 32; ++j) stg[(q * 32 + lane) * PITCH + half * 32 + j] = v[j];
         }
         __syncthreads();
-        for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+        for (int rr = warp; rr < TC_BM; rr += NT / 32) {
           const int gr = row0 + rr;
           if (gr >= M) break;
 #pragma unroll
@@ -549,7 +557,7 @@ static int launch_tc_bk(const float* A, const float* B, float* C, const pml_gemm
       return PML_ERR_LAUNCH;
     configured[slot] = true;
   }
-  launch_pdl(gemm_grouped_tc_kernel<BN, PROMOTE, BK>, grid, dim3(TC_THREADS), smem, stream, A, B, C, probs, M_runtime, splitk);
+  launch_pdl(gemm_grouped_tc_kernel<BN, PROMOTE, BK>, grid, dim3(tc_threads<BK>()), smem, stream, A, B, C, probs, M_runtime, splitk);
   return PML_OK;
 }
 
@@ -567,9 +575,8 @@ static int launch_tc(const float* A, const float* B, float* C, const pml_gemm_pr
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms[slot], cudaDevAttrMultiProcessorCount, dev);
   }
-  // BK = 32 holds 64 (BN + 128) bytes x 16 of shared memory per CTA (128 KB at BN = 128): used where the whole grid fits in
-  // one wave of one (BN = 128) or two CTAs per SM
-  if ((long long)grid.x * grid.y * grid.z <= ((BN >= 128 || PROMOTE) ? 1ll : 2ll) * sms[slot])
+  // BK = 32 runs 512 threads at up to 126 registers: one CTA per SM - used where the whole grid fits in one such wave
+  if ((long long)grid.x * grid.y * grid.z <= (long long)sms[slot])
     return launch_tc_bk<BN, PROMOTE, 32>(A, B, C, probs, nprobs, M_runtime, grid, splitk, stream);
   return launch_tc_bk<BN, PROMOTE, 16>(A, B, C, probs, nprobs, M_runtime, grid, splitk, stream);
 }
