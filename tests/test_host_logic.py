@@ -211,6 +211,73 @@ def test_linear_plan_component_major_tables_address_the_same_elements():
     assert np.abs(dwe).max() > 0 and np.allclose(dwe, dwc, rtol=0, atol=1e-12)
 
 
+def test_element_linear_segment_tables_equal_the_dense_definition():
+    """ElementLinearPlan's template problems, placed on the element groups the way pml_segment_problems does it
+    (M / kc = group size, offsets + group start x row stride) and executed in numpy on the gathered component-major copies,
+    equal out[n, w, m] = alpha sum_u W[u, z_n, w] x[n, u, m], its dx and its dW - incl. an element that does not occur"""
+    import copy
+
+    from physicsml_b200 import so3
+    from physicsml_b200.plans import ElementLinearPlan
+
+    rng = np.random.default_rng(3)
+    irr_in, irr_out, Z, n = "4x0e+4x1o+4x1e", "4x0e+4x1e+4x1o+4x2e", 4, 23
+    pl = ElementLinearPlan(irr_in, Z, irr_out)
+    z = rng.integers(0, Z, n)
+    z[z == 2] = 0  # element 2 is absent: an empty group
+    order = np.argsort(z, kind="stable")
+    seg = np.concatenate([[0], np.cumsum(np.bincount(z, minlength=Z))])
+    x = rng.standard_normal((n, pl.d_in))
+    g = rng.standard_normal((n, pl.d_out))
+    w = rng.standard_normal(pl.weight_numel)
+
+    def place(tmpl, meta):
+        out = []
+        for q0, m in zip(tmpl, meta):
+            q = copy.copy(q0)
+            start, count = int(seg[m.v]), int(seg[m.v + 1] - seg[m.v])
+            q.a_off[0] += start * m.a_mult
+            q.b_off[0] += start * m.b_mult
+            q.c_off += start * m.c_mult
+            if m.mode == 0:
+                q.M = count
+            else:
+                q.kc[0] = count
+            out.append(q)
+        return out
+
+    N = pl.seg_nprob
+    fwd, bx, bw = (place(pl._seg_tmpl[k * N:(k + 1) * N], pl._seg_meta[k * N:(k + 1) * N]) for k in range(3))
+    xs, gs = x[order][:, pl._cm_in], g[order][:, pl._cm_out]  # rows grouped by element, blocks component-major
+    # dense definition
+    want, want_dx, want_dw = np.zeros((n, pl.d_out)), np.zeros((n, pl.d_in)), np.zeros(pl.weight_numel)
+    in_off, out_off = so3.irreps_offsets(pl.irreps_in), so3.irreps_offsets(pl.irreps_out)
+    P = pl.c_plan
+    for k in range(P.npaths):
+        d, mi, mo = P.d[k], P.mul_in[k], P.mul_out[k]
+        W = w[P.w_off[k]:P.w_off[k] + mi * Z * mo].reshape(mi, Z, mo)
+        dW = want_dw[P.w_off[k]:P.w_off[k] + mi * Z * mo].reshape(mi, Z, mo)
+        for b in range(n):
+            xb = x[b, P.x_off[k]:P.x_off[k] + mi * d].reshape(mi, d)
+            gb = g[b, P.o_off[k]:P.o_off[k] + mo * d].reshape(mo, d)
+            want[b, P.o_off[k]:P.o_off[k] + mo * d] += (P.alpha[k] * np.einsum("uw,um->wm", W[:, z[b]], xb)).ravel()
+            want_dx[b, P.x_off[k]:P.x_off[k] + mi * d] += (P.alpha[k] * np.einsum("uw,wm->um", W[:, z[b]], gb)).ravel()
+            dW[:, z[b]] += P.alpha[k] * np.einsum("um,wm->uw", xb, gb)
+    ys = np.zeros(n * pl.d_out_c)
+    _run_gemm_table(fwd, xs.ravel(), w, ys, n)
+    out = np.zeros((n, pl.d_out))
+    out[np.ix_(order, pl._cm_out)] = ys.reshape(n, pl.d_out_c)
+    assert np.abs(want).max() > 0 and np.allclose(out, want, rtol=0, atol=1e-12)
+    dxs = np.zeros(n * pl.d_in_c)
+    _run_gemm_table(bx, gs.ravel(), w, dxs, n)
+    dx = np.zeros((n, pl.d_in))
+    dx[np.ix_(order, pl._cm_in)] = dxs.reshape(n, pl.d_in_c)
+    assert np.allclose(dx, want_dx, rtol=0, atol=1e-12)
+    dw = np.zeros(pl.weight_numel)
+    _run_gemm_table(bw, xs.ravel(), gs.ravel(), dw, n)
+    assert np.abs(want_dw).max() > 0 and np.allclose(dw, want_dw, rtol=0, atol=1e-12)
+
+
 def test_gemm_scheduling_helpers_and_grad_pruning_flag():
     """host-side scheduling of the grouped GEMM (whole waves, no nearly empty extra wave) and the context manager that
     switches weight gradients off for the force pass"""
