@@ -47,7 +47,8 @@ def shared_config(world: int = 1) -> dict:
             "step": "training: fwd + forces(create_graph) + MSE(E)+MSE(F) + bwd + allreduce + Adam(amsgrad)",
             "molecules_per_gpu": wl.CONFIGS[WORKLOAD]["n_mol"], "atoms_per_gpu": int(data["coordinates"].shape[0]),
             "edges_per_gpu": int(data["edge_index"].shape[1]),
-            "per_rank_batches": "same molecule sizes on every rank (fixed work per GPU), different coordinates and species"}
+            "per_rank_batches": "same molecule sizes on every rank (fixed work per GPU), different coordinates and species",
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB memset outside the per-step CUDA-event pair)"}
 
 
 class ClockSampler:
