@@ -346,6 +346,7 @@ class MACE(torch.nn.Module):
         self._el_plans = None
 
     def forward(self, data: dict) -> dict:
+        ops.reset_pending()
         pos = data["coordinates"]
         edge_index = data["edge_index"]
         attrs = data["node_attrs"]

@@ -192,6 +192,7 @@ class Nequip(torch.nn.Module):
         self._el_plans = None
 
     def forward(self, data: dict) -> dict:
+        ops.reset_pending()
         pos = data["coordinates"]
         cell = shift = None
         if "cell" in data:

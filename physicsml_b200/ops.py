@@ -414,6 +414,13 @@ FUSE_DR = [os.environ.get("PML_FUSE_DR", "1") == "1"]
 _PENDING_DR: dict = {}
 
 
+def reset_pending() -> None:
+    """drop anything a backward pass that died half-way (an exception inside a formula) left parked; called by the models at
+    the start of every forward, which never runs inside a backward pass"""
+    if _PENDING_DR:
+        _PENDING_DR.clear()
+
+
 def _pending_dr_check() -> None:
     """end of a backward pass.  A contribution that is still parked belongs to a tensor product whose forward node the engine
     did not execute - which, given the graph edge through `anchor`, only happens when the pass was restricted
