@@ -594,7 +594,12 @@ extern "C" int pml_gemm_grouped_tc(const float* A, const float* B, float* C, con
   // With the cross terms in their own accumulator a plain reduction of 256 truncates the running sum 32 times - fewer than
   // the 48 of a 128-long reduction before that change - so up to 256 the faster plain kernels run (BN up to 128, three /
   // two CTAs per SM); beyond, the promoting variant.
-  const bool promote = max_k <= 0 || max_k > pml::kPlainMaxK;
+  static int plain_max_k = 0;  // PML_GEMM_PLAIN_MAX_K in the environment overrides the limit (accuracy / speed A/B runs)
+  if (plain_max_k == 0) {
+    const char* e = getenv("PML_GEMM_PLAIN_MAX_K");
+    plain_max_k = (e && atoi(e) > 0) ? atoi(e) : pml::kPlainMaxK;
+  }
+  const bool promote = max_k <= 0 || max_k > plain_max_k;
   int rc;
   if (promote) {
     if (max_N <= 32) rc = pml::launch_tc<32, true>(A, B, C, probs, nprobs, M_runtime, max_M, max_N, max_batch, splitk, stream);
