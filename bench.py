@@ -191,6 +191,12 @@ def gpu_eager_step_rate(dev, steps: int = 5, warmup: int = 2) -> dict:
             "steps": steps}
 
 
+def CONFIG_MOLECULES() -> int:
+    from physicsml_b200 import workloads as wl
+
+    return int(wl.CONFIGS[WORKLOAD]["n_mol"])
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -199,6 +205,13 @@ def run_reference(args) -> None:
     # scaling run (N > 1) the reference arm is still one CPU process on rank 0: there it runs a bounded 4-molecule sample
     # of the same workload so that four more runs of K + W steps stay within minutes (cpu_baseline.sample says which)
     n_mol = args.ref_molecules if args.ref_molecules > 0 else (None if args.gpus <= 1 else PARITY_MOLECULES)
+    if n_mol is None:
+        # the whole K + W run has to end within a few minutes: one full-batch step of the reference costs ~19 s on 16 host
+        # cores (0.6 s per molecule, measured), so the full batch is run when K + W <= 12 steps fit the budget and the
+        # largest prefix of the batch that does otherwise (cpu_baseline.sample says which; atoms/s barely depends on it)
+        total = CONFIG_MOLECULES()
+        fit = int(args.ref_budget_s / (max(1, args.steps) + max(1, args.warmup)) / 0.6)
+        n_mol = None if fit >= total else max(PARITY_MOLECULES, fit)
     rate, cores, sample, ms, kind = cpu_reference_step_rate(n_mol, max(1, args.steps), max(1, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "atoms/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -242,6 +255,8 @@ def main() -> None:
     ap.add_argument("--ref-molecules", type=int, default=0,
                     help="molecules of the batch the --impl reference arm runs (0 = the full 32-molecule batch at --gpus 1, a "
                          "4-molecule sample in the scaling runs)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="wall-clock budget of the --impl reference run at --gpus 1: the sample of the batch is sized to it")
     ap.add_argument("--cpu-baseline-molecules", type=int, default=PARITY_MOLECULES,
                     help="bounded sample of the cpu_baseline leg inside the GPU arm's run")
     ap.add_argument("--configs", default="all", help="'all', 'headline' or a comma-separated list of other_configs to run")
