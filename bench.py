@@ -191,7 +191,7 @@ def gpu_eager_step_rate(dev, steps: int = 5, warmup: int = 2) -> dict:
             "steps": steps}
 
 
-def CONFIG_MOLECULES() -> int:
+def _config_molecules() -> int:
     from physicsml_b200 import workloads as wl
 
     return int(wl.CONFIGS[WORKLOAD]["n_mol"])
@@ -209,7 +209,7 @@ def run_reference(args) -> None:
         # the whole K + W run has to end within a few minutes: one full-batch step of the reference costs ~19 s on 16 host
         # cores (0.6 s per molecule, measured), so the full batch is run when K + W <= 12 steps fit the budget and the
         # largest prefix of the batch that does otherwise (cpu_baseline.sample says which; atoms/s barely depends on it)
-        total = CONFIG_MOLECULES()
+        total = _config_molecules()
         fit = int(args.ref_budget_s / (max(1, args.steps) + max(1, args.warmup)) / 0.6)
         n_mol = None if fit >= total else max(PARITY_MOLECULES, fit)
     rate, cores, sample, ms, kind = cpu_reference_step_rate(n_mol, max(1, args.steps), max(1, args.warmup))
